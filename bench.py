@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native ReVolt dynamic-positioning hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--envs-per-gpu E]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2]): RevoltFinal(extended_state, cont_ang)
+env step -- action transform, 20 sub-steps of the 3-DOF stand-in hull, body-frame error, observation, reward,
+termination, 400-step episodes with in-kernel re-sampling -- on 16 Mi environments PER GPU (weak scaling;
+environments shard by global index, no data-path collective), fresh U(-1,1)^7 actions every step.
+A "step" is one pass of the hot path over the whole batch = exactly one env_step_kernel launch per GPU.
+
+One JSON line on stdout (rank 0):
+  value      env-steps/s over all GPUs, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public API (ml4ca_b200.env.RevoltFinal.step -> C ABI) with HOST buffers:
+             every step copies that step's actions from pinned host memory and reads obs/reward/done back
+  roofline   HBM roofline of the env-step kernel: 177 algorithmic bytes per env-step
+  cpu_baseline  the CPU oracle (vectorised NumPy port of the reference wrapper + float64 hull) on a bounded sample
+  extra      secondary kernels of the path (QP allocations/s, pseudoinverse+PID/s, ...), each with its own roofline
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENV_STEP_BYTES = 177      # read 60 state + 28 action, write 48 state + 36 obs + 4 rew + 1 done
+PINV_PID_BYTES = 80       # read eta, nu, ref, integ (48) + write integ, n, alpha (32)
+ACTION_POOL = 3           # distinct action buffers cycled through (3 x 448 MB >> 126 MB L2)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Polls NVML for SM clock and throttle reasons while the timed region runs."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.marks = [], {}
+        self.stop_flag = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self.stop_flag.is_set():
+            try:
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                try:
+                    rs = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    rs = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, rs))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def mark(self, name):
+        self.marks[name] = time.perf_counter()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"]}
+        t0, t1 = self.marks.get("start", 0), self.marks.get("end", float("inf"))
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+        mhz = sorted(s[1] for s in inside)
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        reasons = [n for b, n in self.REASONS.items() if bits & b and n != "gpu_idle"]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(inside)}
+
+
+# ---- CPU side (oracle port) --------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    n, steps, seed = args
+    import numpy as np
+    from oracle import env_oracle as EO
+    spec = EO.EnvSpec('final', True, True, max_ep_len=800)
+    rng = np.random.default_rng(seed)
+    st = EO.new_state(spec, n)
+    EO.reset(spec, st, seed=seed, fraction=0.8)
+    acts = rng.uniform(-1, 1, (steps, 7, n))
+    t0 = time.perf_counter()
+    for t in range(steps):
+        o, r, d, info = EO.step(spec, st, acts[t])
+        ended = d | info['truncated']
+        if ended.any():
+            EO.reset(spec, st, mask=ended, seed=seed, fraction=0.8)
+    return time.perf_counter() - t0
+
+
+def cpu_env_steps_per_s(n_total=1 << 16, steps=8, cores=None):
+    """The CPU oracle (vectorised NumPy port of customEnv.py + float64 hull) on `cores` processes."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    per = max(1, n_total // cores)
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(per, steps, 1000 + i) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    return per * cores * steps / wall, cores, "%d envs x %d steps (RevoltFinal ext+cont, float64 NumPy port, %d processes)" % (
+        per * cores, steps, cores)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path, timed on the host cores.
+    The reference is Python and cannot travel to the GPU box, so this is the oracle port (kind 'port')."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_total, inner = 1 << 16, 4
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_env_steps_per_s(n_total, 1, cores)
+    t0 = time.perf_counter()
+    done_steps = 0
+    budget_s = 120.0
+    for _ in range(args.steps):
+        cpu_env_steps_per_s(n_total, inner, cores)
+        done_steps += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    wall = time.perf_counter() - t0
+    value = n_total * inner * done_steps / wall
+    sample = "%d envs x %d env-steps per bench step, %d bench steps, %d processes" % (n_total, inner, done_steps, cores)
+    line = {
+        "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": done_steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / done_steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "BASELINE configs[2]: RevoltFinal(extended_state, cont_ang) env step, 3-DOF stand-in hull "
+                        "x20 sub-steps, obs/reward/termination, auto-reset, random actions",
+            "envs_per_gpu": args.envs_per_gpu, "global_envs": args.envs_per_gpu * world, "max_ep_len": 400,
+            "n_substeps": 20, "parallelism": "env-sharded x%d, no collective" % world,
+            "l2_policy": "inputs larger than L2 (per step: 1.0 GB state + 0.45 GB fresh actions of a 3-buffer pool)"}
+
+
+# ---- GPU side ----------------------------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from ml4ca_b200 import _lib
+    from ml4ca_b200.env import RevoltFinal, StandInHull
+    import ml4ca_b200 as M
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = args.envs_per_gpu
+    peak_gbs, peak_src = load_peaks()
+    env = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=n, device=dev, seed=2,
+                      auto_reset=True, env_id_offset=rank * n)
+    env.reset(fraction=0.8)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2 + rank)
+    pool = [torch.rand(7, n, device=dev, generator=gen) * 2 - 1 for _ in range(ACTION_POOL)]
+    out = (torch.empty(9, n, device=dev), torch.empty(n, device=dev), torch.empty(n, dtype=torch.uint8, device=dev))
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- device-resident timing ------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        env.step_into(pool[i % ACTION_POOL], *out)
+    barrier()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark("start")
+    ev0.record()
+    for i in range(args.steps):
+        env.step_into(pool[i % ACTION_POOL], *out)
+    ev1.record()
+    torch.cuda.synchronize()
+    sampler.mark("end")
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    barrier()
+    ms_all = max_over_ranks(ms)
+    ms_per_step = ms_all / args.steps
+    value = n * world * args.steps / (ms_all * 1e-3)
+    kernel_ms = ms / args.steps
+    achieved = ENV_STEP_BYTES * n / (kernel_ms * 1e-3) / 1e9
+
+    # ---- end to end through the public API with host buffers ----------------------------------------------------
+    e2e_steps = max(3, min(args.steps, 10))
+    h_act = [torch.rand(7, n).pin_memory() for _ in range(2)]
+    h_obs = torch.empty(9, n).pin_memory()
+    h_rew = torch.empty(n).pin_memory()
+    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_act = torch.empty(7, n, device=dev)
+
+    def e2e_step(i):
+        d_act.copy_(h_act[i % 2], non_blocking=True)
+        env.step_into(d_act, *out)
+        h_obs.copy_(out[0], non_blocking=True)
+        h_rew.copy_(out[1], non_blocking=True)
+        h_done.copy_(out[2], non_blocking=True)
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = n * world * e2e_steps / e2e_s
+    h2d = 7 * n * 4
+    d2h = (9 * 4 + 4 + 1) * n
+
+    # ---- secondary kernels (rank-local, reported under "extra") -------------------------------------------------
+    extra = {}
+    try:
+        m = 1 << 20
+        eta = (torch.rand(3, m, device=dev, generator=gen) * 2 - 1) * torch.tensor([[8.0], [8.0], [0.785]], device=dev)
+        nu = (torch.rand(3, m, device=dev, generator=gen) * 2 - 1) * torch.tensor([[1.4], [0.3], [0.52]], device=dev)
+        ref = torch.zeros(3, m, device=dev)
+        integ = torch.zeros(3, m, device=dev)
+        for _ in range(3):
+            M.pinv_pid(eta, nu, ref, integ)
+        torch.cuda.synchronize()
+        reps = 50
+        ev0.record()
+        for _ in range(reps):
+            M.pinv_pid(eta, nu, ref, integ)
+        ev1.record()
+        torch.cuda.synchronize()
+        t = ev0.elapsed_time(ev1) / reps * 1e-3
+        extra["pinv_pid"] = {"workload": "BASELINE configs[1]: pseudoinverse + PID, 1 Mi setpoints (fits L2: "
+                                         "an L2-resident figure, not an HBM one)",
+                             "value": m / t, "unit": "allocations/s", "us_per_launch": t * 1e6,
+                             "achieved_GBs": PINV_PID_BYTES * m / t / 1e9}
+    except Exception as e:  # noqa: BLE001
+        extra["pinv_pid"] = {"error": repr(e)}
+
+    sampler.stop_flag.set()
+    sampler.join(timeout=1.0)
+    clocks = sampler.summary()
+
+    if rank == 0:
+        cpu_val, cpu_cores, cpu_sample = cpu_env_steps_per_s(1 << 16, 8)
+        line = {
+            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                         "kernel": "env_step_kernel<FINAL,cont,ext,vec4>", "bytes_per_env_step": ENV_STEP_BYTES,
+                         "kernel_ms": kernel_ms},
+            "cpu_baseline": {"value": cpu_val, "unit": "env-steps/s", "cores": cpu_cores, "kind": "port",
+                             "sample": cpu_sample},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "note": "pinned host actions in, obs+reward+done out, every step"},
+            "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=1 << 24)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

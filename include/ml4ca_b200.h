@@ -1,0 +1,121 @@
+/* ml4ca_b200.h -- C ABI of libml4ca_b200.so: the B200-native ReVolt dynamic-positioning hot path.
+ *
+ * The reference (simensov/ml4ca) is pure Python and has no FFI layer; the seams this ABI replaces are the
+ * Python call signatures listed per function below (paths relative to /root/reference).  INTEGRATION.md shows
+ * the ctypes stub a reference maintainer would add at each seam.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative ml4ca_status; nothing throws across the ABI;
+ *    ml4ca_last_error() gives the message of the last failure on the calling thread.
+ *  - all data pointers are DEVICE pointers owned by the caller (e.g. PyTorch allocations) unless the
+ *    parameter name ends in _host; the library owns only the opaque handles' struct-of-arrays state.
+ *  - batches are struct-of-arrays, row-major [component, n]: component c of env i lives at p[c * n + i].
+ *  - calls are asynchronous and ordered on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *    stream); no hidden synchronisation, no CPU fallback: without a CUDA device every compute entry fails.
+ *  - one handle per device; a handle is not thread-safe, different handles are independent.
+ */
+#ifndef ML4CA_B200_H_
+#define ML4CA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ML4CA_API __attribute__((visibility("default")))
+#else
+#define ML4CA_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  ML4CA_OK = 0,
+  ML4CA_ERR_INVALID = -1, /* bad argument (the reference raises AssertionError, customEnv.py:35,228,238) */
+  ML4CA_ERR_CUDA = -2,    /* CUDA runtime failure, message in ml4ca_last_error */
+  ML4CA_ERR_NO_DEVICE = -3,
+  ML4CA_ERR_UNSUPPORTED = -4
+} ml4ca_status;
+
+/* env kinds = the four reference env classes (customEnv.py:11,327,351,373) */
+enum { ML4CA_ENV_FULL = 0, ML4CA_ENV_SIMPLE = 1, ML4CA_ENV_LIMITED = 2, ML4CA_ENV_FINAL = 3 };
+
+/* done flags written by ml4ca_env_step */
+enum { ML4CA_DONE_TERMINAL = 1, /* Revolt.is_terminal, customEnv.py:207-213 */
+       ML4CA_DONE_TRUNCATED = 2 /* traj_len == max_ep_len, ppo.py:304 */ };
+
+typedef struct ml4ca_env_cfg {
+  int32_t kind;           /* ML4CA_ENV_* */
+  int32_t cont_ang;       /* RevoltFinal(cont_ang=True): 7 network actions, sin/cos azimuths (customEnv.py:227-235) */
+  int32_t extended_state; /* obs 9 (= 6 + previous thrust) instead of 6 (customEnv.py:201-205) */
+  int32_t n_substeps;     /* simulator sub-steps of sim_dt per env step (20, customEnv.py:79-81); 0 = null simulator */
+  int32_t max_ep_len;     /* 400 at 5 Hz (customEnv.py:83) */
+  int32_t auto_reset;     /* 0: reference semantics (caller resets).  1: an env whose done != 0 is re-sampled inside
+                             step and the returned obs is the first obs of its next episode */
+  int32_t reserved0, reserved1;
+  float ss_bounds[6];     /* termination bounds real_ss_bounds (customEnv.py:26,337,361,386) */
+  float sim_dt;           /* 0.01 s */
+  float step_dt;          /* dt used by the action-derivative penalty = 0.01 * 20 (customEnv.py:81,311,317) */
+  float reset_fraction;   /* fraction used by auto_reset (0.8, ppo.py:286,320) */
+  float reserved2;
+  uint64_t seed;          /* Philox key */
+  int64_t env_id_offset;  /* global id of local env 0: RNG streams do not depend on how envs shard over GPUs */
+} ml4ca_env_cfg;
+
+typedef struct ml4ca_env ml4ca_env;
+
+/* Reference defaults for one env class.  Replaces Revolt.__init__ / RevoltSimple / RevoltLimited / RevoltFinal
+ * (src/rl/windows_workspace/specific/customEnv.py:22-90,331-349,355-371,377-399). */
+ML4CA_API int ml4ca_env_cfg_default(int32_t kind, int32_t cont_ang, int32_t extended_state, ml4ca_env_cfg* out);
+/* dims implied by a cfg: network action dim (3/5/6/7) and obs dim (6/9) */
+ML4CA_API int ml4ca_env_dims(const ml4ca_env_cfg* cfg, int32_t* act_dim, int32_t* obs_dim);
+
+ML4CA_API int ml4ca_env_create(const ml4ca_env_cfg* cfg, int64_t n_env, int32_t device, ml4ca_env** out);
+ML4CA_API int ml4ca_env_destroy(ml4ca_env* env);
+
+/* Revolt.reset(fraction=...) in training mode (customEnv.py:135-194; samplers simtools.py:109-124).
+ * mask [n] (nullable = all): envs to reset.  obs [obs_dim, n]: written for the reset envs only. */
+ML4CA_API int ml4ca_env_reset(ml4ca_env* env, const uint8_t* mask, float fraction, float* obs, void* stream);
+/* Revolt.reset(**init) with explicit 'Hull.PosNED/PosAttitude/VelocityNu' (customEnv.py:141-161):
+ * eta [3, n] = N, E, yaw; nu [3, n] = u, v, r. */
+ML4CA_API int ml4ca_env_reset_to(ml4ca_env* env, const uint8_t* mask, const float* eta, const float* nu, float* obs,
+                       void* stream);
+/* ErrorFrame.update(ref=new_ref) (errorFrame.py:34-38; customEnv.py:131,155-156): ref [3, n]. */
+ML4CA_API int ml4ca_env_set_ref(ml4ca_env* env, const float* ref, void* stream);
+/* Revolt.step(action) (customEnv.py:92-133): action [act_dim, n] -> obs [obs_dim, n], rew [n], done [n] flags. */
+ML4CA_API int ml4ca_env_step(ml4ca_env* env, const float* action, float* obs, float* rew, uint8_t* done, void* stream);
+/* Copies of the SoA state (any pointer may be NULL): eta [3,n], nu [3,n], prev_thrust [3,n] (env order bow, port,
+ * star), angles [3,n] (current_angles, customEnv.py:71), ep_len [n].  Also EF.get_NED_pos (errorFrame.py:19). */
+ML4CA_API int ml4ca_env_get_state(ml4ca_env* env, float* eta, float* nu, float* prev_thrust, float* angles, int32_t* ep_len,
+                        void* stream);
+ML4CA_API int64_t ml4ca_env_size(const ml4ca_env* env);
+
+/* Stateless pieces of the wrapper, exposed for callers that own their own state (and for parity tests):
+ * ErrorFrame.transform (errorFrame.py:25-32): eta, ref [3, n] -> err [3, n] body-frame error. */
+ML4CA_API int ml4ca_error_frame(int64_t n, const float* eta, const float* ref, float* err, void* stream);
+/* handle_continuous_angles / wrap_stern_angles + scale_and_clip (customEnv.py:215-244; ROS twin
+ * src/rl/ROS/rl_allocator/src/rl_allocator.py:222-226,275-283): action [act_dim, n] -> act_env [k, n]
+ * (k = 3/5/6 real commands) and sat [k, n] (-1/0/+1 = clipped low / inside / clipped high). */
+ML4CA_API int ml4ca_scale_and_clip(const ml4ca_env_cfg* cfg, int64_t n, const float* action, float* act_env, int8_t* sat,
+                         void* stream);
+
+/* Pseudoinverse allocator + DP PID controller.  ABSENT from the reference (DNV GL's dp_controller package, only
+ * referenced at qp_allocator.py:6,83 and SupervisedTau.py:37); equations are this build's own, see DESIGN.md.
+ * eta, nu, ref [3, n]; integ [3, n] in/out integral state; tau [3, n] (nullable) saturated PID wrench;
+ * n_pct [3, n] thrust in percent, allocator order port, star, bow; alpha [2, n] stern azimuths. */
+ML4CA_API int ml4ca_pinv_pid(int64_t n, const float* eta, const float* nu, const float* ref, float* integ, float* tau,
+                   float* n_pct, float* alpha, void* stream);
+/* Allocation only: tau [3, n] -> n_pct [3, n], alpha [2, n]. */
+ML4CA_API int ml4ca_pinv_allocate(int64_t n, const float* tau, float* n_pct, float* alpha, void* stream);
+
+ML4CA_API const char* ml4ca_last_error(void);
+/* "ml4ca_b200 <version> sm_100a" */
+ML4CA_API const char* ml4ca_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches evidence) */
+ML4CA_API int64_t ml4ca_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ML4CA_B200_H_ */

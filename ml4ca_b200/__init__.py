@@ -1,0 +1,15 @@
+"""ml4ca_b200 -- B200-native (sm_100a) implementation of simensov/ml4ca's dynamic-positioning hot path.
+
+Host-side mirrors of the reference interfaces, all backed by hand-written CUDA kernels behind the
+C ABI of libml4ca_b200.so (include/ml4ca_b200.h):
+
+  env.Revolt / RevoltSimple / RevoltLimited / RevoltFinal, ErrorFrame   (specific/customEnv.py, errorFrame.py)
+  pinv.pinv_pid, pinv.pinv_allocate                                      (dp_controller, absent from the reference)
+
+The package never imports ``oracle`` and has no CPU fallback.
+"""
+from . import _lib  # noqa: F401
+from .env import ErrorFrame, Revolt, RevoltFinal, RevoltLimited, RevoltSimple  # noqa: F401
+from .pinv import pinv_allocate, pinv_pid  # noqa: F401
+
+__version__ = "0.1.0"

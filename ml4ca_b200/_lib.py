@@ -1,0 +1,95 @@
+"""ctypes binding of libml4ca_b200.so (the C ABI declared in include/ml4ca_b200.h).
+
+There is no CPU fallback: if the shared library is missing this module raises at import of the
+first symbol, and every compute entry fails with ML4CA_ERR_NO_DEVICE without a CUDA device.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libml4ca_b200.so")
+
+c_f32p = ctypes.c_void_p
+c_u8p = ctypes.c_void_p
+c_i32p = ctypes.c_void_p
+c_stream = ctypes.c_void_p
+
+
+class EnvCfg(ctypes.Structure):
+    """struct ml4ca_env_cfg"""
+    _fields_ = [
+        ("kind", ctypes.c_int32), ("cont_ang", ctypes.c_int32), ("extended_state", ctypes.c_int32),
+        ("n_substeps", ctypes.c_int32), ("max_ep_len", ctypes.c_int32), ("auto_reset", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32), ("reserved1", ctypes.c_int32),
+        ("ss_bounds", ctypes.c_float * 6), ("sim_dt", ctypes.c_float), ("step_dt", ctypes.c_float),
+        ("reset_fraction", ctypes.c_float), ("reserved2", ctypes.c_float),
+        ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_int64),
+    ]
+
+
+class Ml4caError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_SIGNATURES = {
+    "ml4ca_env_cfg_default": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(EnvCfg)]),
+    "ml4ca_env_dims": (ctypes.c_int, [ctypes.POINTER(EnvCfg), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    "ml4ca_env_create": (ctypes.c_int, [ctypes.POINTER(EnvCfg), ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
+    "ml4ca_env_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "ml4ca_env_reset": (ctypes.c_int, [ctypes.c_void_p, c_u8p, ctypes.c_float, c_f32p, c_stream]),
+    "ml4ca_env_reset_to": (ctypes.c_int, [ctypes.c_void_p, c_u8p, c_f32p, c_f32p, c_f32p, c_stream]),
+    "ml4ca_env_set_ref": (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_stream]),
+    "ml4ca_env_step": (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_u8p, c_stream]),
+    "ml4ca_env_get_state": (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_stream]),
+    "ml4ca_env_size": (ctypes.c_int64, [ctypes.c_void_p]),
+    "ml4ca_error_frame": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_stream]),
+    "ml4ca_scale_and_clip": (ctypes.c_int, [ctypes.POINTER(EnvCfg), ctypes.c_int64, c_f32p, c_f32p, ctypes.c_void_p, c_stream]),
+    "ml4ca_pinv_pid": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_stream]),
+    "ml4ca_pinv_allocate": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_stream]),
+    "ml4ca_last_error": (ctypes.c_char_p, []),
+    "ml4ca_version": (ctypes.c_char_p, []),
+    "ml4ca_launch_count": (ctypes.c_int64, []),
+}
+
+
+def lib():
+    """The loaded library (loads on first use; raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Ml4caError(
+                "libml4ca_b200.so is missing (%s). Build it with `python -m ml4ca_b200.build`; "
+                "there is no CPU fallback." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = lib().ml4ca_last_error().decode("utf-8", "replace")
+        raise Ml4caError("%s failed (status %d): %s" % (what or "ml4ca call", status, msg))
+
+
+def launch_count():
+    return int(lib().ml4ca_launch_count())
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

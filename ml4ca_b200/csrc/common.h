@@ -1,0 +1,43 @@
+// common.h -- error plumbing, launch accounting and small helpers shared by every translation unit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ml4ca_b200.h"
+
+namespace ml4ca {
+
+void set_error(const char* fmt, ...);
+void count_launch(int64_t n = 1);
+
+inline int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return ML4CA_OK;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return ML4CA_ERR_CUDA;
+}
+
+#define ML4CA_CUDA(call)                                        \
+  do {                                                          \
+    int _st = ::ml4ca::check_cuda((call), #call);               \
+    if (_st != ML4CA_OK) return _st;                            \
+  } while (0)
+
+#define ML4CA_REQUIRE(cond, msg)                                \
+  do {                                                          \
+    if (!(cond)) {                                              \
+      ::ml4ca::set_error("%s: %s", __func__, msg);              \
+      return ML4CA_ERR_INVALID;                                 \
+    }                                                           \
+  } while (0)
+
+inline int check_launch(const char* kernel) {
+  count_launch();
+  return check_cuda(cudaGetLastError(), kernel);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kNumSMs = 148;  // B200
+
+}  // namespace ml4ca

@@ -1,0 +1,266 @@
+// env_kernels.cuh -- K3: batched Revolt.reset / Revolt.step for millions of independent environments.
+//
+// Replaces /root/reference/src/rl/windows_workspace/specific/customEnv.py:92-133 (step) and :135-194 (reset):
+// action transform -> thruster commands -> 20 sub-steps of the stand-in 3-DOF hull (in place of the six py4j
+// round trips into the Cybersea JVM, customEnv.py:117-124) -> body-frame error -> observation, reward,
+// termination, episode-length cut, optional in-kernel re-sampling of finished envs.
+//
+// Data layout in HBM: struct-of-arrays fp32, one row per state component, row length n_env:
+//   eta[3] nu[3] ref[3] prev_thrust[3] angles[3]  +  int32 ep_len, episode
+// One thread owns VEC consecutive environments (VEC = 4 -> every row access is one 128-bit, fully coalesced
+// LDG/STG; a warp touches 512 contiguous bytes per row).  There is no reuse between environments, so nothing is
+// staged through shared memory here; the kernel streams 177 algorithmic bytes per env-step (RevoltFinal,
+// extended state, continuous angles: read 60 state + 28 action, write 48 state + 36 obs + 4 rew + 1 done).
+// Grid: enough 256-thread CTAs to cover n_env, rounded so that the last wave is full where possible.
+#pragma once
+#include <new>
+
+#include "common.h"
+#include "env_math.cuh"
+
+namespace ml4ca {
+
+struct EnvParams {
+  float* eta;          // [3, n]
+  float* nu;           // [3, n]
+  float* ref;          // [3, n]
+  float* prev_thrust;  // [3, n]
+  float* angles;       // [3, n] bow, port, star
+  int32_t* ep_len;     // [n]
+  int32_t* episode;    // [n]
+  int64_t n;
+  float bounds[6];
+  float reset_scale[6];
+  float sim_dt, step_dt;
+  int32_t n_sub, max_ep_len;
+  int32_t auto_reset, pad0;
+  uint64_t seed;
+  int64_t env_off;
+};
+
+}  // namespace ml4ca
+
+struct ml4ca_env {
+  ml4ca_env_cfg cfg;
+  int64_t n;
+  int32_t device;
+  void* slab;
+  ml4ca::EnvParams p;
+};
+
+namespace ml4ca {
+
+// ---- vector row access -----------------------------------------------------------------------------------------
+template <int VEC>
+__device__ __forceinline__ void ld_row(const float* __restrict__ row, int64_t i, float (&x)[VEC]) {
+  if constexpr (VEC == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(row + i);
+    x[0] = t.x, x[1] = t.y, x[2] = t.z, x[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(row + i);
+    x[0] = t.x, x[1] = t.y;
+  } else {
+    x[0] = row[i];
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void ld_row_nc(const float* __restrict__ row, int64_t i, float (&x)[VEC]) {
+  if constexpr (VEC == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(row + i));
+    x[0] = t.x, x[1] = t.y, x[2] = t.z, x[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(row + i));
+    x[0] = t.x, x[1] = t.y;
+  } else {
+    x[0] = __ldg(row + i);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void st_row(float* __restrict__ row, int64_t i, const float (&x)[VEC]) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(row + i) = make_float4(x[0], x[1], x[2], x[3]);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<float2*>(row + i) = make_float2(x[0], x[1]);
+  } else {
+    row[i] = x[0];
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void ld_irow(const int32_t* __restrict__ row, int64_t i, int32_t (&x)[VEC]) {
+  if constexpr (VEC == 4) {
+    const int4 t = *reinterpret_cast<const int4*>(row + i);
+    x[0] = t.x, x[1] = t.y, x[2] = t.z, x[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    const int2 t = *reinterpret_cast<const int2*>(row + i);
+    x[0] = t.x, x[1] = t.y;
+  } else {
+    x[0] = row[i];
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void st_irow(int32_t* __restrict__ row, int64_t i, const int32_t (&x)[VEC]) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<int4*>(row + i) = make_int4(x[0], x[1], x[2], x[3]);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<int2*>(row + i) = make_int2(x[0], x[1]);
+  } else {
+    row[i] = x[0];
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void st_flags(uint8_t* __restrict__ row, int64_t i, const uint32_t (&x)[VEC]) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<uint32_t*>(row + i) = x[0] | (x[1] << 8) | (x[2] << 16) | (x[3] << 24);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<uint16_t*>(row + i) = (uint16_t)(x[0] | (x[1] << 8));
+  } else {
+    row[i] = (uint8_t)x[0];
+  }
+}
+
+// ---- K3 ------------------------------------------------------------------------------------------------------------
+template <int KIND, bool CONT, bool EXT, int VEC>
+__global__ void __launch_bounds__(256) env_step_kernel(const EnvParams p, const float* __restrict__ action,
+                                                       float* __restrict__ obs, float* __restrict__ rew,
+                                                       uint8_t* __restrict__ done) {
+  using T = EnvTraits<KIND, CONT>;
+  const int64_t n = p.n;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (i0 >= n) return;
+
+  // ---- loads: issue everything up front so that ~20 independent 128-bit requests are in flight per thread ----
+  float a[T::ACT][VEC];
+#pragma unroll
+  for (int c = 0; c < T::ACT; ++c) ld_row_nc<VEC>(action + (int64_t)c * n, i0, a[c]);
+  float eta[3][VEC], nu[3][VEC], ref[3][VEC], pth[3][VEC], ang[3][VEC];
+  int32_t ep[VEC];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    ld_row<VEC>(p.eta + (int64_t)c * n, i0, eta[c]);
+    ld_row<VEC>(p.nu + (int64_t)c * n, i0, nu[c]);
+    ld_row<VEC>(p.ref + (int64_t)c * n, i0, ref[c]);
+    if constexpr (EXT) ld_row<VEC>(p.prev_thrust + (int64_t)c * n, i0, pth[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const bool is_state = (T::NANG == 3) || (T::NANG == 2 && c > 0);
+    if (is_state) {
+      ld_row<VEC>(p.angles + (int64_t)c * n, i0, ang[c]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) ang[c][j] = (c == 0) ? T::DEF_BOW : (c == 1 ? T::DEF_PORT : T::DEF_STAR);
+    }
+  }
+  ld_irow<VEC>(p.ep_len, i0, ep);
+
+  float o[9][VEC], rw[VEC];
+  uint32_t flags[VEC];
+  bool any_reset = false;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    float act[T::ACT], cmd[T::NCMD];
+    int sat[T::NCMD];
+#pragma unroll
+    for (int c = 0; c < T::ACT; ++c) act[c] = a[c][j];
+    transform_action<KIND, CONT>(act, cmd, sat);                       // customEnv.py:104-110
+    const float pa_bow = ang[0][j], pa_port = ang[1][j], pa_star = ang[2][j];  // prev_angles, :102
+    apply_angle_commands<KIND, CONT>(cmd, ang[0][j], ang[1][j], ang[2][j]);    // :117-122
+    if (p.n_sub > 0) {                                                 // dTwin.step(n_steps), :124
+      float tx, ty, tn;
+      thruster_wrench(cmd[0], cmd[1], cmd[2], ang[0][j], ang[1][j], ang[2][j], tx, ty, tn);
+      integrate_hull(eta[0][j], eta[1][j], eta[2][j], nu[0][j], nu[1][j], nu[2][j], tx, ty, tn, p.n_sub, p.sim_dt);
+    }
+    float xb, yb, pb;                                                  // state_extended(), :125
+    error_frame(eta[0][j], eta[1][j], eta[2][j], ref[0][j], ref[1][j], ref[2][j], xb, yb, pb);
+    o[0][j] = xb, o[1][j] = yb, o[2][j] = pb;
+    o[3][j] = nu[0][j], o[4][j] = nu[1][j], o[5][j] = nu[2][j];
+    float old_scaled[3] = {0.f, 0.f, 0.f};
+    if constexpr (EXT) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[6 + c][j] = old_scaled[c] = __fdiv_rn(pth[c][j], 100.0f);
+    }
+    const float thrust[3] = {cmd[0], cmd[1], cmd[2]};                  // prev_thrust <- action[0:3], :126
+    rw[j] = reward_fn<EXT>(xb, yb, pb, nu[0][j], nu[1][j], nu[2][j], thrust, old_scaled, ang[0][j] - pa_bow,
+                           ang[1][j] - pa_port, ang[2][j] - pa_star, p.step_dt, T::ANG_BOUND);   // :128
+    const bool term = is_terminal(xb, yb, pb, nu[0][j], nu[1][j], nu[2][j], p.bounds);           // :129
+    ep[j] += 1;
+    const bool trunc = ep[j] >= p.max_ep_len;                          // ppo.py:304
+    flags[j] = (term ? ML4CA_DONE_TERMINAL : 0u) | (trunc ? ML4CA_DONE_TRUNCATED : 0u);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pth[c][j] = thrust[c];
+    any_reset |= (flags[j] != 0u);
+  }
+
+  {
+    if (p.auto_reset && any_reset) {  // rare (1 / episode length): keep the RNG and the extra row traffic off the common path
+      int32_t epi[VEC];
+      ld_irow<VEC>(p.episode, i0, epi);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        if (flags[j] == 0u) continue;
+        sample_reset(p.seed, p.env_off + i0 + j, epi[j], p.reset_scale, eta[0][j], eta[1][j], eta[2][j], nu[0][j],
+                     nu[1][j], nu[2][j]);
+        epi[j] += 1;
+        ep[j] = 0;
+        ang[0][j] = T::DEF_BOW, ang[1][j] = T::DEF_PORT, ang[2][j] = T::DEF_STAR;
+        pth[0][j] = pth[1][j] = pth[2][j] = 0.f;
+        error_frame(eta[0][j], eta[1][j], eta[2][j], ref[0][j], ref[1][j], ref[2][j], o[0][j], o[1][j], o[2][j]);
+        o[3][j] = nu[0][j], o[4][j] = nu[1][j], o[5][j] = nu[2][j];
+        if constexpr (EXT) o[6][j] = o[7][j] = o[8][j] = 0.f;
+      }
+      st_irow<VEC>(p.episode, i0, epi);
+    }
+  }
+
+  // ---- stores ---------------------------------------------------------------------------------------------------
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    st_row<VEC>(p.eta + (int64_t)c * n, i0, eta[c]);
+    st_row<VEC>(p.nu + (int64_t)c * n, i0, nu[c]);
+    st_row<VEC>(p.prev_thrust + (int64_t)c * n, i0, pth[c]);
+    const bool is_state = (T::NANG == 3) || (T::NANG == 2 && c > 0);
+    if (is_state) st_row<VEC>(p.angles + (int64_t)c * n, i0, ang[c]);
+  }
+  st_irow<VEC>(p.ep_len, i0, ep);
+#pragma unroll
+  for (int c = 0; c < (EXT ? 9 : 6); ++c) st_row<VEC>(obs + (int64_t)c * n, i0, o[c]);
+  st_row<VEC>(rew, i0, rw);
+  st_flags<VEC>(done, i0, flags);
+}
+
+// ---- reset ----------------------------------------------------------------------------------------------------------
+// mask nullable; explicit eta/nu (reset_to) or Philox sampling.  Writes obs for the reset envs only.
+template <int KIND, bool CONT, bool EXT>
+__global__ void __launch_bounds__(256) env_reset_kernel(const EnvParams p, const uint8_t* __restrict__ mask,
+                                                        const float* __restrict__ eta_in,
+                                                        const float* __restrict__ nu_in,
+                                                        float* __restrict__ obs) {
+  using T = EnvTraits<KIND, CONT>;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  if (mask != nullptr && mask[i] == 0) return;
+  const int64_t n = p.n;
+  float N, E, psi, u, v, r;
+  const int32_t epi = p.episode[i];
+  if (eta_in != nullptr) {
+    N = eta_in[i], E = eta_in[n + i], psi = eta_in[2 * n + i];
+    u = nu_in[i], v = nu_in[n + i], r = nu_in[2 * n + i];
+  } else {
+    sample_reset(p.seed, p.env_off + i, epi, p.reset_scale, N, E, psi, u, v, r);
+  }
+  p.episode[i] = epi + 1;
+  p.eta[i] = N, p.eta[n + i] = E, p.eta[2 * n + i] = psi;
+  p.nu[i] = u, p.nu[n + i] = v, p.nu[2 * n + i] = r;
+  p.prev_thrust[i] = 0.f, p.prev_thrust[n + i] = 0.f, p.prev_thrust[2 * n + i] = 0.f;  // customEnv.py:190
+  p.angles[i] = T::DEF_BOW, p.angles[n + i] = T::DEF_PORT, p.angles[2 * n + i] = T::DEF_STAR;  // :173-177,192
+  p.ep_len[i] = 0;
+  if (obs != nullptr) {
+    float xb, yb, pb;
+    error_frame(N, E, psi, p.ref[i], p.ref[n + i], p.ref[2 * n + i], xb, yb, pb);
+    obs[i] = xb, obs[n + i] = yb, obs[2 * n + i] = pb;
+    obs[3 * n + i] = u, obs[4 * n + i] = v, obs[5 * n + i] = r;
+    if constexpr (EXT) obs[6 * n + i] = 0.f, obs[7 * n + i] = 0.f, obs[8 * n + i] = 0.f;
+  }
+}
+
+}  // namespace ml4ca

@@ -1,0 +1,253 @@
+// env_math.cuh -- per-environment device arithmetic of the ReVolt gym wrapper and the stand-in hull.
+//
+// Everything here is a __device__ __forceinline__ function on scalars so that the stand-alone env-step kernel
+// (env_step.cu) and the fused policy+env rollout kernel (rollout.cu) share one implementation.
+// Reference: /root/reference/src/rl/windows_workspace/specific/customEnv.py (cited per function).
+//
+// Floating point contract (tests/test_env_parity.py):
+//  * integer / compare logic -- clip saturation decisions, termination flags, episode counters, the
+//    action -> thruster index map -- is bit-exact;
+//  * products/quotients that the reference evaluates with one operation (a*bound, prev_thrust/100) use the
+//    _rn intrinsics so that no FMA contraction changes the rounding: they equal the float32 oracle bit for bit;
+//  * transcendental pieces (atan2f, sincosf, expf, sqrtf chains) carry a stated tolerance against float64.
+#pragma once
+#include <stdint.h>
+
+#include "ml4ca_constants.h"
+#include "philox.cuh"
+
+namespace ml4ca {
+
+constexpr float kPi = (float)ML4CA_PI;
+
+// ---- static description of the four reference env classes ---------------------------------------------------
+// ACT  : network action dim           NCMD : real commands after the angle transform (customEnv.py:47-53)
+// NANG : azimuths that are per-env state (the others are constants of the class)
+template <int KIND, bool CONT>
+struct EnvTraits;
+template <bool CONT>
+struct EnvTraits<ML4CA_ENV_FULL, CONT> {  // customEnv.py:58-65
+  static constexpr int ACT = 6, NCMD = 6, NANG = 3;
+  static constexpr float ANG_BOUND = kPi;
+  static constexpr float DEF_BOW = 0.f, DEF_PORT = 0.f, DEF_STAR = 0.f;
+};
+template <bool CONT>
+struct EnvTraits<ML4CA_ENV_SIMPLE, CONT> {  // customEnv.py:331-349
+  static constexpr int ACT = 3, NCMD = 3, NANG = 0;
+  static constexpr float ANG_BOUND = kPi;  // unused
+  static constexpr float DEF_BOW = (float)(ML4CA_PI / 2), DEF_PORT = (float)(-3 * ML4CA_PI / 4),
+                         DEF_STAR = (float)(3 * ML4CA_PI / 4);
+};
+template <bool CONT>
+struct EnvTraits<ML4CA_ENV_LIMITED, CONT> {  // customEnv.py:355-371
+  static constexpr int ACT = 5, NCMD = 5, NANG = 2;
+  static constexpr float ANG_BOUND = (float)(ML4CA_PI / 2);
+  static constexpr float DEF_BOW = (float)(ML4CA_PI / 2), DEF_PORT = 0.f, DEF_STAR = 0.f;
+};
+template <bool CONT>
+struct EnvTraits<ML4CA_ENV_FINAL, CONT> {  // customEnv.py:377-399
+  static constexpr int ACT = CONT ? 7 : 5, NCMD = 5, NANG = 2;
+  static constexpr float ANG_BOUND = kPi;
+  static constexpr float DEF_BOW = (float)(ML4CA_PI / 2), DEF_PORT = 0.f, DEF_STAR = 0.f;
+};
+
+// ---- mathematics.py:14-17 ------------------------------------------------------------------------------------
+// wrap_angle(a, deg=False): mod(a + pi, 2 pi) - pi with Python's sign-of-divisor modulo.
+__device__ __forceinline__ float wrap_rad(float a) {
+  const float two_pi = __fmul_rn(2.0f, kPi);
+  const float x = __fadd_rn(a, kPi);
+  float m = fmodf(x, two_pi);
+  if (m < 0.f) m = __fadd_rn(m, two_pi);
+  return __fsub_rn(m, kPi);
+}
+// wrap_angle(a) with its default deg=True applied to RADIAN inputs (errorFrame.py:29,31): the identity for
+// -180 <= a < 180, where evaluating (a + 180) mod 360 - 180 literally in fp32 would only inject ~1e-5 noise.
+__device__ __forceinline__ float wrap_deg_quirk(float a) {
+  if (a >= -180.f && a < 180.f) return a;
+  const float x = __fadd_rn(a, 180.f);
+  float m = fmodf(x, 360.f);
+  if (m < 0.f) m = __fadd_rn(m, 360.f);
+  return __fsub_rn(m, 180.f);
+}
+
+// ---- customEnv.py:215-244 -------------------------------------------------------------------------------------
+// One command: scale by its bound, clip, report saturation (-1 / 0 / +1).
+__device__ __forceinline__ float scale_clip(float a, float bound, int& sat) {
+  const float s = __fmul_rn(a, bound);
+  sat = (s > bound) - (s < -bound);
+  return fminf(fmaxf(s, -bound), bound);
+}
+
+// Network action -> clipped real commands cmd[NCMD] (thrust % for bow, port, star, then azimuths).
+template <int KIND, bool CONT>
+__device__ __forceinline__ void transform_action(const float (&a)[EnvTraits<KIND, CONT>::ACT],
+                                                 float (&cmd)[EnvTraits<KIND, CONT>::NCMD],
+                                                 int (&sat)[EnvTraits<KIND, CONT>::NCMD]) {
+  using T = EnvTraits<KIND, CONT>;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) cmd[i] = scale_clip(a[i], (float)ML4CA_THRUST_BOUND, sat[i]);
+  if constexpr (KIND == ML4CA_ENV_FINAL) {
+    float ap, as;
+    if constexpr (CONT) {  // handle_continuous_angles :227-235
+      ap = __fdiv_rn(atan2f(a[3], a[4]), T::ANG_BOUND);
+      as = __fdiv_rn(atan2f(a[5], a[6]), T::ANG_BOUND);
+    } else {  // wrap_stern_angles :237-244
+      ap = __fdiv_rn(wrap_rad(__fmul_rn(a[3], T::ANG_BOUND)), T::ANG_BOUND);
+      as = __fdiv_rn(wrap_rad(__fmul_rn(a[4], T::ANG_BOUND)), T::ANG_BOUND);
+    }
+    cmd[3] = scale_clip(ap, T::ANG_BOUND, sat[3]);
+    cmd[4] = scale_clip(as, T::ANG_BOUND, sat[4]);
+  } else {
+#pragma unroll
+    for (int i = 3; i < T::NCMD; ++i) cmd[i] = scale_clip(a[i], T::ANG_BOUND, sat[i]);
+  }
+}
+
+// customEnv.py:117-122: write the azimuth commands into current_angles (env order bow, port, star).
+template <int KIND, bool CONT>
+__device__ __forceinline__ void apply_angle_commands(const float (&cmd)[EnvTraits<KIND, CONT>::NCMD], float& a_bow,
+                                                     float& a_port, float& a_star) {
+  if constexpr (KIND == ML4CA_ENV_FULL) {
+    a_bow = cmd[3];
+    a_port = cmd[4];
+    a_star = cmd[5];
+  } else if constexpr (KIND == ML4CA_ENV_LIMITED || KIND == ML4CA_ENV_FINAL) {
+    a_port = cmd[3];  // act_2_act_map {4:3, 5:4}, customEnv.py:364,392
+    a_star = cmd[4];
+  }
+}
+
+// ---- stand-in hull (DECLARED; see ml4ca_constants.h and oracle/vessel.py) ------------------------------------
+// tau = sum_i F_i [cos a_i, sin a_i, lx_i sin a_i - ly_i cos a_i], F_i = K_i n_i |n_i|; env order bow, port, star.
+__device__ __forceinline__ void thruster_wrench(float n_bow, float n_port, float n_star, float a_bow, float a_port,
+                                                float a_star, float& tx, float& ty, float& tn) {
+  const float fb = (float)ML4CA_K_BOW * n_bow * fabsf(n_bow);
+  const float fp = (float)ML4CA_K_STERN * n_port * fabsf(n_port);
+  const float fs = (float)ML4CA_K_STERN * n_star * fabsf(n_star);
+  float sb, cb, sp, cp, ss, cs;
+  sincosf(a_bow, &sb, &cb);
+  sincosf(a_port, &sp, &cp);
+  sincosf(a_star, &ss, &cs);
+  tx = fb * cb + fp * cp + fs * cs;
+  ty = fb * sb + fp * sp + fs * ss;
+  tn = fb * ((float)ML4CA_LX_BOW * sb - (float)ML4CA_LY_BOW * cb) +
+       fp * ((float)ML4CA_LX_PORT * sp - (float)ML4CA_LY_PORT * cp) +
+       fs * ((float)ML4CA_LX_STAR * ss - (float)ML4CA_LY_STAR * cs);
+}
+
+// n_sub semi-implicit Euler sub-steps of h seconds.  The heading rotation is advanced by the exact angle-sum
+// recurrence with a 3rd-order small-angle kernel (|h r| <= 1e-2: truncation < 1e-13), and the pose increments are
+// accumulated separately from the pose so that 20 small additions do not each round at the magnitude of N, E.
+__device__ __forceinline__ void integrate_hull(float& N, float& E, float& psi, float& u, float& v, float& r,
+                                               float tx, float ty, float tn, int n_sub, float h) {
+  const float hm1 = h / (float)ML4CA_M11, hm2 = h / (float)ML4CA_M22, hm3 = h / (float)ML4CA_M33;
+  const float ax = hm1 * tx, ay = hm2 * ty, an = hm3 * tn;
+  const float k_vr = hm1 * (float)ML4CA_M22, k_ur = hm2 * (float)ML4CA_M11,
+              k_uv = hm3 * (float)(ML4CA_M22 - ML4CA_M11);
+  const float xu = hm1 * (float)ML4CA_XU, xuu = hm1 * (float)ML4CA_XUU;
+  const float yv = hm2 * (float)ML4CA_YV, yvv = hm2 * (float)ML4CA_YVV;
+  const float nr = hm3 * (float)ML4CA_NR, nrr = hm3 * (float)ML4CA_NRR;
+  float s, c;
+  sincosf(psi, &s, &c);
+  float dN = 0.f, dE = 0.f, dpsi = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < n_sub; ++k) {
+    const float vr = v * r, ur = u * r, uv = u * v;
+    const float un = u + (ax + k_vr * vr - (xu + xuu * fabsf(u)) * u);
+    const float vn = v + (ay - k_ur * ur - (yv + yvv * fabsf(v)) * v);
+    const float rn = r + (an - k_uv * uv - (nr + nrr * fabsf(r)) * r);
+    u = un;
+    v = vn;
+    r = rn;
+    dN = fmaf(h, c * u - s * v, dN);
+    dE = fmaf(h, s * u + c * v, dE);
+    const float d = h * r;
+    dpsi += d;
+    const float d2 = d * d;
+    const float cd = fmaf(-0.5f, d2, 1.0f);
+    const float sd = fmaf(d * d2, -1.0f / 6.0f, d);
+    const float cn = c * cd - s * sd;
+    s = s * cd + c * sd;
+    c = cn;
+  }
+  N += dN;
+  E += dE;
+  psi += dpsi;
+}
+
+// ---- errorFrame.py:25-32 --------------------------------------------------------------------------------------
+__device__ __forceinline__ void error_frame(float N, float E, float psi, float rN, float rE, float rpsi, float& xb,
+                                            float& yb, float& psib) {
+  const float eN = __fsub_rn(N, rN), eE = __fsub_rn(E, rE), ep = __fsub_rn(psi, rpsi);
+  float s, c;
+  sincosf(wrap_deg_quirk(psi), &s, &c);
+  xb = c * eN + s * eE;  // R(psi)^T e
+  yb = c * eE - s * eN;
+  psib = wrap_deg_quirk(ep);
+}
+
+// ---- customEnv.py:253-325, coefficients of :263 -----------------------------------------------------------------
+// thrust[3] = this step's clipped thrust (the NEW prev_thrust, :126), old_scaled[3] = state_ext[-3:] (previous
+// thrust / 100), angle deltas = current_angles - prev_angles, env order bow, port, star.
+template <bool EXT>
+__device__ __forceinline__ float reward_fn(float xb, float yb, float psib, float u, float v, float r,
+                                           const float (&thrust)[3], const float (&old_scaled)[3], float da_bow,
+                                           float da_port, float da_star, float step_dt, float ang_bound) {
+  // vel_reward :267-273
+  const float vel = -sqrtf((u * u) * (float)ML4CA_REW_VEL_CU + (v * v) * (float)ML4CA_REW_VEL_CV +
+                           (r * r) * (float)ML4CA_REW_VEL_CR);
+  // multivariate_gaussian :275-290
+  const float d2 = xb * xb + yb * yb;
+  const float yaw = psib * 180.0f / kPi;
+  const float quad = d2 * (float)(1.0 / (ML4CA_REW_SIGMA_POS * ML4CA_REW_SIGMA_POS)) +
+                     (yaw * yaw) * (float)(1.0 / (ML4CA_REW_SIGMA_YAW * ML4CA_REW_SIGMA_YAW));
+  const float multivar = 2.0f * expf(-0.5f * quad);
+  const float yq = yaw * 0.25f;
+  const float special = sqrtf(d2 + yq * yq);
+  const float anti = fmaxf(-1.0f, 1.0f - 0.1f * special);
+  float rew = vel + (multivar + anti + 0.5f);
+  // thrust_penalty :292-302
+  rew -= fabsf(thrust[0]) / 100.0f * (float)ML4CA_REW_THRUST_C_BOW;
+  rew -= fabsf(thrust[1]) / 100.0f * (float)ML4CA_REW_THRUST_C_STERN;
+  rew -= fabsf(thrust[2]) / 100.0f * (float)ML4CA_REW_THRUST_C_STERN;
+  // action_derivative_penalty :304-325 (returns 0 without the extended state)
+  if constexpr (EXT) {
+    float pen = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float derr = (thrust[i] - old_scaled[i] * 100.0f) / step_dt;
+      pen -= fabsf(derr / 100.0f) * (float)ML4CA_REW_DTHRUST_C;
+    }
+    float angpen = -fabsf(da_bow / step_dt / ang_bound) * (float)ML4CA_REW_DANGLE_C_BOW;
+    angpen -= fabsf(da_port / step_dt / ang_bound) * (float)ML4CA_REW_DANGLE_C_STERN;
+    angpen -= fabsf(da_star / step_dt / ang_bound) * (float)ML4CA_REW_DANGLE_C_STERN;
+    rew += pen + fmaxf(-1.0f, angpen);
+  }
+  return rew;
+}
+
+// customEnv.py:207-213: any(|obs[i]| > bound[i]), i < 6, strict.
+__device__ __forceinline__ bool is_terminal(float xb, float yb, float psib, float u, float v, float r,
+                                            const float* __restrict__ b) {
+  return (fabsf(xb) > b[0]) | (fabsf(yb) > b[1]) | (fabsf(psib) > b[2]) | (fabsf(u) > b[3]) | (fabsf(v) > b[4]) |
+         (fabsf(r) > b[5]);
+}
+
+// customEnv.py:141-145 + simtools.py:109-124 on the Philox stream: pose ~ U(+-fraction*b[0:3]),
+// velocity ~ U(+-0.30*fraction*b[3:6]).  scale[6] is precomputed on the host in fp32 (see make_reset_scale).
+__device__ __forceinline__ void sample_reset(uint64_t seed, int64_t env_id, int32_t episode,
+                                             const float* __restrict__ scale, float& N, float& E, float& psi, float& u,
+                                             float& v, float& r) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ 0x5EED5EEDu;
+  const uint32_t lo = (uint32_t)((uint64_t)env_id), hi = (uint32_t)((uint64_t)env_id >> 32);
+  const Philox4 a = philox4x32_10(lo, hi, (uint32_t)episode, 0u, k0, k1);
+  const Philox4 b = philox4x32_10(lo, hi, (uint32_t)episode, 1u, k0, k1);
+  N = __fmul_rn(scale[0], symmetric_unit(a.x));
+  E = __fmul_rn(scale[1], symmetric_unit(a.y));
+  psi = __fmul_rn(scale[2], symmetric_unit(a.z));
+  u = __fmul_rn(scale[3], symmetric_unit(a.w));
+  v = __fmul_rn(scale[4], symmetric_unit(b.x));
+  r = __fmul_rn(scale[5], symmetric_unit(b.y));
+}
+
+}  // namespace ml4ca

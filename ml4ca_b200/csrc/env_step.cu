@@ -1,0 +1,281 @@
+// env_step.cu -- host side of K3: handle life cycle and the extern "C" entry points of the env.
+// Kernels: env_kernels.cuh; per-class instantiations: env_step_inst.cu.
+#include <new>
+
+#include "env_kernels.cuh"
+
+namespace ml4ca {
+
+__global__ void __launch_bounds__(256) error_frame_kernel(int64_t n, const float* __restrict__ eta,
+                                                          const float* __restrict__ ref, float* __restrict__ err) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float xb, yb, pb;
+  error_frame(eta[i], eta[n + i], eta[2 * n + i], ref[i], ref[n + i], ref[2 * n + i], xb, yb, pb);
+  err[i] = xb, err[n + i] = yb, err[2 * n + i] = pb;
+}
+
+template <int KIND, bool CONT>
+__global__ void __launch_bounds__(256) scale_clip_kernel(int64_t n, const float* __restrict__ action,
+                                                         float* __restrict__ act_env, int8_t* __restrict__ sat_out) {
+  using T = EnvTraits<KIND, CONT>;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a[T::ACT], cmd[T::NCMD];
+  int sat[T::NCMD];
+#pragma unroll
+  for (int c = 0; c < T::ACT; ++c) a[c] = action[(int64_t)c * n + i];
+  transform_action<KIND, CONT>(a, cmd, sat);
+#pragma unroll
+  for (int c = 0; c < T::NCMD; ++c) {
+    act_env[(int64_t)c * n + i] = cmd[c];
+    if (sat_out != nullptr) sat_out[(int64_t)c * n + i] = (int8_t)sat[c];
+  }
+}
+
+// ---- host-side dispatch -------------------------------------------------------------------------------------------
+static int validate_cfg(const ml4ca_env_cfg* c) {
+  ML4CA_REQUIRE(c != nullptr, "cfg is NULL");
+  ML4CA_REQUIRE(c->kind >= ML4CA_ENV_FULL && c->kind <= ML4CA_ENV_FINAL, "unknown env kind");
+  ML4CA_REQUIRE(!(c->cont_ang && c->kind != ML4CA_ENV_FINAL),
+                "continuous angles only work with the final environment (customEnv.py:228)");
+  ML4CA_REQUIRE(!(c->kind == ML4CA_ENV_SIMPLE && c->extended_state),
+                "RevoltSimple has no azimuth bound for the extended-state penalty (customEnv.py:319,339)");
+  ML4CA_REQUIRE(c->n_substeps >= 0 && c->max_ep_len > 0, "n_substeps >= 0 and max_ep_len > 0 required");
+  return ML4CA_OK;
+}
+
+static void make_reset_scale(const ml4ca_env_cfg& c, float fraction, float (&scale)[6]) {
+  // fp32, one rounding per product, same order as oracle/env_oracle.py::sample_reset
+  const float vfr = (float)ML4CA_VEL_FRACTION * fraction;
+  for (int i = 0; i < 3; ++i) scale[i] = c.ss_bounds[i] * fraction;
+  for (int i = 3; i < 6; ++i) scale[i] = c.ss_bounds[i] * vfr;
+}
+
+#define ML4CA_DECL_UNIT(name)                                                                                   \
+  int launch_step_##name(const ml4ca_env*, const float*, float*, float*, uint8_t*, cudaStream_t);                \
+  int launch_reset_##name(const ml4ca_env*, const EnvParams&, const uint8_t*, const float*, const float*, float*, \
+                          cudaStream_t);
+ML4CA_DECL_UNIT(full)
+ML4CA_DECL_UNIT(simple)
+ML4CA_DECL_UNIT(limited)
+ML4CA_DECL_UNIT(final_wrap)
+ML4CA_DECL_UNIT(final_cont)
+#undef ML4CA_DECL_UNIT
+
+static int launch_step(const ml4ca_env* e, const float* action, float* obs, float* rew, uint8_t* done,
+                       cudaStream_t st) {
+  switch (e->cfg.kind) {
+    case ML4CA_ENV_FULL: return launch_step_full(e, action, obs, rew, done, st);
+    case ML4CA_ENV_SIMPLE: return launch_step_simple(e, action, obs, rew, done, st);
+    case ML4CA_ENV_LIMITED: return launch_step_limited(e, action, obs, rew, done, st);
+    default:
+      return e->cfg.cont_ang ? launch_step_final_cont(e, action, obs, rew, done, st)
+                             : launch_step_final_wrap(e, action, obs, rew, done, st);
+  }
+}
+
+static int launch_reset(const ml4ca_env* e, const EnvParams& p, const uint8_t* mask, const float* eta,
+                        const float* nu, float* obs, cudaStream_t st) {
+  switch (e->cfg.kind) {
+    case ML4CA_ENV_FULL: return launch_reset_full(e, p, mask, eta, nu, obs, st);
+    case ML4CA_ENV_SIMPLE: return launch_reset_simple(e, p, mask, eta, nu, obs, st);
+    case ML4CA_ENV_LIMITED: return launch_reset_limited(e, p, mask, eta, nu, obs, st);
+    default:
+      return e->cfg.cont_ang ? launch_reset_final_cont(e, p, mask, eta, nu, obs, st)
+                             : launch_reset_final_wrap(e, p, mask, eta, nu, obs, st);
+  }
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace ml4ca
+
+using namespace ml4ca;
+
+extern "C" {
+
+int ml4ca_env_cfg_default(int32_t kind, int32_t cont_ang, int32_t extended_state, ml4ca_env_cfg* out) {
+  ML4CA_REQUIRE(out != nullptr, "out is NULL");
+  ml4ca_env_cfg c = {};
+  c.kind = kind;
+  c.cont_ang = cont_ang ? 1 : 0;
+  c.extended_state = extended_state ? 1 : 0;
+  c.n_substeps = ML4CA_N_SUBSTEPS;
+  c.max_ep_len = ML4CA_MAX_EP_LEN;  // int(800 * 10 / 20), customEnv.py:83
+  c.auto_reset = 0;
+  const float b_full[6] = {8.0f, 8.0f, (float)(ML4CA_PI / 2), 1.4f, 0.30f, 0.52f};    // customEnv.py:26
+  const float b_simple[6] = {8.0f, 8.0f, (float)(ML4CA_PI / 2), 1.75f, 0.30f, 0.51f};  // :337
+  for (int i = 0; i < 6; ++i) c.ss_bounds[i] = (kind == ML4CA_ENV_SIMPLE) ? b_simple[i] : b_full[i];
+  if (kind == ML4CA_ENV_LIMITED || kind == ML4CA_ENV_FINAL) c.ss_bounds[2] = (float)ML4CA_BOUND_YAW;  // :361,386
+  c.sim_dt = (float)ML4CA_SIM_DT;
+  c.step_dt = (float)(0.01 * ML4CA_N_SUBSTEPS);
+  c.reset_fraction = 0.8f;
+  c.seed = 0;
+  c.env_id_offset = 0;
+  int st = validate_cfg(&c);
+  if (st != ML4CA_OK) return st;
+  *out = c;
+  return ML4CA_OK;
+}
+
+int ml4ca_env_dims(const ml4ca_env_cfg* cfg, int32_t* act_dim, int32_t* obs_dim) {
+  int st = validate_cfg(cfg);
+  if (st != ML4CA_OK) return st;
+  static const int act[4] = {6, 3, 5, 5};
+  if (act_dim) *act_dim = (cfg->kind == ML4CA_ENV_FINAL && cfg->cont_ang) ? 7 : act[cfg->kind];
+  if (obs_dim) *obs_dim = cfg->extended_state ? 9 : 6;
+  return ML4CA_OK;
+}
+
+int ml4ca_env_create(const ml4ca_env_cfg* cfg, int64_t n_env, int32_t device, ml4ca_env** out) {
+  ML4CA_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  int st = validate_cfg(cfg);
+  if (st != ML4CA_OK) return st;
+  ML4CA_REQUIRE(n_env > 0, "n_env must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("ml4ca_env_create: no CUDA device (this library has no CPU fallback)");
+    return ML4CA_ERR_NO_DEVICE;
+  }
+  ML4CA_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+  DeviceGuard guard(device);
+  ml4ca_env* e = new (std::nothrow) ml4ca_env();
+  ML4CA_REQUIRE(e != nullptr, "out of host memory");
+  e->cfg = *cfg;
+  e->n = n_env;
+  e->device = device;
+  // one slab: 15 fp32 rows + 2 int32 rows, each row padded to a 16-byte multiple so that every row start is
+  // float4-aligned whenever n % 4 == 0 (rows are indexed with stride n, so the padding only sits at the end).
+  const size_t row = (size_t)n_env * sizeof(float);
+  const size_t bytes = 17 * row + 256;
+  cudaError_t ce = cudaMalloc(&e->slab, bytes);
+  if (ce != cudaSuccess) {
+    delete e;
+    return check_cuda(ce, "cudaMalloc(env state)");
+  }
+  ce = cudaMemset(e->slab, 0, bytes);
+  if (ce != cudaSuccess) {
+    cudaFree(e->slab);
+    delete e;
+    return check_cuda(ce, "cudaMemset(env state)");
+  }
+  float* f = static_cast<float*>(e->slab);
+  EnvParams& p = e->p;
+  p.eta = f;
+  p.nu = f + 3 * n_env;
+  p.ref = f + 6 * n_env;
+  p.prev_thrust = f + 9 * n_env;
+  p.angles = f + 12 * n_env;
+  p.ep_len = reinterpret_cast<int32_t*>(f + 15 * n_env);
+  p.episode = reinterpret_cast<int32_t*>(f + 16 * n_env);
+  p.n = n_env;
+  for (int i = 0; i < 6; ++i) p.bounds[i] = cfg->ss_bounds[i];
+  make_reset_scale(*cfg, cfg->reset_fraction, p.reset_scale);
+  p.sim_dt = cfg->sim_dt;
+  p.step_dt = cfg->step_dt;
+  p.n_sub = cfg->n_substeps;
+  p.max_ep_len = cfg->max_ep_len;
+  p.auto_reset = cfg->auto_reset;
+  p.pad0 = 0;
+  p.seed = cfg->seed;
+  p.env_off = cfg->env_id_offset;
+  *out = e;
+  return ML4CA_OK;
+}
+
+int ml4ca_env_destroy(ml4ca_env* env) {
+  if (env == nullptr) return ML4CA_OK;
+  DeviceGuard guard(env->device);
+  cudaFree(env->slab);
+  delete env;
+  return ML4CA_OK;
+}
+
+int64_t ml4ca_env_size(const ml4ca_env* env) { return env ? env->n : 0; }
+
+int ml4ca_env_reset(ml4ca_env* env, const uint8_t* mask, float fraction, float* obs, void* stream) {
+  ML4CA_REQUIRE(env != nullptr, "env is NULL");
+  DeviceGuard guard(env->device);
+  EnvParams p = env->p;
+  make_reset_scale(env->cfg, fraction, p.reset_scale);
+  return launch_reset(env, p, mask, nullptr, nullptr, obs, static_cast<cudaStream_t>(stream));
+}
+
+int ml4ca_env_reset_to(ml4ca_env* env, const uint8_t* mask, const float* eta, const float* nu, float* obs,
+                       void* stream) {
+  ML4CA_REQUIRE(env != nullptr, "env is NULL");
+  ML4CA_REQUIRE(eta != nullptr && nu != nullptr, "eta and nu are required");
+  DeviceGuard guard(env->device);
+  return launch_reset(env, env->p, mask, eta, nu, obs, static_cast<cudaStream_t>(stream));
+}
+
+int ml4ca_env_set_ref(ml4ca_env* env, const float* ref, void* stream) {
+  ML4CA_REQUIRE(env != nullptr && ref != nullptr, "env and ref are required");
+  DeviceGuard guard(env->device);
+  ML4CA_CUDA(cudaMemcpyAsync(env->p.ref, ref, 3 * (size_t)env->n * sizeof(float), cudaMemcpyDeviceToDevice,
+                             static_cast<cudaStream_t>(stream)));
+  return ML4CA_OK;
+}
+
+int ml4ca_env_step(ml4ca_env* env, const float* action, float* obs, float* rew, uint8_t* done, void* stream) {
+  ML4CA_REQUIRE(env != nullptr, "env is NULL");
+  ML4CA_REQUIRE(action != nullptr && obs != nullptr && rew != nullptr && done != nullptr,
+                "action, obs, rew and done are required");
+  DeviceGuard guard(env->device);
+  return launch_step(env, action, obs, rew, done, static_cast<cudaStream_t>(stream));
+}
+
+int ml4ca_env_get_state(ml4ca_env* env, float* eta, float* nu, float* prev_thrust, float* angles, int32_t* ep_len,
+                        void* stream) {
+  ML4CA_REQUIRE(env != nullptr, "env is NULL");
+  DeviceGuard guard(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t row3 = 3 * (size_t)env->n * sizeof(float);
+  if (eta) ML4CA_CUDA(cudaMemcpyAsync(eta, env->p.eta, row3, cudaMemcpyDeviceToDevice, st));
+  if (nu) ML4CA_CUDA(cudaMemcpyAsync(nu, env->p.nu, row3, cudaMemcpyDeviceToDevice, st));
+  if (prev_thrust) ML4CA_CUDA(cudaMemcpyAsync(prev_thrust, env->p.prev_thrust, row3, cudaMemcpyDeviceToDevice, st));
+  if (angles) ML4CA_CUDA(cudaMemcpyAsync(angles, env->p.angles, row3, cudaMemcpyDeviceToDevice, st));
+  if (ep_len)
+    ML4CA_CUDA(cudaMemcpyAsync(ep_len, env->p.ep_len, (size_t)env->n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  return ML4CA_OK;
+}
+
+int ml4ca_error_frame(int64_t n, const float* eta, const float* ref, float* err, void* stream) {
+  ML4CA_REQUIRE(n >= 0 && eta && ref && err, "bad arguments");
+  if (n == 0) return ML4CA_OK;
+  error_frame_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, eta, ref, err);
+  return check_launch("error_frame_kernel");
+}
+
+int ml4ca_scale_and_clip(const ml4ca_env_cfg* cfg, int64_t n, const float* action, float* act_env, int8_t* sat,
+                         void* stream) {
+  int stv = validate_cfg(cfg);
+  if (stv != ML4CA_OK) return stv;
+  ML4CA_REQUIRE(n >= 0 && action && act_env, "bad arguments");
+  if (n == 0) return ML4CA_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  switch (cfg->kind) {
+    case ML4CA_ENV_FULL: scale_clip_kernel<ML4CA_ENV_FULL, false><<<blocks, 256, 0, st>>>(n, action, act_env, sat); break;
+    case ML4CA_ENV_SIMPLE: scale_clip_kernel<ML4CA_ENV_SIMPLE, false><<<blocks, 256, 0, st>>>(n, action, act_env, sat); break;
+    case ML4CA_ENV_LIMITED: scale_clip_kernel<ML4CA_ENV_LIMITED, false><<<blocks, 256, 0, st>>>(n, action, act_env, sat); break;
+    default:
+      if (cfg->cont_ang) scale_clip_kernel<ML4CA_ENV_FINAL, true><<<blocks, 256, 0, st>>>(n, action, act_env, sat);
+      else scale_clip_kernel<ML4CA_ENV_FINAL, false><<<blocks, 256, 0, st>>>(n, action, act_env, sat);
+  }
+  return check_launch("scale_clip_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// env_step_inst.cu -- one translation unit per env class (compiled with -DML4CA_STEP_UNIT=0..4) so that the
+// kernel instantiations of env_kernels.cuh build in parallel.  Units: 0 full, 1 simple, 2 limited,
+// 3 final (wrapped angles), 4 final (continuous angles).
+#include "env_kernels.cuh"
+
+#ifndef ML4CA_STEP_UNIT
+#error "compile with -DML4CA_STEP_UNIT=<0..4>"
+#endif
+
+namespace ml4ca {
+
+#if ML4CA_STEP_UNIT == 0
+#define UNIT_KIND ML4CA_ENV_FULL
+#define UNIT_CONT false
+#define UNIT_NAME launch_step_full
+#define UNIT_RESET launch_reset_full
+#elif ML4CA_STEP_UNIT == 1
+#define UNIT_KIND ML4CA_ENV_SIMPLE
+#define UNIT_CONT false
+#define UNIT_NAME launch_step_simple
+#define UNIT_RESET launch_reset_simple
+#elif ML4CA_STEP_UNIT == 2
+#define UNIT_KIND ML4CA_ENV_LIMITED
+#define UNIT_CONT false
+#define UNIT_NAME launch_step_limited
+#define UNIT_RESET launch_reset_limited
+#elif ML4CA_STEP_UNIT == 3
+#define UNIT_KIND ML4CA_ENV_FINAL
+#define UNIT_CONT false
+#define UNIT_NAME launch_step_final_wrap
+#define UNIT_RESET launch_reset_final_wrap
+#else
+#define UNIT_KIND ML4CA_ENV_FINAL
+#define UNIT_CONT true
+#define UNIT_NAME launch_step_final_cont
+#define UNIT_RESET launch_reset_final_cont
+#endif
+
+template <int KIND, bool CONT, bool EXT>
+static int launch_step_vec(const ml4ca_env* e, const float* action, float* obs, float* rew, uint8_t* done,
+                           cudaStream_t st) {
+  const int64_t n = e->n;
+  const bool vec4 = (n % 4 == 0) && aligned16(action) && aligned16(obs) && aligned16(rew) &&
+                    ((reinterpret_cast<uintptr_t>(done) & 3u) == 0);
+  const int threads = 256;
+  if (vec4) {
+    const int64_t blocks = (n / 4 + threads - 1) / threads;
+    env_step_kernel<KIND, CONT, EXT, 4><<<(unsigned)blocks, threads, 0, st>>>(e->p, action, obs, rew, done);
+  } else {
+    const int64_t blocks = (n + threads - 1) / threads;
+    env_step_kernel<KIND, CONT, EXT, 1><<<(unsigned)blocks, threads, 0, st>>>(e->p, action, obs, rew, done);
+  }
+  return check_launch("env_step_kernel");
+}
+
+int UNIT_NAME(const ml4ca_env* e, const float* action, float* obs, float* rew, uint8_t* done, cudaStream_t st) {
+  if (e->cfg.extended_state) {
+#if ML4CA_STEP_UNIT == 1
+    return ML4CA_ERR_UNSUPPORTED;
+#else
+    return launch_step_vec<UNIT_KIND, UNIT_CONT, true>(e, action, obs, rew, done, st);
+#endif
+  }
+  return launch_step_vec<UNIT_KIND, UNIT_CONT, false>(e, action, obs, rew, done, st);
+}
+
+int UNIT_RESET(const ml4ca_env* e, const EnvParams& p, const uint8_t* mask, const float* eta, const float* nu,
+               float* obs, cudaStream_t st) {
+  const int threads = 256;
+  const int64_t blocks = (e->n + threads - 1) / threads;
+  if (e->cfg.extended_state)
+    env_reset_kernel<UNIT_KIND, UNIT_CONT, true><<<(unsigned)blocks, threads, 0, st>>>(p, mask, eta, nu, obs);
+  else
+    env_reset_kernel<UNIT_KIND, UNIT_CONT, false><<<(unsigned)blocks, threads, 0, st>>>(p, mask, eta, nu, obs);
+  return check_launch("env_reset_kernel");
+}
+
+}  // namespace ml4ca

@@ -1,0 +1,197 @@
+"""The reference thrust-allocation NLP (qp_allocator.py::QPTA.solve_QP) restated on SciPy SLSQP.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Paths relative to
+/root/reference/src/qp/ROS/qp_allocator/src/qp_allocator.py.
+
+The arithmetic of the reference lives in third-party SciPy (``scipy.optimize.minimize(method=
+'SLSQP')``, call site :206), pinned ``scipy==1.2.0`` in src/rl/windows_workspace/requirements.txt;
+that Fortran build is absent.  This container has SciPy 1.18.1 (C re-implementation, same
+defaults: maxiter 100, ftol 1e-6, forward differences with step 1.49e-8).  So the pin is
+"reference code + container SciPy": ``solve_stock`` reproduces ``QPTA.solve_QP`` bit for bit
+(tests/test_oracle_pinning.py) and tests/golden/qp_*.npz holds the reference's own outputs.
+
+Decision vector x = [f_port, f_star, f_bow, a_port, a_star, s1, s2, s3]  (:118).
+
+  minimise   0.5 * ( |s|^2 + sum |f_i|^3 + 0.25 |a - a_prev|^2 + 0.25 |f - f_prev|^2 )        (:125-150)
+  subject to B(a) f - s = tau   (bow azimuth fixed at pi/2)                                     (:156-158)
+             |f_i - f_prev_i| <= [5, 5, 2]           |a_i - a_prev_i| <= pi/12                (:57-58,164-175)
+             |f_i| <= [20.5, 20.5, 9],  |a_i| <= 2 pi,  |s_i| <= 1                            (:196-200)
+  x0 = [f_prev, a_prev, 0, 0, 0]                                                               (:203)
+
+``solve_tight`` solves the SAME problem with analytic derivatives and ftol=1e-14 -- the converged
+KKT point that the 1e-5 tolerance of BASELINE.json's north_star is measured against (the stock
+solve is only reproducible to ~1e-4).
+"""
+import numpy as np
+from scipy.optimize import minimize
+
+from . import constants as C
+
+LX, LY = C.LX, C.LY
+_COSB = np.cos(np.pi / 2)      # 6.1e-17: the reference keeps these literal terms (:156-158)
+_SINB = np.sin(np.pi / 2)
+
+
+def wrench_rows(f, a):
+    """B(a) f with the bow azimuth fixed at pi/2, rows as written at :156-158 (without s and tau)."""
+    c1 = np.cos(a[0]) * f[0] + np.cos(a[1]) * f[1] + _COSB * f[2]
+    c2 = np.sin(a[0]) * f[0] + np.sin(a[1]) * f[1] + _SINB * f[2]
+    c3 = ((LX[0] * np.sin(a[0]) - LY[0] * np.cos(a[0])) * f[0]
+          + (LX[1] * np.sin(a[1]) - LY[1] * np.cos(a[1])) * f[1]
+          + (LX[2] * _SINB - LY[2] * _COSB) * f[2])
+    return np.array([c1, c2, c3])
+
+
+def _objective(x, prev):
+    obj = np.hstack((x[5:], np.abs(x[0:3]) ** 1.5,
+                     np.abs(x[3] - prev[3]), np.abs(x[4] - prev[4]),
+                     np.abs(x[0:3] - np.asarray(prev[0:3]))))
+    q = np.array([1, 1, 1, 1, 1, 1, .25, .25, .25, .25, .25])
+    return 0.5 * float(np.dot(obj * q, obj))
+
+
+def _objective_grad(x, prev):
+    g = np.zeros(8)
+    g[5:] = x[5:]
+    g[0:3] = 1.5 * np.abs(x[0:3]) * x[0:3] + C.QP_W_RATE * (x[0:3] - np.asarray(prev[0:3]))
+    g[3:5] = C.QP_W_RATE * (x[3:5] - np.asarray(prev[3:5]))
+    return g
+
+
+def _eq_jac(x):
+    f, a = x[0:3], x[3:5]
+    J = np.zeros((3, 8))
+    for i in range(2):
+        c, s = np.cos(a[i]), np.sin(a[i])
+        J[0, i] = c
+        J[1, i] = s
+        J[2, i] = LX[i] * s - LY[i] * c
+        J[0, 3 + i] = -s * f[i]
+        J[1, 3 + i] = c * f[i]
+        J[2, 3 + i] = (LX[i] * c + LY[i] * s) * f[i]
+    J[0, 2] = _COSB
+    J[1, 2] = _SINB
+    J[2, 2] = LX[2] * _SINB - LY[2] * _COSB
+    J[0, 5] = J[1, 6] = J[2, 7] = -1.0
+    return J
+
+
+def _bounds(slack=C.QP_SLACK_BOUND):
+    fm, ab = C.F_MAX, C.QP_ALPHA_BOUND
+    return ((-fm[0], fm[0]), (-fm[1], fm[1]), (-fm[2], fm[2]), (-ab, ab), (-ab, ab),
+            (-slack, slack), (-slack, slack), (-slack, slack))
+
+
+def _constraints(tau, prev, analytic):
+    tau = np.asarray(tau, dtype=np.float64).reshape(3)
+    cons = []
+    for r in range(3):
+        c = {'type': 'eq', 'fun': (lambda x, r=r: wrench_rows(x[0:3], x[3:5])[r] - x[5 + r] - tau[r])}
+        if analytic:
+            c['jac'] = (lambda x, r=r: _eq_jac(x)[r])
+        cons.append(c)
+    rates = [(0, C.QP_DF[0]), (1, C.QP_DF[1]), (2, C.QP_DF[2]), (3, C.QP_DA[0]), (4, C.QP_DA[1])]
+    for i, lim in rates:   # order :164-175 (c4..c13); for the angles the reference lists '+' first
+        signs = (-1.0, +1.0) if i < 3 else (+1.0, -1.0)
+        for sg in signs:
+            c = {'type': 'ineq', 'fun': (lambda x, i=i, lim=lim, sg=sg: lim + sg * (x[i] - prev[i]))}
+            if analytic:
+                e = np.zeros(8)
+                e[i] = sg
+                c['jac'] = (lambda x, e=e: e)
+            cons.append(c)
+    return cons
+
+
+def solve_stock(tau, prev):
+    """QPTA.solve_QP (:108-234) with rospy.get_time() pinned (retry loop :209 never runs).
+
+    tau (3,), prev (5,) = [f_prev(3), a_prev(2)].  Returns (x (8,) after the |x|<0.01 clean-up, success, raw x).
+    """
+    prev = [float(p) for p in prev]
+    x0 = np.array([prev[0], prev[1], prev[2], prev[3], prev[4], 0.0, 0.0, 0.0])
+    sol = minimize(lambda x: _objective(x, prev), x0, method='SLSQP', bounds=_bounds(),
+                   constraints=_constraints(tau, prev, analytic=False))
+    raw = np.array(sol.x, dtype=np.float64)
+    x = raw.copy()
+    x[np.abs(x) < C.QP_CLEAN_EPS] = 0.0            # :232
+    return x, bool(sol.success), raw
+
+
+def solve_tight(tau, prev, x0=None):
+    """Same NLP, analytic derivatives, ftol 1e-14: the converged KKT point.  Returns (raw x, success, nit)."""
+    prev = [float(p) for p in prev]
+    if x0 is None:
+        x0 = np.array([prev[0], prev[1], prev[2], prev[3], prev[4], 0.0, 0.0, 0.0])
+    sol = minimize(lambda x: _objective(x, prev), np.asarray(x0, dtype=np.float64), jac=lambda x: _objective_grad(x, prev),
+                   method='SLSQP', bounds=_bounds(), constraints=_constraints(tau, prev, analytic=True),
+                   options={'ftol': 1e-14, 'maxiter': 500})
+    return np.array(sol.x, dtype=np.float64), bool(sol.success), int(sol.nit)
+
+
+def box(prev):
+    """Effective box of the reduced variables z = [f(3), a(2)]: bounds intersected with the rate limits."""
+    prev = np.asarray(prev, dtype=np.float64)
+    lim = np.array([C.QP_DF[0], C.QP_DF[1], C.QP_DF[2], C.QP_DA[0], C.QP_DA[1]])
+    cap = np.array([C.F_MAX[0], C.F_MAX[1], C.F_MAX[2], C.QP_ALPHA_BOUND, C.QP_ALPHA_BOUND])
+    return np.maximum(prev - lim, -cap), np.minimum(prev + lim, cap)
+
+
+def active_set(x, prev, tol=1e-6):
+    """Bit mask of the tight constraints at x (raw, before clean-up).
+
+    bits 0..4  : z_i at its LOWER effective bound (rate limit or variable bound)
+    bits 5..9  : z_i at its UPPER effective bound
+    bits 10..12: s_i = -1        bits 13..15: s_i = +1
+    """
+    lo, hi = box(prev)
+    m = 0
+    for i in range(5):
+        if x[i] <= lo[i] + tol:
+            m |= 1 << i
+        if x[i] >= hi[i] - tol:
+            m |= 1 << (5 + i)
+    for i in range(3):
+        if x[5 + i] <= -C.QP_SLACK_BOUND + tol:
+            m |= 1 << (10 + i)
+        if x[5 + i] >= C.QP_SLACK_BOUND - tol:
+            m |= 1 << (13 + i)
+    return m
+
+
+def map_to_pi(a):
+    """:101-106"""
+    return np.mod(np.asarray(a, dtype=np.float64) + np.pi, 2 * np.pi) - np.pi
+
+
+def postprocess(x, success, prev6, simulation=False):
+    """tau_controller_callback_func :267-320.
+
+    x (8,) cleaned solution, prev6 = previous_thruster_state [F(3), alpha(3)].
+    Returns dict(n=(3,) percent [port, star, bow], alpha=(3,), bow_throttle, new_prev=(6,)).
+    """
+    sol = np.asarray(x, dtype=np.float64) if success else np.asarray(prev6, dtype=np.float64)   # :267-269
+    F = np.array([sol[0], sol[1], sol[2]])
+    alpha = map_to_pi(np.array([sol[3], sol[4], C.BOW_ANGLE_FIXED]))                            # :276-277
+    fk = F / np.asarray(C.K_THRUST)
+    n = np.sign(fk) * np.sqrt(np.abs(fk))                                                       # :287-288
+    bow = n[2] if simulation else float(np.clip(n[2] * C.BOW_THROTTLE_GAIN, -100.0, 100.0))     # :302-308
+    return {'n': n, 'alpha': alpha, 'bow_throttle': bow,
+            'new_prev': np.array([F[0], F[1], F[2], alpha[0], alpha[1], alpha[2]])}             # :318-320
+
+
+def synth_batch(n, seed=0, tail_fraction=0.10):
+    """previous state f ~ U(+-[10,10,4]), a ~ U(+-pi/2);
+    tau = B(a_prev) f_prev + U(+-[4,2,2]); the last ``tail_fraction`` get tau ~ U(+-[40,20,30])
+    (exercises the infeasible / hold-previous path).  Returns tau [3,n], prev [5,n] float64."""
+    rng = np.random.default_rng(seed)
+    fp = rng.uniform(-1, 1, (3, n)) * np.array([[10.0], [10.0], [4.0]])
+    ap = rng.uniform(-1, 1, (2, n)) * (np.pi / 2)
+    tau = np.zeros((3, n))
+    for j in range(n):
+        tau[:, j] = wrench_rows(fp[:, j], ap[:, j])
+    tau += rng.uniform(-1, 1, (3, n)) * np.array([[4.0], [2.0], [2.0]])
+    nt = int(round(n * tail_fraction))
+    if nt:
+        tau[:, n - nt:] = rng.uniform(-1, 1, (3, nt)) * np.array([[40.0], [20.0], [30.0]])
+    return tau, np.vstack([fp, ap])

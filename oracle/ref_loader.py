@@ -1,0 +1,131 @@
+"""Import the UNMODIFIED reference modules from /root/reference behind stub modules.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Only works in the build container, where the
+read-only reference checkout exists; on the GPU box ``available()`` is False and callers fall back
+to the committed golden vectors under tests/golden/.
+
+Stubbed third-party modules (absent here, and irrelevant to the arithmetic on the hot path):
+  gym / gym.spaces   -> ``Env`` base class and a ``Box`` record   (customEnv.py:1-2,62-64)
+  keras / keras.backend -> dead import in specific/misc/mathematics.py:2
+  rospy, custom_msgs.msg, geometry_msgs.msg -> ROS I/O of qp_allocator.py:17-19,40-87
+``rospy.get_time()`` is pinned to 0.0, which disables the wall-clock keyed retry loop of
+qp_allocator.py:209 and makes ``solve_QP`` deterministic.
+"""
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("ML4CA_REFERENCE_ROOT", "/root/reference")
+_RL_ROOT = os.path.join(REFERENCE_ROOT, "src", "rl", "windows_workspace")
+_QP_ROOT = os.path.join(REFERENCE_ROOT, "src", "qp", "ROS", "qp_allocator", "src")
+
+
+def available():
+    return os.path.isfile(os.path.join(_RL_ROOT, "specific", "customEnv.py"))
+
+
+def _install_stubs():
+    if "gym" not in sys.modules:
+        gym = types.ModuleType("gym")
+
+        class Env(object):
+            pass
+
+        class Box(object):
+            def __init__(self, low=None, high=None, dtype=None, shape=None):
+                self.low, self.high, self.dtype = low, high, dtype
+                self.shape = tuple(low.shape) if shape is None else tuple(shape)
+
+        spaces = types.ModuleType("gym.spaces")
+        spaces.Box = Box
+        spaces.Discrete = type("Discrete", (), {})
+        gym.Env = Env
+        gym.spaces = spaces
+        sys.modules["gym"] = gym
+        sys.modules["gym.spaces"] = spaces
+    if "keras" not in sys.modules:
+        keras = types.ModuleType("keras")
+        backend = types.ModuleType("keras.backend")
+        keras.backend = backend
+        sys.modules["keras"] = keras
+        sys.modules["keras.backend"] = backend
+    if "rospy" not in sys.modules:
+        rospy = types.ModuleType("rospy")
+        rospy.init_node = lambda *a, **k: None
+        rospy.Rate = lambda hz: types.SimpleNamespace(sleep=lambda: None)
+        rospy.get_time = lambda: 0.0
+        rospy.loginfo = lambda *a, **k: None
+        rospy.logwarn = lambda *a, **k: None
+        rospy.spin = lambda: None
+        rospy.ROSInterruptException = type("ROSInterruptException", (Exception,), {})
+
+        class _Pub(object):
+            def __init__(self, *a, **k):
+                self.last = None
+
+            def publish(self, msg):
+                self.last = msg
+
+        rospy.Publisher = _Pub
+        rospy.Subscriber = lambda *a, **k: None
+        sys.modules["rospy"] = rospy
+
+        def _msg(name, fields):
+            def __init__(self):
+                for f in fields:
+                    setattr(self, f, 0.0)
+            return type(name, (), {"__init__": __init__})
+
+        custom = types.ModuleType("custom_msgs")
+        cmsg = types.ModuleType("custom_msgs.msg")
+        cmsg.podAngle = _msg("podAngle", ["port", "star"])
+        cmsg.SternThrusterSetpoints = _msg("SternThrusterSetpoints", ["port_effort", "star_effort"])
+        cmsg.bowControl = _msg("bowControl", ["throttle_bow", "position_bow", "lin_act_bow"])
+        cmsg.diffThrottleStern = _msg("diffThrottleStern", ["throttle", "rudder"])
+        custom.msg = cmsg
+        sys.modules["custom_msgs"] = custom
+        sys.modules["custom_msgs.msg"] = cmsg
+
+        geo = types.ModuleType("geometry_msgs")
+        gmsg = types.ModuleType("geometry_msgs.msg")
+
+        class Wrench(object):
+            def __init__(self, fx=0.0, fy=0.0, tz=0.0):
+                self.force = types.SimpleNamespace(x=fx, y=fy, z=0.0)
+                self.torque = types.SimpleNamespace(x=0.0, y=0.0, z=tz)
+
+        gmsg.Wrench = Wrench
+        geo.msg = gmsg
+        sys.modules["geometry_msgs"] = geo
+        sys.modules["geometry_msgs.msg"] = gmsg
+
+
+def load_env_module():
+    """-> the reference ``specific.customEnv`` module (Revolt, RevoltFinal, ...)."""
+    if not available():
+        raise RuntimeError("reference checkout not present at %s" % REFERENCE_ROOT)
+    _install_stubs()
+    if _RL_ROOT not in sys.path:
+        sys.path.insert(0, _RL_ROOT)
+    return importlib.import_module("specific.customEnv")
+
+
+def load_error_frame_module():
+    load_env_module()
+    return importlib.import_module("specific.errorFrame")
+
+
+def load_qp_module():
+    """-> the reference ROS ``qp_allocator`` module (class QPTA)."""
+    if not available():
+        raise RuntimeError("reference checkout not present at %s" % REFERENCE_ROOT)
+    _install_stubs()
+    if _QP_ROOT not in sys.path:
+        sys.path.insert(0, _QP_ROOT)
+    return importlib.import_module("qp_allocator")
+
+
+def wrench(fx, fy, tz):
+    _install_stubs()
+    return sys.modules["geometry_msgs.msg"].Wrench(fx, fy, tz)

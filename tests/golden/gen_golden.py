@@ -1,0 +1,146 @@
+"""Generate the golden vectors under tests/golden/ by RUNNING THE UNMODIFIED REFERENCE CODE.
+
+Only works in the build container (needs the read-only checkout at /root/reference); the resulting
+.npz files are committed so that the GPU box -- where the reference does not exist -- can check the
+oracle and the CUDA path against the reference's own outputs.
+
+    python tests/golden/gen_golden.py
+
+env_<kind>_<mode>.npz : reference customEnv classes driven through the DigiTwin duck type
+                        oracle.vessel.VesselTwin (float64).  mode 'null' = frozen simulator (wrapper
+                        arithmetic only), 'hull' = the declared stand-in hull integrated in float64.
+qp_config1.npz        : reference QPTA.solve_QP + tau_controller_callback_func post-processing on the
+                        SURVEY.md section 8(d) config-1 demand distribution (container SciPy, see
+                        oracle/qp_oracle.py header), rospy.get_time() pinned to 0.
+gae.npz               : reference core.discount_cumsum formulation (scipy.signal.lfilter) and the
+                        TrajectoryBuffer.finish_path arithmetic (ppo.py:82-91).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+from oracle import ref_loader, vessel, qp_oracle  # noqa: E402
+import scipy  # noqa: E402
+import scipy.signal  # noqa: E402
+
+
+def gen_env(kind, cls_name, kwargs, frozen, B, T, seed):
+    mod = ref_loader.load_env_module()
+    rng = np.random.default_rng(seed)
+    act_dim = None
+    rec = {k: [] for k in ('eta0', 'nu0', 'actions', 'obs0', 'obs', 'rew', 'done', 'eta', 'nu')}
+    for b in range(B):
+        twin = vessel.VesselTwin(frozen=frozen)
+        if cls_name == 'Revolt':
+            env = mod.Revolt(digitwin=twin, real_ss_bounds=[8.0, 8.0, np.pi / 2, 1.4, 0.30, 0.52], **kwargs)
+        else:
+            env = getattr(mod, cls_name)(twin, **kwargs)
+        act_dim = env.num_actions
+        eta0 = rng.uniform(-1, 1, 3) * np.array([7.0, 7.0, 0.7])
+        nu0 = rng.uniform(-1, 1, 3) * np.array([0.5, 0.12, 0.2])
+        init = {'Hull.PosNED': [eta0[0], eta0[1]], 'Hull.PosAttitude': [0, 0, eta0[2]],
+                'Hull.VelocityNu': [nu0[0], nu0[1], 0, 0, 0, nu0[2]]}
+        o0 = env.reset(**init)
+        acts, obs, rew, done, etas, nus = [], [], [], [], [], []
+        for t in range(T):
+            a = rng.uniform(-1.25, 1.25, act_dim)
+            if t % 7 == 3:
+                a[rng.integers(0, act_dim)] = 1.0      # exactly on the clip boundary
+            o, r, d, _ = env.step(a)
+            acts.append(a); obs.append(np.array(o, dtype=np.float64))
+            rew.append(float(np.asarray(r).ravel()[0])); done.append(bool(d))
+            etas.append(twin.eta.copy()); nus.append(twin.nu.copy())
+        rec['eta0'].append(eta0); rec['nu0'].append(nu0); rec['obs0'].append(np.array(o0, dtype=np.float64))
+        rec['actions'].append(acts); rec['obs'].append(obs); rec['rew'].append(rew); rec['done'].append(done)
+        rec['eta'].append(etas); rec['nu'].append(nus)
+        max_ep_len, dt = env.max_ep_len, env.dt
+    out = {
+        'eta0': np.array(rec['eta0']).T,                               # [3, B]
+        'nu0': np.array(rec['nu0']).T,
+        'obs0': np.array(rec['obs0']).T,                               # [obs, B]
+        'actions': np.transpose(np.array(rec['actions']), (1, 2, 0)),  # [T, act, B]
+        'obs': np.transpose(np.array(rec['obs']), (1, 2, 0)),          # [T, obs, B]
+        'rew': np.array(rec['rew']).T,                                 # [T, B]
+        'done': np.array(rec['done']).T,
+        'eta': np.transpose(np.array(rec['eta']), (1, 2, 0)),          # [T, 3, B]
+        'nu': np.transpose(np.array(rec['nu']), (1, 2, 0)),
+        'max_ep_len': np.array(max_ep_len), 'dt': np.array(dt),
+    }
+    return out
+
+
+def gen_qp(n, seed):
+    qp = ref_loader.load_qp_module()
+    ta = qp.QPTA()
+    tau, prev = qp_oracle.synth_batch(n, seed=seed)
+    xs, oks, ns, alphas, bows, newprev = [], [], [], [], [], []
+    for j in range(n):
+        ta.previous_thruster_state = [float(v) for v in prev[:, j]] + [np.pi / 2]
+        x, ok = ta.solve_QP(tau[:, j].reshape(3, 1))
+        xs.append(np.array(x)); oks.append(bool(ok))
+        # full callback (post-processing :267-320) on a fresh object state
+        ta.previous_thruster_state = [float(v) for v in prev[:, j]] + [np.pi / 2]
+        ta.tau_controller_callback_func(ref_loader.wrench(tau[0, j], tau[1, j], tau[2, j]))
+        ns.append([ta.pub_stern_thruster_setpoints.last.port_effort, ta.pub_stern_thruster_setpoints.last.star_effort])
+        alphas.append([ta.pub_stern_angles.last.port, ta.pub_stern_angles.last.star])
+        bows.append(float(ta.pub_bow_control.last.throttle_bow))
+        newprev.append(list(ta.previous_thruster_state))
+    return {'tau': tau, 'prev': prev, 'x': np.array(xs).T, 'success': np.array(oks),
+            'stern_effort': np.array(ns).T, 'pod_angle_deg': np.array(alphas).T, 'bow_throttle': np.array(bows),
+            'new_prev': np.array(newprev).T, 'scipy_version': np.array(scipy.__version__)}
+
+
+def gen_gae(seed):
+    """Reference formulas: core.py:48-63 (lfilter) and ppo.py:82-91 -- evaluated directly (TF1 import impossible)."""
+    rng = np.random.default_rng(seed)
+    T = 37
+    rews = rng.normal(size=T).astype(np.float32)
+    vals = rng.normal(size=T).astype(np.float32)
+    last_val = np.float32(0.37)
+    gamma, lam = 0.99, 0.97
+
+    def discount_cumsum(x, discount):
+        return scipy.signal.lfilter([1], [1, float(-discount)], x[::-1], axis=0)[::-1]
+
+    r = np.append(rews, last_val)
+    v = np.append(vals, last_val)
+    deltas = r[:-1] + gamma * v[1:] - v[:-1]
+    adv = discount_cumsum(deltas, gamma * lam).astype(np.float32)
+    ret = discount_cumsum(r, gamma)[:-1].astype(np.float32)
+    return {'rews': rews, 'vals': vals, 'last_val': last_val, 'gamma': np.array(gamma), 'lam': np.array(lam),
+            'adv': adv, 'ret': ret}
+
+
+def main():
+    assert ref_loader.available(), "reference checkout not found"
+    cases = [
+        ('final_cont_ext', 'final', 'RevoltFinal', dict(cont_ang=True, extended_state=True), 32, 40),
+        ('final_wrap_ext', 'final', 'RevoltFinal', dict(cont_ang=False, extended_state=True), 8, 20),
+        ('final_cont_std', 'final', 'RevoltFinal', dict(cont_ang=True, extended_state=False), 8, 20),
+        ('limited_ext', 'limited', 'RevoltLimited', dict(extended_state=True), 8, 20),
+        ('simple_std', 'simple', 'RevoltSimple', dict(extended_state=False), 8, 20),
+        ('full_ext', 'full', 'Revolt', dict(extended_state=True), 8, 20),
+    ]
+    for i, (tag, kind, cls, kw, B, T) in enumerate(cases):
+        for mode, frozen in (('null', True), ('hull', False)):
+            out = gen_env(kind, cls, kw, frozen, B, T, seed=100 + i)
+            out['kind'] = np.array(kind)
+            out['cont_ang'] = np.array(bool(kw.get('cont_ang', False)))
+            out['extended_state'] = np.array(bool(kw['extended_state']))
+            path = os.path.join(HERE, 'env_%s_%s.npz' % (tag, mode))
+            np.savez_compressed(path, **out)
+            print('wrote', path)
+    out = gen_qp(256, seed=0)
+    np.savez_compressed(os.path.join(HERE, 'qp_config1.npz'), **out)
+    print('wrote qp_config1.npz  success rate %.3f' % out['success'].mean())
+    np.savez_compressed(os.path.join(HERE, 'gae.npz'), **gen_gae(7))
+    print('wrote gae.npz')
+
+
+if __name__ == '__main__':
+    main()
