@@ -290,7 +290,10 @@ def run_b200(args, rank, local_rank, world):
     clocks = sampler.summary()
 
     if rank == 0:
-        cpu_val, cpu_cores, cpu_sample = cpu_env_steps_per_s(1 << 16, 8)
+        if args.skip_cpu:
+            cpu_val, cpu_cores, cpu_sample = None, 0, "skipped (--skip-cpu)"
+        else:
+            cpu_val, cpu_cores, cpu_sample = cpu_env_steps_per_s(1 << 16, 8)
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -318,6 +321,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 24)
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the CPU baseline leg (used for ncu captures)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

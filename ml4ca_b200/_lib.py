@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libml4ca_b200.so")
+LIB_PATH = os.environ.get("ML4CA_LIB", os.path.join(_HERE, "libml4ca_b200.so"))   # ML4CA_LIB: tuning variants only
 
 c_f32p = ctypes.c_void_p
 c_u8p = ctypes.c_void_p

@@ -46,8 +46,14 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source into libml4ca_b200.so.  Returns the library path."""
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile every CUDA source into libml4ca_b200.so.  Returns the library path.
+    extra_flags/out build an experimental variant next to the default library (tuning only)."""
+    global LIB, STAMP
+    if out is not None:
+        LIB = os.path.join(HERE, out)
+        STAMP = LIB + ".stamp"
+        force = True
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
@@ -58,8 +64,9 @@ def build(force=False, verbose=False):
 
     def compile_one(item):
         src, defines, suffix = item
-        obj = os.path.join(CSRC, src.replace(".cu", suffix + ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + defines + ["-c", os.path.join(CSRC, src), "-o", obj]
+        tag = "" if out is None else "_" + os.path.splitext(out)[0]
+        obj = os.path.join(CSRC, src.replace(".cu", suffix + tag + ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + defines + ["-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, "$ " + " ".join(cmd) + "\n" + res.stdout + res.stderr, res.returncode
 

@@ -18,6 +18,10 @@
 #include "common.h"
 #include "env_math.cuh"
 
+#ifndef ML4CA_ENV_MIN_BLOCKS
+#define ML4CA_ENV_MIN_BLOCKS 6  // scalar-row kernel: 40 registers, 48 resident warps/SM (measured best on B200)
+#endif
+
 namespace ml4ca {
 
 struct EnvParams {
@@ -31,7 +35,8 @@ struct EnvParams {
   int64_t n;
   float bounds[6];
   float reset_scale[6];
-  float sim_dt, step_dt;
+  float inv_step_dt, pad1;
+  HullConsts hull;
   int32_t n_sub, max_ep_len;
   int32_t auto_reset, pad0;
   uint64_t seed;
@@ -120,7 +125,7 @@ __device__ __forceinline__ void st_flags(uint8_t* __restrict__ row, int64_t i, c
 
 // ---- K3 ------------------------------------------------------------------------------------------------------------
 template <int KIND, bool CONT, bool EXT, int VEC>
-__global__ void __launch_bounds__(256) env_step_kernel(const EnvParams p, const float* __restrict__ action,
+__global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : 1) env_step_kernel(const EnvParams p, const float* __restrict__ action,
                                                        float* __restrict__ obs, float* __restrict__ rew,
                                                        uint8_t* __restrict__ done) {
   using T = EnvTraits<KIND, CONT>;
@@ -166,22 +171,40 @@ __global__ void __launch_bounds__(256) env_step_kernel(const EnvParams p, const 
     const float pa_bow = ang[0][j], pa_port = ang[1][j], pa_star = ang[2][j];  // prev_angles, :102
     apply_angle_commands<KIND, CONT>(cmd, ang[0][j], ang[1][j], ang[2][j]);    // :117-122
     if (p.n_sub > 0) {                                                 // dTwin.step(n_steps), :124
+      float sb, cb, sp, cp, ss, cs;
+      if constexpr (T::NANG == 3) {
+        sincosf(ang[0][j], &sb, &cb);
+      } else if constexpr (KIND == ML4CA_ENV_SIMPLE) {
+        sincosf(T::DEF_BOW, &sb, &cb);
+      } else {
+        sb = 1.f, cb = 0.f;                                            // bow azimuth fixed at 90 deg (:394-399)
+      }
+      if constexpr (KIND == ML4CA_ENV_FINAL && CONT) {
+        unit_from_pair(act[3], act[4], sp, cp);                        // (sin, cos) straight from the network pair
+        unit_from_pair(act[5], act[6], ss, cs);
+      } else {
+        sincosf(ang[1][j], &sp, &cp);
+        sincosf(ang[2][j], &ss, &cs);
+      }
       float tx, ty, tn;
-      thruster_wrench(cmd[0], cmd[1], cmd[2], ang[0][j], ang[1][j], ang[2][j], tx, ty, tn);
-      integrate_hull(eta[0][j], eta[1][j], eta[2][j], nu[0][j], nu[1][j], nu[2][j], tx, ty, tn, p.n_sub, p.sim_dt);
+      thruster_wrench_sc(cmd[0], cmd[1], cmd[2], sb, cb, sp, cp, ss, cs, tx, ty, tn);
+      integrate_hull(eta[0][j], eta[1][j], eta[2][j], nu[0][j], nu[1][j], nu[2][j], tx, ty, tn, p.n_sub, p.hull);
     }
     float xb, yb, pb;                                                  // state_extended(), :125
     error_frame(eta[0][j], eta[1][j], eta[2][j], ref[0][j], ref[1][j], ref[2][j], xb, yb, pb);
     o[0][j] = xb, o[1][j] = yb, o[2][j] = pb;
     o[3][j] = nu[0][j], o[4][j] = nu[1][j], o[5][j] = nu[2][j];
-    float old_scaled[3] = {0.f, 0.f, 0.f};
+    float old_thrust[3] = {0.f, 0.f, 0.f};
     if constexpr (EXT) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) o[6 + c][j] = old_scaled[c] = __fdiv_rn(pth[c][j], 100.0f);
+      for (int c = 0; c < 3; ++c) {
+        old_thrust[c] = pth[c][j];
+        o[6 + c][j] = __fdiv_rn(pth[c][j], 100.0f);                    // prev_thrust / 100.0, :204 (bit-exact)
+      }
     }
     const float thrust[3] = {cmd[0], cmd[1], cmd[2]};                  // prev_thrust <- action[0:3], :126
-    rw[j] = reward_fn<EXT>(xb, yb, pb, nu[0][j], nu[1][j], nu[2][j], thrust, old_scaled, ang[0][j] - pa_bow,
-                           ang[1][j] - pa_port, ang[2][j] - pa_star, p.step_dt, T::ANG_BOUND);   // :128
+    rw[j] = reward_fn<EXT>(xb, yb, pb, nu[0][j], nu[1][j], nu[2][j], thrust, old_thrust, ang[0][j] - pa_bow,
+                           ang[1][j] - pa_port, ang[2][j] - pa_star, p.inv_step_dt, 1.0f / T::ANG_BOUND);   // :128
     const bool term = is_terminal(xb, yb, pb, nu[0][j], nu[1][j], nu[2][j], p.bounds);           // :129
     ep[j] += 1;
     const bool trunc = ep[j] >= p.max_ep_len;                          // ppo.py:304

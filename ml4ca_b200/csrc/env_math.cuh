@@ -87,16 +87,19 @@ __device__ __forceinline__ void transform_action(const float (&a)[EnvTraits<KIND
 #pragma unroll
   for (int i = 0; i < 3; ++i) cmd[i] = scale_clip(a[i], (float)ML4CA_THRUST_BOUND, sat[i]);
   if constexpr (KIND == ML4CA_ENV_FINAL) {
-    float ap, as;
-    if constexpr (CONT) {  // handle_continuous_angles :227-235
-      ap = __fdiv_rn(atan2f(a[3], a[4]), T::ANG_BOUND);
-      as = __fdiv_rn(atan2f(a[5], a[6]), T::ANG_BOUND);
+    if constexpr (CONT) {
+      // handle_continuous_angles :227-235 then scale_and_clip: (atan2(s, c) / pi) * pi clipped to +-pi.  The
+      // divide/multiply round trip is the identity up to one ulp and |atan2f| <= fl(pi) never clips, so the
+      // command is atan2f itself (transcendental piece, tolerance-checked; saves two IEEE divisions per env).
+      cmd[3] = fminf(fmaxf(atan2f(a[3], a[4]), -T::ANG_BOUND), T::ANG_BOUND);
+      cmd[4] = fminf(fmaxf(atan2f(a[5], a[6]), -T::ANG_BOUND), T::ANG_BOUND);
+      sat[3] = sat[4] = 0;
     } else {  // wrap_stern_angles :237-244
-      ap = __fdiv_rn(wrap_rad(__fmul_rn(a[3], T::ANG_BOUND)), T::ANG_BOUND);
-      as = __fdiv_rn(wrap_rad(__fmul_rn(a[4], T::ANG_BOUND)), T::ANG_BOUND);
+      const float ap = __fdiv_rn(wrap_rad(__fmul_rn(a[3], T::ANG_BOUND)), T::ANG_BOUND);
+      const float as = __fdiv_rn(wrap_rad(__fmul_rn(a[4], T::ANG_BOUND)), T::ANG_BOUND);
+      cmd[3] = scale_clip(ap, T::ANG_BOUND, sat[3]);
+      cmd[4] = scale_clip(as, T::ANG_BOUND, sat[4]);
     }
-    cmd[3] = scale_clip(ap, T::ANG_BOUND, sat[3]);
-    cmd[4] = scale_clip(as, T::ANG_BOUND, sat[4]);
   } else {
 #pragma unroll
     for (int i = 3; i < T::NCMD; ++i) cmd[i] = scale_clip(a[i], T::ANG_BOUND, sat[i]);
@@ -118,16 +121,21 @@ __device__ __forceinline__ void apply_angle_commands(const float (&cmd)[EnvTrait
 }
 
 // ---- stand-in hull (DECLARED; see ml4ca_constants.h and oracle/vessel.py) ------------------------------------
+__device__ __forceinline__ float fast_sqrt(float x) {  // sqrt.approx: 1 ulp, no IEEE fix-up sequence
+  float y;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // tau = sum_i F_i [cos a_i, sin a_i, lx_i sin a_i - ly_i cos a_i], F_i = K_i n_i |n_i|; env order bow, port, star.
-__device__ __forceinline__ void thruster_wrench(float n_bow, float n_port, float n_star, float a_bow, float a_port,
-                                                float a_star, float& tx, float& ty, float& tn) {
+// The caller supplies sin/cos of each azimuth (for the continuous-angle env they come straight from the
+// network's (sin, cos) pair: cos(atan2(y, x)) = x / hypot(x, y), no atan2f -> sincosf round trip).
+__device__ __forceinline__ void thruster_wrench_sc(float n_bow, float n_port, float n_star, float sb, float cb,
+                                                   float sp, float cp, float ss, float cs, float& tx, float& ty,
+                                                   float& tn) {
   const float fb = (float)ML4CA_K_BOW * n_bow * fabsf(n_bow);
   const float fp = (float)ML4CA_K_STERN * n_port * fabsf(n_port);
   const float fs = (float)ML4CA_K_STERN * n_star * fabsf(n_star);
-  float sb, cb, sp, cp, ss, cs;
-  sincosf(a_bow, &sb, &cb);
-  sincosf(a_port, &sp, &cp);
-  sincosf(a_star, &ss, &cs);
   tx = fb * cb + fp * cp + fs * cs;
   ty = fb * sb + fp * sp + fs * ss;
   tn = fb * ((float)ML4CA_LX_BOW * sb - (float)ML4CA_LY_BOW * cb) +
@@ -135,44 +143,81 @@ __device__ __forceinline__ void thruster_wrench(float n_bow, float n_port, float
        fs * ((float)ML4CA_LX_STAR * ss - (float)ML4CA_LY_STAR * cs);
 }
 
-// n_sub semi-implicit Euler sub-steps of h seconds.  The heading rotation is advanced by the exact angle-sum
-// recurrence with a 3rd-order small-angle kernel (|h r| <= 1e-2: truncation < 1e-13), and the pose increments are
-// accumulated separately from the pose so that 20 small additions do not each round at the magnitude of N, E.
+// (sin, cos) of atan2(y, x) without evaluating the angle: (y, x) / hypot(x, y); atan2(0, 0) = 0 -> (0, 1).
+__device__ __forceinline__ void unit_from_pair(float y, float x, float& s, float& c) {
+  const float h2 = x * x + y * y;
+  const float inv = rsqrtf(h2);
+  const bool ok = h2 > 1e-30f && h2 < 1e30f;
+  s = ok ? y * inv : 0.f;
+  c = ok ? x * inv : 1.f;
+  if (!ok && h2 != 0.f) sincosf(atan2f(y, x), &s, &c);  // denormal / overflow corner: exact route
+}
+
+// Per-launch constants of the integrator, folded on the host (hull_consts()).
+struct HullConsts {
+  float h;                    // sub-step, s
+  float hm1, hm2, hm3;        // h / m11, h / m22, h / m33
+  float k_vr, k_ur, k_uv;     // Coriolis couplings times h / m
+  float one_xu, xuu, one_yv, yvv, one_nr, nrr;  // 1 - h Xu/m11, h Xuu/m11, ...
+  float rot_c2, rot_s1, rot_s3;  // -h^2/2, h, -h^3/6: small-angle rotation kernel in terms of r
+};
+
+inline HullConsts hull_consts(float h) {
+  HullConsts k;
+  k.h = h;
+  k.hm1 = (float)((double)h / ML4CA_M11);
+  k.hm2 = (float)((double)h / ML4CA_M22);
+  k.hm3 = (float)((double)h / ML4CA_M33);
+  k.k_vr = (float)((double)h * ML4CA_M22 / ML4CA_M11);
+  k.k_ur = (float)((double)h * ML4CA_M11 / ML4CA_M22);
+  k.k_uv = (float)((double)h * (ML4CA_M22 - ML4CA_M11) / ML4CA_M33);
+  k.one_xu = (float)(1.0 - (double)h * ML4CA_XU / ML4CA_M11);
+  k.xuu = (float)((double)h * ML4CA_XUU / ML4CA_M11);
+  k.one_yv = (float)(1.0 - (double)h * ML4CA_YV / ML4CA_M22);
+  k.yvv = (float)((double)h * ML4CA_YVV / ML4CA_M22);
+  k.one_nr = (float)(1.0 - (double)h * ML4CA_NR / ML4CA_M33);
+  k.nrr = (float)((double)h * ML4CA_NRR / ML4CA_M33);
+  k.rot_c2 = (float)(-0.5 * (double)h * h);
+  k.rot_s1 = h;
+  k.rot_s3 = (float)(-(double)h * h * h / 6.0);
+  return k;
+}
+
+// n_sub semi-implicit Euler sub-steps:  nu+ = nu + h nu_dot(nu);  N,E += h R(psi) nu+;  psi += h r+.
+// 25 FP32 instructions per sub-step:
+//  * nu+ = (1 - h d(nu)/m) nu + h (tau + coriolis)/m      -- 3 products + 3 x 3 FMA
+//  * the pose increments are summed un-scaled (sum R nu, sum r) and multiplied by h once, apart from the pose
+//    itself, so 20 small additions do not each round at the magnitude of N, E
+//  * R(psi) advances by the angle-sum recurrence with a 3rd-order small-angle kernel written in r
+//    (|h r| <= 1e-2: truncation ~1e-13 per sub-step); (s, c) only feed the position increment.
 __device__ __forceinline__ void integrate_hull(float& N, float& E, float& psi, float& u, float& v, float& r,
-                                               float tx, float ty, float tn, int n_sub, float h) {
-  const float hm1 = h / (float)ML4CA_M11, hm2 = h / (float)ML4CA_M22, hm3 = h / (float)ML4CA_M33;
-  const float ax = hm1 * tx, ay = hm2 * ty, an = hm3 * tn;
-  const float k_vr = hm1 * (float)ML4CA_M22, k_ur = hm2 * (float)ML4CA_M11,
-              k_uv = hm3 * (float)(ML4CA_M22 - ML4CA_M11);
-  const float xu = hm1 * (float)ML4CA_XU, xuu = hm1 * (float)ML4CA_XUU;
-  const float yv = hm2 * (float)ML4CA_YV, yvv = hm2 * (float)ML4CA_YVV;
-  const float nr = hm3 * (float)ML4CA_NR, nrr = hm3 * (float)ML4CA_NRR;
+                                               float tx, float ty, float tn, int n_sub, const HullConsts& k) {
+  const float ax = k.hm1 * tx, ay = k.hm2 * ty, an = k.hm3 * tn;
   float s, c;
   sincosf(psi, &s, &c);
-  float dN = 0.f, dE = 0.f, dpsi = 0.f;
-#pragma unroll 4
-  for (int k = 0; k < n_sub; ++k) {
+  float sN = 0.f, sE = 0.f, sr = 0.f;
+#pragma unroll 5
+  for (int i = 0; i < n_sub; ++i) {
     const float vr = v * r, ur = u * r, uv = u * v;
-    const float un = u + (ax + k_vr * vr - (xu + xuu * fabsf(u)) * u);
-    const float vn = v + (ay - k_ur * ur - (yv + yvv * fabsf(v)) * v);
-    const float rn = r + (an - k_uv * uv - (nr + nrr * fabsf(r)) * r);
+    const float un = fmaf(fmaf(-k.xuu, fabsf(u), k.one_xu), u, fmaf(k.k_vr, vr, ax));
+    const float vn = fmaf(fmaf(-k.yvv, fabsf(v), k.one_yv), v, fmaf(-k.k_ur, ur, ay));
+    const float rn = fmaf(fmaf(-k.nrr, fabsf(r), k.one_nr), r, fmaf(-k.k_uv, uv, an));
     u = un;
     v = vn;
     r = rn;
-    dN = fmaf(h, c * u - s * v, dN);
-    dE = fmaf(h, s * u + c * v, dE);
-    const float d = h * r;
-    dpsi += d;
-    const float d2 = d * d;
-    const float cd = fmaf(-0.5f, d2, 1.0f);
-    const float sd = fmaf(d * d2, -1.0f / 6.0f, d);
-    const float cn = c * cd - s * sd;
-    s = s * cd + c * sd;
+    sN = fmaf(-s, v, fmaf(c, u, sN));
+    sE = fmaf(c, v, fmaf(s, u, sE));
+    sr += r;
+    const float r2 = r * r;
+    const float cd = fmaf(k.rot_c2, r2, 1.0f);
+    const float sd = r * fmaf(k.rot_s3, r2, k.rot_s1);
+    const float cn = fmaf(-s, sd, c * cd);
+    s = fmaf(c, sd, s * cd);
     c = cn;
   }
-  N += dN;
-  E += dE;
-  psi += dpsi;
+  N = fmaf(k.h, sN, N);
+  E = fmaf(k.h, sE, E);
+  psi = fmaf(k.h, sr, psi);
 }
 
 // ---- errorFrame.py:25-32 --------------------------------------------------------------------------------------
@@ -187,41 +232,39 @@ __device__ __forceinline__ void error_frame(float N, float E, float psi, float r
 }
 
 // ---- customEnv.py:253-325, coefficients of :263 -----------------------------------------------------------------
-// thrust[3] = this step's clipped thrust (the NEW prev_thrust, :126), old_scaled[3] = state_ext[-3:] (previous
-// thrust / 100), angle deltas = current_angles - prev_angles, env order bow, port, star.
+// thrust[3] = this step's clipped thrust (the NEW prev_thrust, :126), old_thrust[3] = the previous step's thrust
+// (the reference reads it back as state_ext[-3:] * 100, :311), angle deltas = current_angles - prev_angles, env
+// order bow, port, star.  Tolerance-checked piece: quotients by constants are products with the reciprocal,
+// sqrt/exp use the MUFU approximations (<= 2 ulp); inv_dt = 1 / step_dt, inv_bound = 1 / real_action_bounds[4].
 template <bool EXT>
 __device__ __forceinline__ float reward_fn(float xb, float yb, float psib, float u, float v, float r,
-                                           const float (&thrust)[3], const float (&old_scaled)[3], float da_bow,
-                                           float da_port, float da_star, float step_dt, float ang_bound) {
+                                           const float (&thrust)[3], const float (&old_thrust)[3], float da_bow,
+                                           float da_port, float da_star, float inv_dt, float inv_bound) {
   // vel_reward :267-273
-  const float vel = -sqrtf((u * u) * (float)ML4CA_REW_VEL_CU + (v * v) * (float)ML4CA_REW_VEL_CV +
-                           (r * r) * (float)ML4CA_REW_VEL_CR);
+  const float vel = -fast_sqrt((u * u) * (float)ML4CA_REW_VEL_CU + (v * v) * (float)ML4CA_REW_VEL_CV +
+                               (r * r) * (float)ML4CA_REW_VEL_CR);
   // multivariate_gaussian :275-290
   const float d2 = xb * xb + yb * yb;
-  const float yaw = psib * 180.0f / kPi;
+  const float yaw = psib * (float)(180.0 / ML4CA_PI);
+  const float y2 = yaw * yaw;
   const float quad = d2 * (float)(1.0 / (ML4CA_REW_SIGMA_POS * ML4CA_REW_SIGMA_POS)) +
-                     (yaw * yaw) * (float)(1.0 / (ML4CA_REW_SIGMA_YAW * ML4CA_REW_SIGMA_YAW));
-  const float multivar = 2.0f * expf(-0.5f * quad);
-  const float yq = yaw * 0.25f;
-  const float special = sqrtf(d2 + yq * yq);
-  const float anti = fmaxf(-1.0f, 1.0f - 0.1f * special);
+                     y2 * (float)(1.0 / (ML4CA_REW_SIGMA_YAW * ML4CA_REW_SIGMA_YAW));
+  const float multivar = 2.0f * __expf(-0.5f * quad);
+  const float special = fast_sqrt(fmaf(y2, 0.0625f, d2));
+  const float anti = fmaxf(-1.0f, fmaf(-0.1f, special, 1.0f));
   float rew = vel + (multivar + anti + 0.5f);
   // thrust_penalty :292-302
-  rew -= fabsf(thrust[0]) / 100.0f * (float)ML4CA_REW_THRUST_C_BOW;
-  rew -= fabsf(thrust[1]) / 100.0f * (float)ML4CA_REW_THRUST_C_STERN;
-  rew -= fabsf(thrust[2]) / 100.0f * (float)ML4CA_REW_THRUST_C_STERN;
+  rew -= fabsf(thrust[0]) * (float)(ML4CA_REW_THRUST_C_BOW / 100.0);
+  rew -= (fabsf(thrust[1]) + fabsf(thrust[2])) * (float)(ML4CA_REW_THRUST_C_STERN / 100.0);
   // action_derivative_penalty :304-325 (returns 0 without the extended state)
   if constexpr (EXT) {
-    float pen = 0.f;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const float derr = (thrust[i] - old_scaled[i] * 100.0f) / step_dt;
-      pen -= fabsf(derr / 100.0f) * (float)ML4CA_REW_DTHRUST_C;
-    }
-    float angpen = -fabsf(da_bow / step_dt / ang_bound) * (float)ML4CA_REW_DANGLE_C_BOW;
-    angpen -= fabsf(da_port / step_dt / ang_bound) * (float)ML4CA_REW_DANGLE_C_STERN;
-    angpen -= fabsf(da_star / step_dt / ang_bound) * (float)ML4CA_REW_DANGLE_C_STERN;
-    rew += pen + fmaxf(-1.0f, angpen);
+    const float kd = inv_dt * (float)(ML4CA_REW_DTHRUST_C / 100.0);
+    const float pen = (fabsf(thrust[0] - old_thrust[0]) + fabsf(thrust[1] - old_thrust[1]) +
+                       fabsf(thrust[2] - old_thrust[2])) * kd;
+    const float ka = inv_dt * inv_bound;
+    const float angpen = fabsf(da_bow) * (ka * (float)ML4CA_REW_DANGLE_C_BOW) +
+                         (fabsf(da_port) + fabsf(da_star)) * (ka * (float)ML4CA_REW_DANGLE_C_STERN);
+    rew -= pen + fminf(1.0f, angpen);
   }
   return rew;
 }

@@ -183,8 +183,9 @@ int ml4ca_env_create(const ml4ca_env_cfg* cfg, int64_t n_env, int32_t device, ml
   p.n = n_env;
   for (int i = 0; i < 6; ++i) p.bounds[i] = cfg->ss_bounds[i];
   make_reset_scale(*cfg, cfg->reset_fraction, p.reset_scale);
-  p.sim_dt = cfg->sim_dt;
-  p.step_dt = cfg->step_dt;
+  p.inv_step_dt = 1.0f / cfg->step_dt;
+  p.pad1 = 0.f;
+  p.hull = hull_consts(cfg->sim_dt);
   p.n_sub = cfg->n_substeps;
   p.max_ep_len = cfg->max_ep_len;
   p.auto_reset = cfg->auto_reset;

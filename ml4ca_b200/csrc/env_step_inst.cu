@@ -1,6 +1,8 @@
 // env_step_inst.cu -- one translation unit per env class (compiled with -DML4CA_STEP_UNIT=0..4) so that the
 // kernel instantiations of env_kernels.cuh build in parallel.  Units: 0 full, 1 simple, 2 limited,
 // 3 final (wrapped angles), 4 final (continuous angles).
+#include <stdlib.h>
+
 #include "env_kernels.cuh"
 
 #ifndef ML4CA_STEP_UNIT
@@ -43,9 +45,19 @@ static int launch_step_vec(const ml4ca_env* e, const float* action, float* obs, 
   const bool vec4 = (n % 4 == 0) && aligned16(action) && aligned16(obs) && aligned16(rew) &&
                     ((reinterpret_cast<uintptr_t>(done) & 3u) == 0);
   const int threads = 256;
-  if (vec4) {
+  // One env per thread is the default: the kernel is issue-bound (~1000 instructions per env-step), and 48
+  // resident warps of the 40-register scalar variant hide latency better than the 128-register float4 variant
+  // (measured on B200, profiles/env_step_r1.md: 0.64 ms vs 0.73 ms (x2) vs 0.82 ms (x4) for 16 Mi envs).
+  static const int vec_pref = [] {   // tuning knob: ML4CA_ENV_VEC=1|2|4
+    const char* e = getenv("ML4CA_ENV_VEC");
+    return e ? atoi(e) : 1;
+  }();
+  if (vec4 && vec_pref == 4) {
     const int64_t blocks = (n / 4 + threads - 1) / threads;
     env_step_kernel<KIND, CONT, EXT, 4><<<(unsigned)blocks, threads, 0, st>>>(e->p, action, obs, rew, done);
+  } else if (vec4 && vec_pref == 2) {
+    const int64_t blocks = (n / 2 + threads - 1) / threads;
+    env_step_kernel<KIND, CONT, EXT, 2><<<(unsigned)blocks, threads, 0, st>>>(e->p, action, obs, rew, done);
   } else {
     const int64_t blocks = (n + threads - 1) / threads;
     env_step_kernel<KIND, CONT, EXT, 1><<<(unsigned)blocks, threads, 0, st>>>(e->p, action, obs, rew, done);

@@ -195,7 +195,8 @@ def test_full_size_properties(cuda_device):
     assert bool((st['prev_thrust'] == (a[:3] * 100).clamp(-100, 100)).all())
     assert bool((st['ep_len'] == 1).all())
     o2, _, _, _ = env.step(a)
-    assert bool((o2[6:9] == st['prev_thrust'] / 100.0).all())           # obs tail = previous step's thrust / 100
+    hundred = torch.full_like(st['prev_thrust'], 100.0)   # tensor divisor: torch turns '/ scalar' into '* (1/scalar)'
+    assert bool((o2[6:9] == st['prev_thrust'] / hundred).all())         # obs tail = previous step's thrust / 100
 
 
 def test_bad_arguments_raise(cuda_device):

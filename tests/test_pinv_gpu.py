@@ -25,7 +25,13 @@ def test_pinv_pid_matches_oracle(cuda_device, n):
         np.testing.assert_allclose(tau.cpu().numpy(), wtau, rtol=2e-6, atol=2e-4)
         # allocation parity is checked from the kernel's own (saturated, fp32) wrench
         wn2, wa2 = PO.allocate(tau.cpu().numpy().astype(np.float64))
-        np.testing.assert_allclose(n_pct.cpu().numpy(), wn2, rtol=2e-6, atol=2e-4)
+        # n = sign(F) sqrt(|F| / K) amplifies fp32 rounding of F near zero (dn = dF / (2 K n)): compare the
+        # physical force K n |n| everywhere and the percentage where the thruster is actually loaded.
+        K = np.asarray(C.K_THRUST)[:, None]
+        got = n_pct.cpu().numpy().astype(np.float64)
+        np.testing.assert_allclose(K * got * np.abs(got), K * wn2 * np.abs(wn2), rtol=1e-5, atol=5e-5)
+        loaded = np.abs(wn2) > 10.0
+        np.testing.assert_allclose(got[loaded], wn2[loaded], rtol=2e-5, atol=0)
         big = np.hypot(*(np.linalg.pinv(PO.config_matrix()) @ tau.cpu().numpy().astype(np.float64))[0:2]) > 1e-3
         d = np.angle(np.exp(1j * (alpha.cpu().numpy() - wa2)))
         assert np.abs(d[0][big]).max() < 1e-5
