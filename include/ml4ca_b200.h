@@ -109,6 +109,19 @@ ML4CA_API int ml4ca_pinv_pid(int64_t n, const float* eta, const float* nu, const
 /* Allocation only: tau [3, n] -> n_pct [3, n], alpha [2, n]. */
 ML4CA_API int ml4ca_pinv_allocate(int64_t n, const float* tau, float* n_pct, float* alpha, void* stream);
 
+/* QPTA.solve_QP (src/qp/ROS/qp_allocator/src/qp_allocator.py:108-234): tau [3, n] desired wrench, prev [5, n]
+ * previous thruster state [f_port, f_star, f_bow, a_port, a_star] -> x [8, n] = [f(3), a(2), s(3)] after the
+ * |x| < 0.01 clean-up (:232), status [n]: bit 0 = success (the reference's second return value; on failure the
+ * caller holds the previous state, :267-269), bits 1..16 = active set at x (bits 1-5 z_i at its lower effective
+ * bound, 6-10 upper, 11-13 s_i = -1, 14-16 s_i = +1), bits 24..31 = SQP iterations.  Never fails on infeasible
+ * demands: it reports success = 0, like the reference. */
+ML4CA_API int ml4ca_qp_solve(int64_t n, const float* tau, const float* prev, float* x, uint32_t* status, void* stream);
+/* QPTA.tau_controller_callback_func (:247-320): solve + post-processing + state update.  prev [5, n] is updated
+ * in place to [F, mapToPi(alpha)] (held where the solve failed); out [7, n] = thrust percent n_port, n_star, n_bow
+ * (n = sign(F/K) sqrt(|F/K|), :284-288), azimuths a_port, a_star, a_bow in rad mapped to [-pi, pi) (:276-277), bow
+ * throttle clip(2.5 n_bow, +-100) (:307, SIMULATION = False).  status as above (nullable). */
+ML4CA_API int ml4ca_qp_allocate(int64_t n, const float* tau, float* prev, float* out, uint32_t* status, void* stream);
+
 ML4CA_API const char* ml4ca_last_error(void);
 /* "ml4ca_b200 <version> sm_100a" */
 ML4CA_API const char* ml4ca_version(void);

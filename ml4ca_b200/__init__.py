@@ -4,6 +4,7 @@ Host-side mirrors of the reference interfaces, all backed by hand-written CUDA k
 C ABI of libml4ca_b200.so (include/ml4ca_b200.h):
 
   env.Revolt / RevoltSimple / RevoltLimited / RevoltFinal, ErrorFrame   (specific/customEnv.py, errorFrame.py)
+  qp_allocator.QPTA (solve_QP, tau_controller_callback_func)            (src/qp/ROS/qp_allocator/src/qp_allocator.py)
   pinv.pinv_pid, pinv.pinv_allocate                                      (dp_controller, absent from the reference)
 
 The package never imports ``oracle`` and has no CPU fallback.
@@ -11,5 +12,6 @@ The package never imports ``oracle`` and has no CPU fallback.
 from . import _lib  # noqa: F401
 from .env import ErrorFrame, Revolt, RevoltFinal, RevoltLimited, RevoltSimple  # noqa: F401
 from .pinv import pinv_allocate, pinv_pid  # noqa: F401
+from .qp_allocator import QPTA  # noqa: F401
 
 __version__ = "0.1.0"

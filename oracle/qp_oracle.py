@@ -129,6 +129,140 @@ def solve_tight(tau, prev, x0=None):
     return np.array(sol.x, dtype=np.float64), bool(sol.success), int(sol.nit)
 
 
+def reduced_gradient(z, tau, prev):
+    """Gradient of the reduced objective Phi(z) = 1/2|s(z)|^2 + 1/2 sum|f|^3 + 1/8|z - z_prev|^2 with the slack
+    eliminated (s = B(a) f - tau), its residual s and the 3x5 Jacobian of s."""
+    z = np.asarray(z, dtype=np.float64)
+    x8 = np.concatenate([z, np.zeros(3)])
+    J = _eq_jac(x8)[:, 0:5]
+    res = wrench_rows(z[0:3], z[3:5]) - np.asarray(tau, dtype=np.float64).reshape(3)
+    g = J.T @ res + _objective_grad(np.concatenate([z, res]), prev)[0:5]
+    return g, res, J
+
+
+def kkt_residual(x, tau, prev, act_tol=1e-5):
+    """First-order optimality measure of a candidate solution x (8,) of the reference NLP, independent of how it
+    was computed.  Returns (stationarity residual relative to 1 + |g|, max constraint violation, active mask).
+
+    Constraints within act_tol of their bound count as active; the multipliers are the non-negative
+    least-squares solution of  g + sum_b lambda_b n_b = 0  over the outward normals of the active set.
+    """
+    from scipy.optimize import nnls
+    x = np.asarray(x, dtype=np.float64)
+    z = x[0:5]
+    g, res, J = reduced_gradient(z, tau, prev)
+    lo, hi = box(prev)
+    normals = []
+    mask = 0
+    for i in range(5):
+        e = np.zeros(5)
+        e[i] = 1.0
+        if z[i] <= lo[i] + act_tol:
+            normals.append(-e)
+            mask |= 1 << i
+        if z[i] >= hi[i] - act_tol:
+            normals.append(e)
+            mask |= 1 << (5 + i)
+    for i in range(3):
+        if res[i] <= -C.QP_SLACK_BOUND + act_tol:
+            normals.append(-J[i])
+            mask |= 1 << (10 + i)
+        if res[i] >= C.QP_SLACK_BOUND - act_tol:
+            normals.append(J[i])
+            mask |= 1 << (13 + i)
+    if normals:
+        N = np.array(normals).T
+        lam, rnorm = nnls(N, -g)
+    else:
+        rnorm = float(np.linalg.norm(g))
+    viol = max(float(np.max(lo - z)), float(np.max(z - hi)), float(np.max(np.abs(res)) - C.QP_SLACK_BOUND), 0.0)
+    slack_err = float(np.max(np.abs(x[5:8] - res)))
+    return rnorm / (1.0 + float(np.linalg.norm(g))), max(viol, slack_err), mask
+
+
+def solve_converged(tau, prev):
+    """The converged KKT point in the basin the reference solver lands in: stock solve (same path as the
+    reference) -> tightened SLSQP restart from that point -> Newton polish of the KKT equations on the identified
+    active set (float64).  Returns (raw x (8,), success of the stock solve, kkt residual)."""
+    x_stock, ok, raw = solve_stock(tau, prev)
+    if not ok:
+        return raw, False, np.inf
+    xt, okt, _ = solve_tight(tau, prev, x0=raw)
+    best = raw
+    rb = kkt_residual(raw, tau, prev)[0]
+    rt = kkt_residual(xt, tau, prev)[0]
+    if np.all(np.isfinite(xt)) and rt < rb:
+        best, rb = xt, rt
+    xp = _newton_polish(best, tau, prev)
+    if xp is not None:
+        rp = kkt_residual(xp, tau, prev)
+        if rp[0] <= rb and rp[1] < 1e-9:
+            best, rb = xp, rp[0]
+    return best, True, rb
+
+
+def _newton_polish(x, tau, prev, iters=8):
+    """Newton on the KKT equations with the active set of x held fixed (finite-difference Jacobian, float64)."""
+    tau = np.asarray(tau, dtype=np.float64).reshape(3)
+    z0 = np.asarray(x[0:5], dtype=np.float64).copy()
+    lo, hi = box(prev)
+    _, res0, _ = reduced_gradient(z0, tau, prev)
+    fixed = {}
+    for i in range(5):
+        if z0[i] <= lo[i] + 1e-5:
+            fixed[i] = lo[i]
+        elif z0[i] >= hi[i] - 1e-5:
+            fixed[i] = hi[i]
+    free = [i for i in range(5) if i not in fixed]
+    sact = [(i, np.sign(res0[i]) * C.QP_SLACK_BOUND) for i in range(3) if abs(res0[i]) >= C.QP_SLACK_BOUND - 1e-5]
+    if len(sact) > len(free):
+        return None
+    nf, ns = len(free), len(sact)
+
+    def unpack(v):
+        z = z0.copy()
+        for i, val in fixed.items():
+            z[i] = val
+        for k, i in enumerate(free):
+            z[i] = v[k]
+        return z, v[nf:]
+
+    def F(v):
+        z, mu = unpack(v)
+        g, res, J = reduced_gradient(z, tau, prev)
+        r1 = g[free] + (J[[i for i, _ in sact]][:, free].T @ mu if ns else 0.0)
+        r2 = np.array([res[i] - t for i, t in sact])
+        return np.concatenate([r1, r2])
+
+    v = np.concatenate([[z0[i] for i in free], np.zeros(ns)])
+    if ns:   # least-squares multipliers to start from
+        g, res, J = reduced_gradient(unpack(v)[0], tau, prev)
+        A = J[[i for i, _ in sact]][:, free].T
+        v[nf:] = np.linalg.lstsq(A, -g[free], rcond=None)[0]
+    for _ in range(iters):
+        f0 = F(v)
+        if np.max(np.abs(f0)) < 1e-13:
+            break
+        n = len(v)
+        Jac = np.zeros((n, n))
+        for k in range(n):
+            h = 1e-7 * (1.0 + abs(v[k]))
+            vp = v.copy()
+            vp[k] += h
+            vm = v.copy()
+            vm[k] -= h
+            Jac[:, k] = (F(vp) - F(vm)) / (2 * h)
+        try:
+            v = v - np.linalg.solve(Jac, f0)
+        except np.linalg.LinAlgError:
+            return None
+    z, _ = unpack(v)
+    if not np.all(np.isfinite(z)):
+        return None
+    _, res, _ = reduced_gradient(z, tau, prev)
+    return np.concatenate([z, res])
+
+
 def box(prev):
     """Effective box of the reduced variables z = [f(3), a(2)]: bounds intersected with the rate limits."""
     prev = np.asarray(prev, dtype=np.float64)
