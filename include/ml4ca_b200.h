@@ -122,6 +122,42 @@ ML4CA_API int ml4ca_qp_solve(int64_t n, const float* tau, const float* prev, flo
  * throttle clip(2.5 n_bow, +-100) (:307, SIMULATION = False).  status as above (nullable). */
 ML4CA_API int ml4ca_qp_allocate(int64_t n, const float* tau, float* prev, float* out, uint32_t* status, void* stream);
 
+/* ---- PPO actor/critic MLP (spinup/algos/tf1/ppo/core.py:29-33,42-46,80-107 of src/rl/windows_workspace) ---------
+ * Supported networks: hidden 64x64 (BASELINE config), 64x64x64 and 80x80x80 (the shipped checkpoints); obs_dim <= 15,
+ * act_dim <= 7.  Parameters are one flat fp32 vector in the reference's variable order:
+ *   pi/dense/kernel [obs,H], pi/dense/bias [H], pi/dense_1/..., pi/dense_k/kernel [H,act], bias [act], pi/log_std [act],
+ *   v/dense/kernel [obs,H], ..., v/dense_k/kernel [H,1], bias [1]            (kernels row-major [in, out]). */
+typedef struct ml4ca_policy_cfg {
+  int32_t obs_dim, act_dim;
+  int32_t hidden, n_hidden;
+  int32_t activation; /* 0 tanh (core.py:94 default), 1 leaky_relu alpha 0.2 (train.py:24,31; every shipped model) */
+  int32_t reserved;
+} ml4ca_policy_cfg;
+typedef struct ml4ca_policy ml4ca_policy;
+
+ML4CA_API int64_t ml4ca_policy_num_params(const ml4ca_policy_cfg* cfg);
+/* params_host: ml4ca_policy_num_params floats in HOST memory (NULL = zeros).  The library keeps an fp32 master copy
+ * on the device and the fp16 tensor-core operand image derived from it. */
+ML4CA_API int ml4ca_policy_create(const ml4ca_policy_cfg* cfg, const float* params_host, int32_t device, ml4ca_policy** out);
+ML4CA_API int ml4ca_policy_destroy(ml4ca_policy* p);
+/* device pointer of the fp32 master parameters (an optimizer updates them in place) ... */
+ML4CA_API float* ml4ca_policy_params(ml4ca_policy* p);
+/* ... and re-derives the operand image afterwards */
+ML4CA_API int ml4ca_policy_refresh(ml4ca_policy* p, void* stream);
+/* get_action_ops = [pi, v, logp_pi] of ppo.py:221,291: obs [obs_dim, n] -> act [act_dim, n] = mu + eps * exp(log_std)
+ * (eps ~ N(0,1) from Philox keyed by (seed, env_id_offset + i, step); deterministic != 0: act = mu, the evaluation
+ * action pi/dense_k/BiasAdd of test_policy.py:90), val [n], logp [n], mu [act_dim, n] (nullable). */
+ML4CA_API int ml4ca_policy_forward(ml4ca_policy* p, int64_t n, const float* obs, uint64_t seed, uint32_t step,
+                                   int32_t deterministic, int64_t env_id_offset, float* act, float* val, float* logp,
+                                   float* mu, void* stream);
+
+/* One fused rollout step = ppo.py:291-293 (`sess.run(get_action_ops)` then `env.step(a)`) for every environment of
+ * `env` (RevoltFinal, extended state, continuous angles; 9 -> 7 policy): observation from the state in HBM -> tcgen05
+ * MLP -> sampled action -> env step, in ONE kernel.  Trajectory records of this time step (each nullable):
+ * obs [9, n] = the observation the policy saw, act [7, n], rew [n], val [n], logp [n], done [n] flags. */
+ML4CA_API int ml4ca_rollout_step(ml4ca_env* env, ml4ca_policy* p, uint64_t seed, uint32_t step, int32_t deterministic,
+                                 float* obs, float* act, float* rew, float* val, float* logp, uint8_t* done, void* stream);
+
 ML4CA_API const char* ml4ca_last_error(void);
 /* "ml4ca_b200 <version> sm_100a" */
 ML4CA_API const char* ml4ca_version(void);

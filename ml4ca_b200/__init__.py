@@ -5,6 +5,7 @@ C ABI of libml4ca_b200.so (include/ml4ca_b200.h):
 
   env.Revolt / RevoltSimple / RevoltLimited / RevoltFinal, ErrorFrame   (specific/customEnv.py, errorFrame.py)
   qp_allocator.QPTA (solve_QP, tau_controller_callback_func)            (src/qp/ROS/qp_allocator/src/qp_allocator.py)
+  core.ActorCritic / mlp_actor_critic (tcgen05 MLP forward)              (spinup/algos/tf1/ppo/core.py)
   pinv.pinv_pid, pinv.pinv_allocate                                      (dp_controller, absent from the reference)
 
 The package never imports ``oracle`` and has no CPU fallback.
@@ -13,5 +14,7 @@ from . import _lib  # noqa: F401
 from .env import ErrorFrame, Revolt, RevoltFinal, RevoltLimited, RevoltSimple  # noqa: F401
 from .pinv import pinv_allocate, pinv_pid  # noqa: F401
 from .qp_allocator import QPTA  # noqa: F401
+from .core import ActorCritic, mlp_actor_critic  # noqa: F401
+from .ppo import TrajectoryBuffer, rollout  # noqa: F401
 
 __version__ = "0.1.0"

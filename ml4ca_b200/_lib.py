@@ -27,6 +27,12 @@ class EnvCfg(ctypes.Structure):
     ]
 
 
+class PolicyCfg(ctypes.Structure):
+    """struct ml4ca_policy_cfg"""
+    _fields_ = [("obs_dim", ctypes.c_int32), ("act_dim", ctypes.c_int32), ("hidden", ctypes.c_int32),
+                ("n_hidden", ctypes.c_int32), ("activation", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
 class Ml4caError(RuntimeError):
     pass
 
@@ -50,6 +56,15 @@ _SIGNATURES = {
     "ml4ca_pinv_allocate": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_stream]),
     "ml4ca_qp_solve": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, ctypes.c_void_p, c_stream]),
     "ml4ca_qp_allocate": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, ctypes.c_void_p, c_stream]),
+    "ml4ca_policy_num_params": (ctypes.c_int64, [ctypes.POINTER(PolicyCfg)]),
+    "ml4ca_policy_create": (ctypes.c_int, [ctypes.POINTER(PolicyCfg), ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
+    "ml4ca_policy_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "ml4ca_policy_params": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "ml4ca_policy_refresh": (ctypes.c_int, [ctypes.c_void_p, c_stream]),
+    "ml4ca_policy_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_f32p, ctypes.c_uint64, ctypes.c_uint32,
+                                            ctypes.c_int32, ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_stream]),
+    "ml4ca_rollout_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32,
+                                          c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_stream]),
     "ml4ca_last_error": (ctypes.c_char_p, []),
     "ml4ca_version": (ctypes.c_char_p, []),
     "ml4ca_launch_count": (ctypes.c_int64, []),

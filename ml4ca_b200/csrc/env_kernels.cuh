@@ -30,6 +30,7 @@ struct EnvParams {
   float* ref;          // [3, n]
   float* prev_thrust;  // [3, n]
   float* angles;       // [3, n] bow, port, star
+  float* obs_tail;     // [3, n] tail (prev_thrust / 100) of the last returned observation; fused rollout only
   int32_t* ep_len;     // [n]
   int32_t* episode;    // [n]
   int64_t n;
@@ -50,6 +51,7 @@ struct ml4ca_env {
   int64_t n;
   int32_t device;
   void* slab;
+  bool tail_valid;     // obs_tail rows describe the last returned observation (reset / fused steps keep it so)
   ml4ca::EnvParams p;
 };
 
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(256) env_reset_kernel(const EnvParams p, const
   p.nu[i] = u, p.nu[n + i] = v, p.nu[2 * n + i] = r;
   p.prev_thrust[i] = 0.f, p.prev_thrust[n + i] = 0.f, p.prev_thrust[2 * n + i] = 0.f;  // customEnv.py:190
   p.angles[i] = T::DEF_BOW, p.angles[n + i] = T::DEF_PORT, p.angles[2 * n + i] = T::DEF_STAR;  // :173-177,192
+  p.obs_tail[i] = 0.f, p.obs_tail[n + i] = 0.f, p.obs_tail[2 * n + i] = 0.f;
   p.ep_len[i] = 0;
   if (obs != nullptr) {
     float xb, yb, pb;

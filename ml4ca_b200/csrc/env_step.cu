@@ -156,10 +156,11 @@ int ml4ca_env_create(const ml4ca_env_cfg* cfg, int64_t n_env, int32_t device, ml
   e->cfg = *cfg;
   e->n = n_env;
   e->device = device;
-  // one slab: 15 fp32 rows + 2 int32 rows, each row padded to a 16-byte multiple so that every row start is
+  e->tail_valid = true;
+  // one slab: 18 fp32 rows + 2 int32 rows, each row padded to a 16-byte multiple so that every row start is
   // float4-aligned whenever n % 4 == 0 (rows are indexed with stride n, so the padding only sits at the end).
   const size_t row = (size_t)n_env * sizeof(float);
-  const size_t bytes = 17 * row + 256;
+  const size_t bytes = 20 * row + 256;
   cudaError_t ce = cudaMalloc(&e->slab, bytes);
   if (ce != cudaSuccess) {
     delete e;
@@ -178,8 +179,9 @@ int ml4ca_env_create(const ml4ca_env_cfg* cfg, int64_t n_env, int32_t device, ml
   p.ref = f + 6 * n_env;
   p.prev_thrust = f + 9 * n_env;
   p.angles = f + 12 * n_env;
-  p.ep_len = reinterpret_cast<int32_t*>(f + 15 * n_env);
-  p.episode = reinterpret_cast<int32_t*>(f + 16 * n_env);
+  p.obs_tail = f + 15 * n_env;
+  p.ep_len = reinterpret_cast<int32_t*>(f + 18 * n_env);
+  p.episode = reinterpret_cast<int32_t*>(f + 19 * n_env);
   p.n = n_env;
   for (int i = 0; i < 6; ++i) p.bounds[i] = cfg->ss_bounds[i];
   make_reset_scale(*cfg, cfg->reset_fraction, p.reset_scale);
@@ -211,6 +213,7 @@ int ml4ca_env_reset(ml4ca_env* env, const uint8_t* mask, float fraction, float* 
   DeviceGuard guard(env->device);
   EnvParams p = env->p;
   make_reset_scale(env->cfg, fraction, p.reset_scale);
+  if (mask == nullptr) env->tail_valid = true;
   return launch_reset(env, p, mask, nullptr, nullptr, obs, static_cast<cudaStream_t>(stream));
 }
 
@@ -219,6 +222,7 @@ int ml4ca_env_reset_to(ml4ca_env* env, const uint8_t* mask, const float* eta, co
   ML4CA_REQUIRE(env != nullptr, "env is NULL");
   ML4CA_REQUIRE(eta != nullptr && nu != nullptr, "eta and nu are required");
   DeviceGuard guard(env->device);
+  if (mask == nullptr) env->tail_valid = true;
   return launch_reset(env, env->p, mask, eta, nu, obs, static_cast<cudaStream_t>(stream));
 }
 
@@ -235,6 +239,7 @@ int ml4ca_env_step(ml4ca_env* env, const float* action, float* obs, float* rew, 
   ML4CA_REQUIRE(action != nullptr && obs != nullptr && rew != nullptr && done != nullptr,
                 "action, obs, rew and done are required");
   DeviceGuard guard(env->device);
+  env->tail_valid = false;   // the tail of the returned observation now lives in the caller's obs buffer only
   return launch_step(env, action, obs, rew, done, static_cast<cudaStream_t>(stream));
 }
 

@@ -12,6 +12,7 @@ env_<kind>_<mode>.npz : reference customEnv classes driven through the DigiTwin 
 qp_config1.npz        : reference QPTA.solve_QP + tau_controller_callback_func post-processing on the
                         SURVEY.md section 8(d) config-1 demand distribution (container SciPy, see
                         oracle/qp_oracle.py header), rospy.get_time() pinned to 0.
+policy_*.npz          : the shipped TF1 checkpoints' actor/critic weights, read by ml4ca_b200/tf_checkpoint.py
 gae.npz               : reference core.discount_cumsum formulation (scipy.signal.lfilter) and the
                         TrajectoryBuffer.finish_path arithmetic (ppo.py:82-91).
 """
@@ -116,6 +117,22 @@ def gen_gae(seed):
             'adv': adv, 'ret': ret}
 
 
+def gen_policy():
+    """Shipped actor/critic weights (TF1 bundle, read without TensorFlow) as flat parameter vectors."""
+    from ml4ca_b200 import tf_checkpoint
+    base = os.path.join(ref_loader.REFERENCE_ROOT, 'src', 'rl')
+    models = {
+        'final_80x3': os.path.join(base, 'windows_workspace', 'data', 'finalmodel', 'finconttothighbowder_s0', 'tf1_save'),
+        'limited_64x3': os.path.join(base, 'ROS', 'rl_allocator', 'src', 'models', 'limited', 'tf1_save'),
+    }
+    for tag, path in models.items():
+        flat, dims = tf_checkpoint.load_actor_critic(path)
+        np.savez_compressed(os.path.join(HERE, 'policy_%s.npz' % tag), params=flat,
+                            **{k: np.array(v) for k, v in dims.items()}, activation=np.array('leaky_relu'),
+                            source=np.array(os.path.relpath(path, ref_loader.REFERENCE_ROOT)))
+        print('wrote policy_%s.npz' % tag, dims, flat.shape)
+
+
 def main():
     assert ref_loader.available(), "reference checkout not found"
     cases = [
@@ -140,6 +157,7 @@ def main():
     print('wrote qp_config1.npz  success rate %.3f' % out['success'].mean())
     np.savez_compressed(os.path.join(HERE, 'gae.npz'), **gen_gae(7))
     print('wrote gae.npz')
+    gen_policy()
 
 
 if __name__ == '__main__':
