@@ -158,6 +158,16 @@ ML4CA_API int ml4ca_policy_forward(ml4ca_policy* p, int64_t n, const float* obs,
 ML4CA_API int ml4ca_rollout_step(ml4ca_env* env, ml4ca_policy* p, uint64_t seed, uint32_t step, int32_t deterministic,
                                  float* obs, float* act, float* rew, float* val, float* logp, uint8_t* done, void* stream);
 
+/* TrajectoryBuffer.finish_path for every environment (ppo.py:65-91; core.discount_cumsum core.py:48-63):
+ * rew [T, n], val [T + 1, n] (row T = bootstrap values at the buffer end, ppo.py:311), done [T, n] flag bytes
+ * (nullable), boot [T, n] (nullable) = V(s_{t+1}) at episode-length cuts -> adv [T, n], ret [T, n]. */
+ML4CA_API int ml4ca_gae(int64_t n, int32_t T, const float* rew, const float* val, const uint8_t* done, const float* boot,
+                        float gamma, float lam, float* adv, float* ret, void* stream);
+/* mpi_statistics_scalar (mpi_tools.py:71-93), local part: out3 (device, 3 doubles) = [sum, sum of squares, count]. */
+ML4CA_API int ml4ca_stats(int64_t m, const float* x, double* out3, void* stream);
+/* advantage normalisation x <- (x - mean) / (std + 1e-8) (ppo.py:103). */
+ML4CA_API int ml4ca_normalize(int64_t m, float* x, float mean, float std, void* stream);
+
 ML4CA_API const char* ml4ca_last_error(void);
 /* "ml4ca_b200 <version> sm_100a" */
 ML4CA_API const char* ml4ca_version(void);

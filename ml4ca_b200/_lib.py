@@ -65,6 +65,10 @@ _SIGNATURES = {
                                             ctypes.c_int32, ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_stream]),
     "ml4ca_rollout_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32,
                                           c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_stream]),
+    "ml4ca_gae": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_u8p, c_f32p, ctypes.c_float, ctypes.c_float,
+                                 c_f32p, c_f32p, c_stream]),
+    "ml4ca_stats": (ctypes.c_int, [ctypes.c_int64, c_f32p, ctypes.c_void_p, c_stream]),
+    "ml4ca_normalize": (ctypes.c_int, [ctypes.c_int64, c_f32p, ctypes.c_float, ctypes.c_float, c_stream]),
     "ml4ca_last_error": (ctypes.c_char_p, []),
     "ml4ca_version": (ctypes.c_char_p, []),
     "ml4ca_launch_count": (ctypes.c_int64, []),

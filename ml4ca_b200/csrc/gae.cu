@@ -1,0 +1,114 @@
+// gae.cu -- K5: GAE-lambda advantages and rewards-to-go over a [T, n_env] trajectory buffer.
+//
+// Replaces TrajectoryBuffer.finish_path / get (/root/reference/src/rl/windows_workspace/spinup/algos/tf1/ppo/ppo.py:65-105)
+// and core.discount_cumsum (core.py:48-63, scipy.signal.lfilter):
+//     delta_t = r_t + gamma V_{t+1} - V_t ;  A_t = sum_k (gamma lam)^k delta_{t+k} ;  R_t = sum_k gamma^k r_{t+k} (+ bootstrap)
+// The reference calls finish_path once per trajectory with last_val = 0 if the episode died, else V(o) (ppo.py:311).
+// Batched form: one thread per environment scans its column backwards; the per-step flag byte written by the env
+// kernels (bit 0 terminal, bit 1 episode-length cut) marks the path ends inside the buffer:
+//     terminal  -> last_val = 0
+//     cut       -> last_val = boot[t] if given, else V_t  (the reference evaluates V on the post-step observation;
+//                  with in-kernel restarts that observation is gone, so V of the last observed state stands in)
+//     buffer end-> last_val = val[T]  (row T of the value buffer: the epoch-end bootstrap)
+// HBM-bound: 17 algorithmic bytes per (step, env): read r, V, flag; write A, R.  Coalesced across environments.
+#include "common.h"
+
+namespace ml4ca {
+
+__global__ void __launch_bounds__(256) gae_kernel(int64_t n, int T, const float* __restrict__ rew,
+                                                  const float* __restrict__ val, const uint8_t* __restrict__ done,
+                                                  const float* __restrict__ boot, float gamma, float lam,
+                                                  float* __restrict__ adv, float* __restrict__ ret) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gl = gamma * lam;
+  float next_val = val[(int64_t)T * n + i];
+  float next_adv = 0.f;
+  float next_ret = next_val;
+  for (int t = T - 1; t >= 0; --t) {
+    const int64_t k = (int64_t)t * n + i;
+    const float r = rew[k], v = val[k];
+    const uint32_t f = done != nullptr ? done[k] : 0u;
+    if (f & ML4CA_DONE_TERMINAL) {
+      next_val = 0.f, next_adv = 0.f, next_ret = 0.f;
+    } else if (f & ML4CA_DONE_TRUNCATED) {
+      next_val = boot != nullptr ? boot[k] : v;
+      next_adv = 0.f, next_ret = next_val;
+    }
+    const float delta = r + gamma * next_val - v;      // ppo.py:86
+    const float a = delta + gl * next_adv;              // discount_cumsum(deltas, gamma * lam), :87
+    const float g = r + gamma * next_ret;               // discount_cumsum(rews, gamma)[:-1], :90
+    adv[k] = a;
+    ret[k] = g;
+    next_val = v, next_adv = a, next_ret = g;
+  }
+}
+
+// [sum, sum of squares, count] of x in double (mpi_statistics_scalar, mpi_tools.py:71-93: the caller all-reduces the
+// three numbers over ranks before forming mean / std).
+__global__ void __launch_bounds__(256) stats_kernel(int64_t m, const float* __restrict__ x, double* __restrict__ out3) {
+  double s = 0.0, q = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = (double)x[i];
+    s += v;
+    q += v * v;
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+    q += __shfl_xor_sync(0xFFFFFFFFu, q, off);
+  }
+  __shared__ double ss[8], qq[8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) ss[w] = s, qq[w] = q;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0.0, Q = 0.0;
+    for (int k = 0; k < 8; ++k) S += ss[k], Q += qq[k];
+    atomicAdd(out3, S);
+    atomicAdd(out3 + 1, Q);
+    if (blockIdx.x == 0) atomicAdd(out3 + 2, (double)m);
+  }
+}
+
+// x <- (x - mean) / (std + 1e-8)   (ppo.py:103)
+__global__ void __launch_bounds__(256) normalize_kernel(int64_t m, float* __restrict__ x, float mean, float inv) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) x[i] = (x[i] - mean) * inv;
+}
+
+}  // namespace ml4ca
+
+using namespace ml4ca;
+
+extern "C" {
+
+int ml4ca_gae(int64_t n, int32_t T, const float* rew, const float* val, const uint8_t* done, const float* boot,
+              float gamma, float lam, float* adv, float* ret, void* stream) {
+  ML4CA_REQUIRE(n >= 0 && T >= 0 && rew && val && adv && ret, "bad arguments");
+  if (n == 0 || T == 0) return ML4CA_OK;
+  gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, T, rew, val, done, boot, gamma,
+                                                                                       lam, adv, ret);
+  return check_launch("gae_kernel");
+}
+
+int ml4ca_stats(int64_t m, const float* x, double* out3, void* stream) {
+  ML4CA_REQUIRE(m >= 0 && x && out3, "bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ML4CA_CUDA(cudaMemsetAsync(out3, 0, 3 * sizeof(double), st));
+  if (m == 0) return ML4CA_OK;
+  const int64_t want = (m + 255) / 256;
+  const unsigned blocks = (unsigned)(want < 4 * kNumSMs ? want : 4 * kNumSMs);
+  stats_kernel<<<blocks, 256, 0, st>>>(m, x, out3);
+  return check_launch("stats_kernel");
+}
+
+int ml4ca_normalize(int64_t m, float* x, float mean, float std, void* stream) {
+  ML4CA_REQUIRE(m >= 0 && x, "bad arguments");
+  if (m == 0) return ML4CA_OK;
+  normalize_kernel<<<(unsigned)((m + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(m, x, mean,
+                                                                                             1.0f / (std + 1e-8f));
+  return check_launch("normalize_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+"""Collectives of the PPO path: the reference's MPI helpers on torch.distributed (NCCL over NVLink on GPUs).
+
+Mirrors /root/reference/src/rl/windows_workspace/spinup/utils/mpi_tools.py (proc_id, num_procs, mpi_avg,
+mpi_statistics_scalar :43-93) and mpi_tf.py (sync_all_params :24, the gradient average inside
+MpiAdamOptimizer.compute_gradients :45-70).  One process per GPU; the environments shard by global
+index with no data-path collective -- these calls only carry gradients (one flat fp32 buffer per
+optimizer step) and a handful of scalars.  With a single process every function is the identity.
+The reference's per-step parameter Bcast (mpi_tf.py:72-80) is dropped: every rank applies the same
+averaged gradient deterministically, so one broadcast at start-up (sync_all_params) suffices.
+"""
+import torch
+import torch.distributed as dist
+
+
+def _on():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def proc_id():
+    return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+
+
+def num_procs():
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def shard_bounds(n_global, rank=None, world=None):
+    """Global env index range [lo, hi) of a rank: contiguous blocks, remainder spread over the first ranks."""
+    rank = proc_id() if rank is None else rank
+    world = num_procs() if world is None else world
+    base, rem = divmod(int(n_global), world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_sum_(t):
+    """In-place sum over ranks (mpi_tools.allreduce :47-52)."""
+    if _on():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def mpi_avg(x):
+    """Average a scalar / tensor over ranks (:67-69)."""
+    t = x if torch.is_tensor(x) else torch.tensor(float(x), dtype=torch.float64)
+    if not _on():
+        return x
+    t = t.clone()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    t /= num_procs()
+    return t if torch.is_tensor(x) else float(t.item())
+
+
+def average_gradients_(flat_grad):
+    """MpiAdamOptimizer.compute_gradients (mpi_tf.py:59-62): Allreduce(SUM) of the flat gradient, divided by the
+    number of ranks -- ONE collective per optimizer step on one contiguous buffer."""
+    if _on():
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+        flat_grad /= num_procs()
+    return flat_grad
+
+
+def sync_all_params(flat_params, root=0):
+    """sync_all_params (mpi_tf.py:24-27): broadcast rank 0's parameters once."""
+    if _on():
+        dist.broadcast(flat_params, src=root)
+    return flat_params
+
+
+def statistics_from_sums(sums3):
+    """[sum, sum of squares, count] (already reduced over ranks) -> (mean, std), population std like
+    mpi_statistics_scalar (:85-89: sqrt(sum((x - mean)^2) / n))."""
+    s, q, n = float(sums3[0]), float(sums3[1]), float(sums3[2])
+    mean = s / n
+    var = max(q / n - mean * mean, 0.0)
+    return mean, var ** 0.5
+
+
+def mpi_statistics_scalar(x, with_min_and_max=False):
+    """mpi_statistics_scalar (:71-93) for a tensor on any device."""
+    x = torch.as_tensor(x).to(torch.float64).reshape(-1)
+    sums = torch.stack([x.sum(), (x * x).sum(), torch.tensor(float(x.numel()), dtype=torch.float64, device=x.device)])
+    allreduce_sum_(sums)
+    mean, std = statistics_from_sums(sums.tolist())
+    if with_min_and_max:
+        lo, hi = x.min().clone(), x.max().clone()
+        if _on():
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        return mean, std, float(lo), float(hi)
+    return mean, std

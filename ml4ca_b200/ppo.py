@@ -33,6 +33,31 @@ class TrajectoryBuffer(object):
         self.done_buf = torch.zeros(T, n, dtype=torch.uint8, device=self.device)
         self.gamma, self.lam = gamma, lam
         self.ptr, self.max_size, self.num_envs = 0, T, n
+        self._sums = torch.zeros(3, dtype=torch.float64, device=self.device)
+
+    def finish_path(self, last_val=None, boot=None):
+        """ppo.py:65-91 for every environment at once: GAE-lambda advantages and rewards-to-go, with the path ends
+        taken from the recorded done flags.  ``last_val`` [n] = V(s_T) for the epoch-end bootstrap (ppo.py:311);
+        by default row T of ``val_buf`` as left by the caller."""
+        if last_val is not None:
+            self.val_buf[self.max_size].copy_(last_val)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ml4ca_gae(self.num_envs, self.max_size, _lib.ptr(self.rew_buf), _lib.ptr(self.val_buf),
+                                            _lib.ptr(self.done_buf), _lib.ptr(boot), float(self.gamma), float(self.lam),
+                                            _lib.ptr(self.adv_buf), _lib.ptr(self.ret_buf), _lib.current_stream()),
+                       "ml4ca_gae")
+
+    def get(self):
+        """ppo.py:93-105: advantage normalisation with statistics over ALL ranks, then the five training arrays."""
+        from . import mpi_tools
+        m = self.adv_buf.numel()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ml4ca_stats(m, _lib.ptr(self.adv_buf), _lib.ptr(self._sums), _lib.current_stream()))
+            mpi_tools.allreduce_sum_(self._sums)
+            mean, std = mpi_tools.statistics_from_sums(self._sums.tolist())
+            _lib.check(_lib.lib().ml4ca_normalize(m, _lib.ptr(self.adv_buf), mean, std, _lib.current_stream()))
+        self.ptr = 0
+        return [self.obs_buf, self.act_buf, self.adv_buf, self.ret_buf, self.logp_buf]
 
 
 def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, fused=False):
