@@ -22,6 +22,10 @@
 #define ML4CA_ENV_MIN_BLOCKS 6  // scalar-row kernel: 40 registers, 48 resident warps/SM (measured best on B200)
 #endif
 
+#ifndef ML4CA_ENV_MIN_BLOCKS2
+#define ML4CA_ENV_MIN_BLOCKS2 4  // two-env packed kernel: <= 64 registers
+#endif
+
 namespace ml4ca {
 
 struct EnvParams {
@@ -31,8 +35,7 @@ struct EnvParams {
   float* prev_thrust;  // [3, n]
   float* angles;       // [3, n] bow, port, star
   float* obs_tail;     // [3, n] tail (prev_thrust / 100) of the last returned observation; fused rollout only
-  int32_t* ep_len;     // [n]
-  int32_t* episode;    // [n]
+  int32_t* ep_len;     // [n] episode word: episode counter << 16 | steps in this episode (env_math.cuh)
   int64_t n;
   float bounds[6];
   float reset_scale[6];
@@ -127,7 +130,7 @@ __device__ __forceinline__ void st_flags(uint8_t* __restrict__ row, int64_t i, c
 
 // ---- K3 ------------------------------------------------------------------------------------------------------------
 template <int KIND, bool CONT, bool EXT, int VEC>
-__global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : 1) env_step_kernel(const EnvParams p, const float* __restrict__ action,
+__global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : (VEC == 2 ? ML4CA_ENV_MIN_BLOCKS2 : 1)) env_step_kernel(const EnvParams p, const float* __restrict__ action,
                                                        float* __restrict__ obs, float* __restrict__ rew,
                                                        uint8_t* __restrict__ done) {
   using T = EnvTraits<KIND, CONT>;
@@ -163,6 +166,8 @@ __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : 1) env_
   float o[9][VEC], rw[VEC];
   uint32_t flags[VEC];
   bool any_reset = false;
+  // ---- phase A: action transform, azimuth commands, thruster wrench ------------------------------------------------
+  float thr[3][VEC], dang[3][VEC], wx[VEC], wy[VEC], wn[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     float act[T::ACT], cmd[T::NCMD];
@@ -172,7 +177,10 @@ __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : 1) env_
     transform_action<KIND, CONT>(act, cmd, sat);                       // customEnv.py:104-110
     const float pa_bow = ang[0][j], pa_port = ang[1][j], pa_star = ang[2][j];  // prev_angles, :102
     apply_angle_commands<KIND, CONT>(cmd, ang[0][j], ang[1][j], ang[2][j]);    // :117-122
-    if (p.n_sub > 0) {                                                 // dTwin.step(n_steps), :124
+    dang[0][j] = ang[0][j] - pa_bow, dang[1][j] = ang[1][j] - pa_port, dang[2][j] = ang[2][j] - pa_star;
+    thr[0][j] = cmd[0], thr[1][j] = cmd[1], thr[2][j] = cmd[2];        // prev_thrust <- action[0:3], :126
+    wx[j] = wy[j] = wn[j] = 0.f;
+    if (p.n_sub > 0) {
       float sb, cb, sp, cp, ss, cs;
       if constexpr (T::NANG == 3) {
         sincosf(ang[0][j], &sb, &cb);
@@ -188,10 +196,29 @@ __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : 1) env_
         sincosf(ang[1][j], &sp, &cp);
         sincosf(ang[2][j], &ss, &cs);
       }
-      float tx, ty, tn;
-      thruster_wrench_sc(cmd[0], cmd[1], cmd[2], sb, cb, sp, cp, ss, cs, tx, ty, tn);
-      integrate_hull(eta[0][j], eta[1][j], eta[2][j], nu[0][j], nu[1][j], nu[2][j], tx, ty, tn, p.n_sub, p.hull);
+      thruster_wrench_sc(cmd[0], cmd[1], cmd[2], sb, cb, sp, cp, ss, cs, wx[j], wy[j], wn[j]);
     }
+  }
+  // ---- phase B: dTwin.step(n_steps), :124 ---------------------------------------------------------------------------
+  if (p.n_sub > 0) {
+    if constexpr (VEC == 2) {                                          // two envs per thread: packed FP32 pipe
+      float2 N = make_float2(eta[0][0], eta[0][1]), E = make_float2(eta[1][0], eta[1][1]),
+             psi = make_float2(eta[2][0], eta[2][1]), u = make_float2(nu[0][0], nu[0][1]),
+             v = make_float2(nu[1][0], nu[1][1]), r = make_float2(nu[2][0], nu[2][1]);
+      integrate_hull2(N, E, psi, u, v, r, make_float2(wx[0], wx[1]), make_float2(wy[0], wy[1]),
+                      make_float2(wn[0], wn[1]), p.n_sub, p.hull);
+      eta[0][0] = N.x, eta[0][1] = N.y, eta[1][0] = E.x, eta[1][1] = E.y, eta[2][0] = psi.x, eta[2][1] = psi.y;
+      nu[0][0] = u.x, nu[0][1] = u.y, nu[1][0] = v.x, nu[1][1] = v.y, nu[2][0] = r.x, nu[2][1] = r.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
+        integrate_hull(eta[0][j], eta[1][j], eta[2][j], nu[0][j], nu[1][j], nu[2][j], wx[j], wy[j], wn[j], p.n_sub,
+                       p.hull);
+    }
+  }
+  // ---- phase C: observation, reward, termination --------------------------------------------------------------------
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
     float xb, yb, pb;                                                  // state_extended(), :125
     error_frame(eta[0][j], eta[1][j], eta[2][j], ref[0][j], ref[1][j], ref[2][j], xb, yb, pb);
     o[0][j] = xb, o[1][j] = yb, o[2][j] = pb;
@@ -201,39 +228,33 @@ __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : 1) env_
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         old_thrust[c] = pth[c][j];
-        o[6 + c][j] = __fdiv_rn(pth[c][j], 100.0f);                    // prev_thrust / 100.0, :204 (bit-exact)
+        o[6 + c][j] = div100(pth[c][j]);                               // prev_thrust / 100.0, :204 (bit-exact)
       }
     }
-    const float thrust[3] = {cmd[0], cmd[1], cmd[2]};                  // prev_thrust <- action[0:3], :126
-    rw[j] = reward_fn<EXT>(xb, yb, pb, nu[0][j], nu[1][j], nu[2][j], thrust, old_thrust, ang[0][j] - pa_bow,
-                           ang[1][j] - pa_port, ang[2][j] - pa_star, p.inv_step_dt, 1.0f / T::ANG_BOUND);   // :128
+    const float thrust[3] = {thr[0][j], thr[1][j], thr[2][j]};
+    rw[j] = reward_fn<EXT>(xb, yb, pb, nu[0][j], nu[1][j], nu[2][j], thrust, old_thrust, dang[0][j], dang[1][j],
+                           dang[2][j], p.inv_step_dt, 1.0f / T::ANG_BOUND);                        // :128
     const bool term = is_terminal(xb, yb, pb, nu[0][j], nu[1][j], nu[2][j], p.bounds);           // :129
-    ep[j] += 1;
-    const bool trunc = ep[j] >= p.max_ep_len;                          // ppo.py:304
+    ep[j] += 1;                                                        // low half: steps in this episode
+    const bool trunc = (int32_t)((uint32_t)ep[j] & kEpLenMask) >= p.max_ep_len;   // ppo.py:304
     flags[j] = (term ? ML4CA_DONE_TERMINAL : 0u) | (trunc ? ML4CA_DONE_TRUNCATED : 0u);
 #pragma unroll
     for (int c = 0; c < 3; ++c) pth[c][j] = thrust[c];
     any_reset |= (flags[j] != 0u);
   }
 
-  {
-    if (p.auto_reset && any_reset) {  // rare (1 / episode length): keep the RNG and the extra row traffic off the common path
-      int32_t epi[VEC];
-      ld_irow<VEC>(p.episode, i0, epi);
+  if (p.auto_reset && any_reset) {  // rare (1 / episode length): keeps the RNG off the common path
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        if (flags[j] == 0u) continue;
-        sample_reset(p.seed, p.env_off + i0 + j, epi[j], p.reset_scale, eta[0][j], eta[1][j], eta[2][j], nu[0][j],
-                     nu[1][j], nu[2][j]);
-        epi[j] += 1;
-        ep[j] = 0;
-        ang[0][j] = T::DEF_BOW, ang[1][j] = T::DEF_PORT, ang[2][j] = T::DEF_STAR;
-        pth[0][j] = pth[1][j] = pth[2][j] = 0.f;
-        error_frame(eta[0][j], eta[1][j], eta[2][j], ref[0][j], ref[1][j], ref[2][j], o[0][j], o[1][j], o[2][j]);
-        o[3][j] = nu[0][j], o[4][j] = nu[1][j], o[5][j] = nu[2][j];
-        if constexpr (EXT) o[6][j] = o[7][j] = o[8][j] = 0.f;
-      }
-      st_irow<VEC>(p.episode, i0, epi);
+    for (int j = 0; j < VEC; ++j) {
+      if (flags[j] == 0u) continue;
+      sample_reset(p.seed, p.env_off + i0 + j, ep[j], p.reset_scale, eta[0][j], eta[1][j], eta[2][j], nu[0][j],
+                   nu[1][j], nu[2][j]);
+      ep[j] = next_episode_word(ep[j]);
+      ang[0][j] = T::DEF_BOW, ang[1][j] = T::DEF_PORT, ang[2][j] = T::DEF_STAR;
+      pth[0][j] = pth[1][j] = pth[2][j] = 0.f;
+      error_frame(eta[0][j], eta[1][j], eta[2][j], ref[0][j], ref[1][j], ref[2][j], o[0][j], o[1][j], o[2][j]);
+      o[3][j] = nu[0][j], o[4][j] = nu[1][j], o[5][j] = nu[2][j];
+      if constexpr (EXT) o[6][j] = o[7][j] = o[8][j] = 0.f;
     }
   }
 
@@ -266,20 +287,19 @@ __global__ void __launch_bounds__(256) env_reset_kernel(const EnvParams p, const
   if (mask != nullptr && mask[i] == 0) return;
   const int64_t n = p.n;
   float N, E, psi, u, v, r;
-  const int32_t epi = p.episode[i];
+  const int32_t epi = p.ep_len[i];
   if (eta_in != nullptr) {
     N = eta_in[i], E = eta_in[n + i], psi = eta_in[2 * n + i];
     u = nu_in[i], v = nu_in[n + i], r = nu_in[2 * n + i];
   } else {
     sample_reset(p.seed, p.env_off + i, epi, p.reset_scale, N, E, psi, u, v, r);
   }
-  p.episode[i] = epi + 1;
   p.eta[i] = N, p.eta[n + i] = E, p.eta[2 * n + i] = psi;
   p.nu[i] = u, p.nu[n + i] = v, p.nu[2 * n + i] = r;
   p.prev_thrust[i] = 0.f, p.prev_thrust[n + i] = 0.f, p.prev_thrust[2 * n + i] = 0.f;  // customEnv.py:190
   p.angles[i] = T::DEF_BOW, p.angles[n + i] = T::DEF_PORT, p.angles[2 * n + i] = T::DEF_STAR;  // :173-177,192
   p.obs_tail[i] = 0.f, p.obs_tail[n + i] = 0.f, p.obs_tail[2 * n + i] = 0.f;
-  p.ep_len[i] = 0;
+  p.ep_len[i] = next_episode_word(epi);
   if (obs != nullptr) {
     float xb, yb, pb;
     error_frame(N, E, psi, p.ref[i], p.ref[n + i], p.ref[2 * n + i], xb, yb, pb);

@@ -127,6 +127,36 @@ __device__ __forceinline__ float fast_sqrt(float x) {  // sqrt.approx: 1 ulp, no
   return y;
 }
 
+// (sin, cos) for the hull heading.  |psi| <= pi/4 is the live range of every training env (termination bound
+// 45 deg, customEnv.py:386), where the minimax polynomials of the classic single-precision kernels (Cephes sinf /
+// cosf, ~1 ulp) need no range reduction: 11 instructions instead of the ~30 of sincosf.  Anything larger takes
+// the library route.
+__device__ __forceinline__ void sincos_heading(float x, float& s, float& c) {
+  if (fabsf(x) <= 0.78539816f) {
+    const float z = x * x;
+    const float ps = fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f);
+    s = fmaf(ps, z * x, x);
+    const float pc = fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f);
+    c = fmaf(pc, z * z, fmaf(-0.5f, z, 1.0f));
+  } else {
+    sincosf(x, &s, &c);
+  }
+}
+
+// x / 100.0f, correctly rounded (== __fdiv_rn(x, 100.0f) bit for bit) in three instructions: q = x * RN(1/100),
+// exact remainder r = x - 100 q by FMA, q' = q + r * RN(1/100) (Markstein's correction).  Checked exhaustively
+// against IEEE division over every finite float: exact for |x| >= 4.8e-38; the guard routes the denormal
+// neighbourhood (and nothing else) to the IEEE sequence.
+__device__ __forceinline__ float div100(float x) {
+  const float q = __fmul_rn(x, 0.01f);
+  const float r = __fmaf_rn(-q, 100.0f, x);
+  const float q2 = __fmaf_rn(r, 0.01f, q);
+  const bool ok = fabsf(x) >= 1e-30f;
+  float res = ok ? q2 : q;                                   // x = +-0 (every freshly reset env): q = +-0 is the quotient
+  if (!ok && x != 0.f) res = __fdiv_rn(x, 100.0f);           // denormal neighbourhood only
+  return res;
+}
+
 // tau = sum_i F_i [cos a_i, sin a_i, lx_i sin a_i - ly_i cos a_i], F_i = K_i n_i |n_i|; env order bow, port, star.
 // The caller supplies sin/cos of each azimuth (for the continuous-angle env they come straight from the
 // network's (sin, cos) pair: cos(atan2(y, x)) = x / hypot(x, y), no atan2f -> sincosf round trip).
@@ -194,7 +224,7 @@ __device__ __forceinline__ void integrate_hull(float& N, float& E, float& psi, f
                                                float tx, float ty, float tn, int n_sub, const HullConsts& k) {
   const float ax = k.hm1 * tx, ay = k.hm2 * ty, an = k.hm3 * tn;
   float s, c;
-  sincosf(psi, &s, &c);
+  sincos_heading(psi, s, c);
   float sN = 0.f, sE = 0.f, sr = 0.f;
 #pragma unroll 5
   for (int i = 0; i < n_sub; ++i) {
@@ -220,12 +250,52 @@ __device__ __forceinline__ void integrate_hull(float& N, float& E, float& psi, f
   psi = fmaf(k.h, sr, psi);
 }
 
+// Two environments per thread on the packed FP32 pipe (FFMA2 / FMUL2 / FADD2, sm_100a): the same recurrence as
+// integrate_hull, operand for operand (every lane rounds exactly like the scalar code), at 14 issue slots per
+// environment sub-step instead of 25.  The damping factors stay scalar FFMAs: |.| is a free operand modifier
+// there, while the packed form would need separate abs instructions.
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ void integrate_hull2(float2& N, float2& E, float2& psi, float2& u, float2& v, float2& r,
+                                                float2 tx, float2 ty, float2 tn, int n_sub, const HullConsts& k) {
+  const float2 ax = __fmul2_rn(splat2(k.hm1), tx), ay = __fmul2_rn(splat2(k.hm2), ty), an = __fmul2_rn(splat2(k.hm3), tn);
+  float2 s, c;
+  sincos_heading(psi.x, s.x, c.x);
+  sincos_heading(psi.y, s.y, c.y);
+  float2 sN = splat2(0.f), sE = splat2(0.f), sr = splat2(0.f);
+  const float2 kvr = splat2(k.k_vr), nkur = splat2(-k.k_ur), nkuv = splat2(-k.k_uv);
+  const float2 c2 = splat2(k.rot_c2), s1 = splat2(k.rot_s1), s3 = splat2(k.rot_s3), one = splat2(1.0f);
+#pragma unroll 5
+  for (int i = 0; i < n_sub; ++i) {
+    const float2 vr = __fmul2_rn(v, r), ur = __fmul2_rn(u, r), uv = __fmul2_rn(u, v);
+    const float2 du = make_float2(fmaf(-k.xuu, fabsf(u.x), k.one_xu), fmaf(-k.xuu, fabsf(u.y), k.one_xu));
+    const float2 dv = make_float2(fmaf(-k.yvv, fabsf(v.x), k.one_yv), fmaf(-k.yvv, fabsf(v.y), k.one_yv));
+    const float2 dr = make_float2(fmaf(-k.nrr, fabsf(r.x), k.one_nr), fmaf(-k.nrr, fabsf(r.y), k.one_nr));
+    u = __ffma2_rn(du, u, __ffma2_rn(kvr, vr, ax));
+    v = __ffma2_rn(dv, v, __ffma2_rn(nkur, ur, ay));
+    r = __ffma2_rn(dr, r, __ffma2_rn(nkuv, uv, an));
+    sN = __ffma2_rn(neg2(s), v, __ffma2_rn(c, u, sN));
+    sE = __ffma2_rn(c, v, __ffma2_rn(s, u, sE));
+    sr = __fadd2_rn(sr, r);
+    const float2 r2 = __fmul2_rn(r, r);
+    const float2 cd = __ffma2_rn(c2, r2, one);
+    const float2 sd = __fmul2_rn(r, __ffma2_rn(s3, r2, s1));
+    const float2 cn = __ffma2_rn(neg2(s), sd, __fmul2_rn(c, cd));
+    s = __ffma2_rn(c, sd, __fmul2_rn(s, cd));
+    c = cn;
+  }
+  const float2 h = splat2(k.h);
+  N = __ffma2_rn(h, sN, N);
+  E = __ffma2_rn(h, sE, E);
+  psi = __ffma2_rn(h, sr, psi);
+}
+
 // ---- errorFrame.py:25-32 --------------------------------------------------------------------------------------
 __device__ __forceinline__ void error_frame(float N, float E, float psi, float rN, float rE, float rpsi, float& xb,
                                             float& yb, float& psib) {
   const float eN = __fsub_rn(N, rN), eE = __fsub_rn(E, rE), ep = __fsub_rn(psi, rpsi);
   float s, c;
-  sincosf(wrap_deg_quirk(psi), &s, &c);
+  sincos_heading(wrap_deg_quirk(psi), s, c);
   xb = c * eN + s * eE;  // R(psi)^T e
   yb = c * eE - s * eN;
   psib = wrap_deg_quirk(ep);
@@ -276,21 +346,29 @@ __device__ __forceinline__ bool is_terminal(float xb, float yb, float psib, floa
          (fabsf(r) > b[5]);
 }
 
+// Episode word: one int32 per env = (episode counter mod 2^16) << 16 | steps taken in the current episode.
+// One row instead of two keeps the in-kernel restart free of a dependent load: the word is on the step path
+// anyway (episode-length cut, ppo.py:304).  The Philox counter of a restart is the word at that moment, so
+// the draws of an env repeat only if episode number (mod 65536) AND episode length coincide.
+constexpr uint32_t kEpLenMask = 0xFFFFu;
+__device__ __forceinline__ int32_t next_episode_word(int32_t w) { return (int32_t)((((uint32_t)w >> 16) + 1u) << 16); }
+
 // customEnv.py:141-145 + simtools.py:109-124 on the Philox stream: pose ~ U(+-fraction*b[0:3]),
 // velocity ~ U(+-0.30*fraction*b[3:6]).  scale[6] is precomputed on the host in fp32 (see make_reset_scale).
+// `episode` is the env's episode word at the moment of the reset.
 __device__ __forceinline__ void sample_reset(uint64_t seed, int64_t env_id, int32_t episode,
                                              const float* __restrict__ scale, float& N, float& E, float& psi, float& u,
                                              float& v, float& r) {
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ 0x5EED5EEDu;
   const uint32_t lo = (uint32_t)((uint64_t)env_id), hi = (uint32_t)((uint64_t)env_id >> 32);
-  const Philox4 a = philox4x32_10(lo, hi, (uint32_t)episode, 0u, k0, k1);
-  const Philox4 b = philox4x32_10(lo, hi, (uint32_t)episode, 1u, k0, k1);
-  N = __fmul_rn(scale[0], symmetric_unit(a.x));
-  E = __fmul_rn(scale[1], symmetric_unit(a.y));
-  psi = __fmul_rn(scale[2], symmetric_unit(a.z));
-  u = __fmul_rn(scale[3], symmetric_unit(a.w));
-  v = __fmul_rn(scale[4], symmetric_unit(b.x));
-  r = __fmul_rn(scale[5], symmetric_unit(b.y));
+  // one Philox block = 128 bits = six 21-bit uniforms (resolution 2^-20 of each interval)
+  const Philox4 q = philox4x32_10(lo, hi, (uint32_t)episode, 0u, k0, k1);
+  N = __fmul_rn(scale[0], symmetric_unit21(q.x));
+  E = __fmul_rn(scale[1], symmetric_unit21(q.y));
+  psi = __fmul_rn(scale[2], symmetric_unit21(q.z));
+  u = __fmul_rn(scale[3], symmetric_unit21(q.w));
+  v = __fmul_rn(scale[4], symmetric_unit21(((q.x >> 21) | (q.y >> 21 << 11)) & 0x1FFFFFu));
+  r = __fmul_rn(scale[5], symmetric_unit21(((q.z >> 21) | (q.w >> 21 << 11)) & 0x1FFFFFu));
 }
 
 }  // namespace ml4ca

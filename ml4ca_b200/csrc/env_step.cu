@@ -15,6 +15,12 @@ __global__ void __launch_bounds__(256) error_frame_kernel(int64_t n, const float
   err[i] = xb, err[n + i] = yb, err[2 * n + i] = pb;
 }
 
+__global__ void __launch_bounds__(256) unpack_ep_len_kernel(int64_t n, const int32_t* __restrict__ word,
+                                                            int32_t* __restrict__ ep_len) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ep_len[i] = (int32_t)((uint32_t)word[i] & kEpLenMask);
+}
+
 template <int KIND, bool CONT>
 __global__ void __launch_bounds__(256) scale_clip_kernel(int64_t n, const float* __restrict__ action,
                                                          float* __restrict__ act_env, int8_t* __restrict__ sat_out) {
@@ -41,7 +47,8 @@ static int validate_cfg(const ml4ca_env_cfg* c) {
                 "continuous angles only work with the final environment (customEnv.py:228)");
   ML4CA_REQUIRE(!(c->kind == ML4CA_ENV_SIMPLE && c->extended_state),
                 "RevoltSimple has no azimuth bound for the extended-state penalty (customEnv.py:319,339)");
-  ML4CA_REQUIRE(c->n_substeps >= 0 && c->max_ep_len > 0, "n_substeps >= 0 and max_ep_len > 0 required");
+  ML4CA_REQUIRE(c->n_substeps >= 0 && c->max_ep_len > 0 && c->max_ep_len <= 65535,
+                "n_substeps >= 0 and 0 < max_ep_len <= 65535 required");
   return ML4CA_OK;
 }
 
@@ -157,10 +164,10 @@ int ml4ca_env_create(const ml4ca_env_cfg* cfg, int64_t n_env, int32_t device, ml
   e->n = n_env;
   e->device = device;
   e->tail_valid = true;
-  // one slab: 18 fp32 rows + 2 int32 rows, each row padded to a 16-byte multiple so that every row start is
+  // one slab: 18 fp32 rows + 1 int32 row (the episode words), each row padded to a 16-byte multiple so that every row start is
   // float4-aligned whenever n % 4 == 0 (rows are indexed with stride n, so the padding only sits at the end).
   const size_t row = (size_t)n_env * sizeof(float);
-  const size_t bytes = 20 * row + 256;
+  const size_t bytes = 19 * row + 256;
   cudaError_t ce = cudaMalloc(&e->slab, bytes);
   if (ce != cudaSuccess) {
     delete e;
@@ -181,7 +188,6 @@ int ml4ca_env_create(const ml4ca_env_cfg* cfg, int64_t n_env, int32_t device, ml
   p.angles = f + 12 * n_env;
   p.obs_tail = f + 15 * n_env;
   p.ep_len = reinterpret_cast<int32_t*>(f + 18 * n_env);
-  p.episode = reinterpret_cast<int32_t*>(f + 19 * n_env);
   p.n = n_env;
   for (int i = 0; i < 6; ++i) p.bounds[i] = cfg->ss_bounds[i];
   make_reset_scale(*cfg, cfg->reset_fraction, p.reset_scale);
@@ -253,8 +259,10 @@ int ml4ca_env_get_state(ml4ca_env* env, float* eta, float* nu, float* prev_thrus
   if (nu) ML4CA_CUDA(cudaMemcpyAsync(nu, env->p.nu, row3, cudaMemcpyDeviceToDevice, st));
   if (prev_thrust) ML4CA_CUDA(cudaMemcpyAsync(prev_thrust, env->p.prev_thrust, row3, cudaMemcpyDeviceToDevice, st));
   if (angles) ML4CA_CUDA(cudaMemcpyAsync(angles, env->p.angles, row3, cudaMemcpyDeviceToDevice, st));
-  if (ep_len)
-    ML4CA_CUDA(cudaMemcpyAsync(ep_len, env->p.ep_len, (size_t)env->n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  if (ep_len) {
+    unpack_ep_len_kernel<<<(unsigned)((env->n + 255) / 256), 256, 0, st>>>(env->n, env->p.ep_len, ep_len);
+    return check_launch("unpack_ep_len_kernel");
+  }
   return ML4CA_OK;
 }
 

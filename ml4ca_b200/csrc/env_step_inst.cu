@@ -44,23 +44,29 @@ static int launch_step_vec(const ml4ca_env* e, const float* action, float* obs, 
   const int64_t n = e->n;
   const bool vec4 = (n % 4 == 0) && aligned16(action) && aligned16(obs) && aligned16(rew) &&
                     ((reinterpret_cast<uintptr_t>(done) & 3u) == 0);
-  const int threads = 256;
-  // One env per thread is the default: the kernel is issue-bound (~1000 instructions per env-step), and 48
-  // resident warps of the 40-register scalar variant hide latency better than the 128-register float4 variant
-  // (measured on B200, profiles/env_step_r1.md: 0.64 ms vs 0.73 ms (x2) vs 0.82 ms (x4) for 16 Mi envs).
+  static const int threads = [] {   // tuning knob: ML4CA_ENV_THREADS=64|128|256
+    const char* e = getenv("ML4CA_ENV_THREADS");
+    const int t = e ? atoi(e) : 256;
+    return (t == 64 || t == 128 || t == 256) ? t : 256;
+  }();
+  // Two envs per thread is the default: the kernel is issue-bound, and the packed-FP32 integrator (FFMA2) of the
+  // two-env variant issues 28 % fewer instructions per env-step than the scalar one (profiles/env_step_r1.md:
+  // 0.50 ms vs 0.59 ms for 16 Mi envs).  One env per thread serves batches whose rows are not 16-byte aligned.
   static const int vec_pref = [] {   // tuning knob: ML4CA_ENV_VEC=1|2|4
     const char* e = getenv("ML4CA_ENV_VEC");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 2;
   }();
-  if (vec4 && vec_pref == 4) {
+  const EnvParams& p = e->p;
+  const int vec = (vec4 && (vec_pref == 4 || vec_pref == 2)) ? vec_pref : 1;
+  if (vec == 4) {
     const int64_t blocks = (n / 4 + threads - 1) / threads;
-    env_step_kernel<KIND, CONT, EXT, 4><<<(unsigned)blocks, threads, 0, st>>>(e->p, action, obs, rew, done);
-  } else if (vec4 && vec_pref == 2) {
+    env_step_kernel<KIND, CONT, EXT, 4><<<(unsigned)blocks, threads, 0, st>>>(p, action, obs, rew, done);
+  } else if (vec == 2) {
     const int64_t blocks = (n / 2 + threads - 1) / threads;
-    env_step_kernel<KIND, CONT, EXT, 2><<<(unsigned)blocks, threads, 0, st>>>(e->p, action, obs, rew, done);
+    env_step_kernel<KIND, CONT, EXT, 2><<<(unsigned)blocks, threads, 0, st>>>(p, action, obs, rew, done);
   } else {
     const int64_t blocks = (n + threads - 1) / threads;
-    env_step_kernel<KIND, CONT, EXT, 1><<<(unsigned)blocks, threads, 0, st>>>(e->p, action, obs, rew, done);
+    env_step_kernel<KIND, CONT, EXT, 1><<<(unsigned)blocks, threads, 0, st>>>(p, action, obs, rew, done);
   }
   return check_launch("env_step_kernel");
 }

@@ -40,6 +40,10 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
 __host__ __device__ __forceinline__ float symmetric_unit(uint32_t x) {
   return (float)((int32_t)(x >> 8) - (1 << 23)) * 1.1920928955078125e-07f;
 }
+// low 21 bits -> float in [-1, 1): ((x & 0x1FFFFF) - 2^20) * 2^-20, exact in fp32.
+__host__ __device__ __forceinline__ float symmetric_unit21(uint32_t x) {
+  return (float)((int32_t)(x & 0x1FFFFFu) - (1 << 20)) * 9.5367431640625e-07f;
+}
 // uint32 -> float in (0, 1]: ((x >> 8) + 1) * 2^-24.
 __host__ __device__ __forceinline__ float unit_open(uint32_t x) {
   return ((float)(x >> 8) + 1.0f) * 5.9604644775390625e-08f;

@@ -469,14 +469,12 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
                                             ep.inv_step_dt, 1.0f / T::ANG_BOUND);
           const bool term = is_terminal(xb, yb, pb, eu, ev, er, ep.bounds);
           epl += 1;
-          const bool trunc = epl >= ep.max_ep_len;
+          const bool trunc = (int32_t)((uint32_t)epl & kEpLenMask) >= ep.max_ep_len;
           const uint32_t flags = (term ? ML4CA_DONE_TERMINAL : 0u) | (trunc ? ML4CA_DONE_TRUNCATED : 0u);
           float npt[3] = {thrust[0], thrust[1], thrust[2]};
           if (ep.auto_reset && flags != 0u) {
-            const int32_t epi = ep.episode[env];
-            sample_reset(ep.seed, ep.env_off + env, epi, ep.reset_scale, eN, eE, ePsi, eu, ev, er);
-            ep.episode[env] = epi + 1;
-            epl = 0;
+            sample_reset(ep.seed, ep.env_off + env, epl, ep.reset_scale, eN, eE, ePsi, eu, ev, er);
+            epl = next_episode_word(epl);
             a_port = T::DEF_PORT, a_star = T::DEF_STAR;
             npt[0] = npt[1] = npt[2] = 0.f;
           }
@@ -486,7 +484,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
           for (int c = 0; c < 3; ++c) {
             ep.prev_thrust[(int64_t)c * ep.n + env] = npt[c];
             // tail of the observation this step returns: previous thrust / 100 (0 after a re-sample, :190)
-            ep.obs_tail[(int64_t)c * ep.n + env] = (ep.auto_reset && flags != 0u) ? 0.f : __fdiv_rn(pth[c], 100.0f);
+            ep.obs_tail[(int64_t)c * ep.n + env] = (ep.auto_reset && flags != 0u) ? 0.f : div100(pth[c]);
           }
           ep.angles[ep.n + env] = a_port, ep.angles[2 * ep.n + env] = a_star;
           ep.ep_len[env] = epl;

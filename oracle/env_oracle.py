@@ -193,8 +193,15 @@ def new_state(spec, n, dt=np.float64):
     }
 
 
+def episode_word(state):
+    """The per-env word the kernels keep: (episode counter mod 2^16) << 16 | steps in this episode.  It is the
+    Philox counter of a restart (csrc/env_math.cuh: next_episode_word / sample_reset)."""
+    return ((state['episode'].astype(np.int64) & 0xFFFF) << 16) | (state['ep_len'].astype(np.int64) & 0xFFFF)
+
+
 def sample_reset(spec, seed, env_ids, episodes, fraction=0.8):
     """customEnv.py:141-145 + simtools.py:109-124 on the Philox stream (float32, bit-equal to the kernel).
+    ``episodes`` = the episode words at the moment of the reset.
 
     pose ~ U(+-fraction * ss_bounds[0:3]),  vel ~ U(+-0.30 * fraction * ss_bounds[3:6]).
     value = (bound * scale) * symmetric_unit, all in float32, one rounding per product.
@@ -216,7 +223,7 @@ def reset(spec, state, mask=None, seed=0, env_id_offset=0, fraction=0.8, eta=Non
     m = np.ones(n, dtype=bool) if mask is None else np.asarray(mask, dtype=bool)
     if eta is None:
         ids = np.arange(n, dtype=np.int64) + int(env_id_offset)
-        e32, v32 = sample_reset(spec, seed, ids, state['episode'], fraction)
+        e32, v32 = sample_reset(spec, seed, ids, episode_word(state), fraction)
         eta, nu = e32.astype(dt), v32.astype(dt)
     state['eta'][:, m] = np.asarray(eta, dtype=dt)[:, m]
     state['nu'][:, m] = np.asarray(nu, dtype=dt)[:, m]

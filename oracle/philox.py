@@ -48,8 +48,16 @@ def unit_open(x):
     return ((x >> np.uint32(8)).astype(np.float32) + np.float32(1.0)) * np.float32(2.0 ** -24)
 
 
+def symmetric_unit21(x):
+    """low 21 bits -> float32 in [-1, 1):  ((x & 0x1FFFFF) - 2^20) * 2^-20, exact in float32."""
+    i = (np.asarray(x, dtype=np.uint32) & np.uint32(0x1FFFFF)).astype(np.int64) - (1 << 20)
+    return (i.astype(np.float32) * np.float32(2.0 ** -20)).astype(np.float32)
+
+
 def reset_draws(seed, env_id, episode):
-    """The six reset uniforms of one (env, episode): two Philox blocks, counters (env_lo, env_hi, episode, blk).
+    """The six reset uniforms of one (env, episode word): ONE Philox block, counter (env_lo, env_hi, word, 0),
+    split into six 21-bit fields: the low 21 bits of each of the four outputs, then the top 11 bits of
+    outputs 0|1 and of outputs 2|3 (11 + 11 = 22 bits, masked to 21).
 
     Returns float32 array [6, n] of symmetric units in [-1, 1): N, E, psi, u, v, r order.
     Key = (seed_lo, seed_hi ^ 0x5EED5EED).
@@ -60,7 +68,9 @@ def reset_draws(seed, env_id, episode):
     k1 = ((int(seed) >> 32) & 0xFFFFFFFF) ^ 0x5EED5EED
     lo = env_id & _MASK
     hi = env_id >> np.uint64(32)
-    a = philox4x32(lo, hi, episode & _MASK, np.zeros_like(lo), k0, k1)
-    b = philox4x32(lo, hi, episode & _MASK, np.ones_like(lo), k0, k1)
-    return np.stack([symmetric_unit(a[0]), symmetric_unit(a[1]), symmetric_unit(a[2]),
-                     symmetric_unit(a[3]), symmetric_unit(b[0]), symmetric_unit(b[1])])
+    q = philox4x32(lo, hi, episode & _MASK, np.zeros_like(lo), k0, k1)
+    s = np.uint32
+    v5 = (q[0] >> s(21)) | ((q[1] >> s(21)) << s(11))
+    v6 = (q[2] >> s(21)) | ((q[3] >> s(21)) << s(11))
+    return np.stack([symmetric_unit21(q[0]), symmetric_unit21(q[1]), symmetric_unit21(q[2]),
+                     symmetric_unit21(q[3]), symmetric_unit21(v5), symmetric_unit21(v6)])

@@ -142,7 +142,7 @@ def test_reset_sampling_is_bit_identical_to_oracle(cuda_device):
     # second episode of a masked subset, and a shard starting at global id 6000
     mask = np.zeros(n, dtype=bool); mask[::3] = True
     env.reset(fraction=0.5, mask=mask)
-    eta2, _ = EO.sample_reset(spec, seed, np.arange(n), np.ones(n, dtype=np.int64), 0.5)
+    eta2, _ = EO.sample_reset(spec, seed, np.arange(n), np.full(n, 1 << 16, dtype=np.int64), 0.5)   # episode word: episode 1, 0 steps
     got = env.get_state()['eta'].cpu().numpy()
     np.testing.assert_array_equal(got[:, mask], eta2[:, mask])
     np.testing.assert_array_equal(got[:, ~mask], eta[:, ~mask])
@@ -160,7 +160,8 @@ def test_auto_reset_and_episode_cut(cuda_device):
     env.reset(fraction=0.8)
     zero = torch.zeros(7, n, device=cuda_device)
     zero[4] = 1.0; zero[6] = 1.0               # cos = 1 -> azimuth 0, no thrust: the vessel coasts
-    episodes = np.zeros(n, dtype=np.int64)     # episodes started so far - 1
+    episodes = np.ones(n, dtype=np.int64)      # episode counter (the explicit reset above started episode 1)
+    prev_len = np.zeros(n, dtype=np.int64)
     for t in range(45):
         o, r, d, info = env.step(zero)
         flags = info['flags'].cpu().numpy()
@@ -169,12 +170,15 @@ def test_auto_reset_and_episode_cut(cuda_device):
         ep_len = st['ep_len'].cpu().numpy()
         assert (ep_len[ended] == 0).all() and (ep_len[~ended] >= 1).all() and ep_len.max() < 20
         if ended.any():
+            # Philox counter of a restart = the env's episode word at that moment: episode << 16 | steps taken
+            word = (episodes << 16) | (prev_len + 1)
+            eta_new, nu_new = EO.sample_reset(spec, seed, np.arange(n), word, 0.8)
             episodes[ended] += 1
-            eta_new, nu_new = EO.sample_reset(spec, seed, np.arange(n), episodes, 0.8)
             np.testing.assert_array_equal(st['eta'].cpu().numpy()[:, ended], eta_new[:, ended])
             np.testing.assert_array_equal(o.cpu().numpy()[3:6, ended], nu_new[:, ended])
             assert (st['prev_thrust'].cpu().numpy()[:, ended] == 0).all()
-    assert episodes.min() >= 2      # every env was cut at least twice in 45 steps of 20-step episodes
+        prev_len = ep_len.astype(np.int64)
+    assert episodes.min() >= 3      # every env was cut at least twice in 45 steps of 20-step episodes
 
 
 def test_full_size_properties(cuda_device):
