@@ -32,6 +32,10 @@ if ROOT not in sys.path:
 
 ENV_STEP_BYTES = 177      # read 60 state + 28 action, write 48 state + 36 obs + 4 rew + 1 done
 PINV_PID_BYTES = 80       # read eta, nu, ref, integ (48) + write integ, n, alpha (32)
+QP_BYTES = 68             # read tau 3 + prev 5 words, write x 8 + status 1
+POLICY_BYTES = 72         # read obs 36, write action 28 + value 4 + logp 4
+ROLLOUT_TRAIN_BYTES = 185  # state r/w 108 + trajectory record 77
+GAE_BYTES = 17            # read r, V, flag byte; write A, R
 ACTION_POOL = 2           # flat U(-1,1) buffers; step i reads a [7, n] window at a new offset: fresh actions per (env, step)
 ACTION_SHIFT = 4 * 1031   # floats between consecutive windows (16-byte aligned, so the vectorised kernel path is kept)
 
@@ -242,18 +246,14 @@ def run_b200(args, rank, local_rank, world):
 
     # ---- end to end through the public API with host buffers ----------------------------------------------------
     e2e_steps = max(3, min(args.steps, 10))
-    h_act = [torch.rand(7, n).pin_memory() for _ in range(2)]
+    h_act = [(torch.rand(7, n) * 2 - 1).pin_memory() for _ in range(2)]
     h_obs = torch.empty(9, n).pin_memory()
     h_rew = torch.empty(n).pin_memory()
     h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
-    d_act = torch.empty(7, n, device=dev)
 
     def e2e_step(i):
-        d_act.copy_(h_act[i % 2], non_blocking=True)
-        env.step_into(d_act, *out)
-        h_obs.copy_(out[0], non_blocking=True)
-        h_rew.copy_(out[1], non_blocking=True)
-        h_done.copy_(out[2], non_blocking=True)
+        # public API with host buffers: RevoltFinal.step_host -> ml4ca_env_step_host (chunked copy/compute pipeline)
+        env.step_host(h_act[i % 2], h_obs, h_rew, h_done)
 
     for i in range(2):
         e2e_step(i)
@@ -292,6 +292,75 @@ def run_b200(args, rank, local_rank, world):
     except Exception as e:  # noqa: BLE001
         extra["pinv_pid"] = {"error": repr(e)}
 
+    def timed(fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(reps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / reps * 1e-3
+
+    if not args.skip_extra:
+        # K1: QP thrust allocation (BASELINE configs[0] batch law), 1 Mi demands
+        try:
+            import numpy as np
+            from ml4ca_b200 import synth
+            m = 1 << 20
+            tau_np, prev_np = synth.qp_batch(4096, seed=0)
+            reps_t = m // 4096
+            tau_t = torch.as_tensor(np.tile(tau_np, reps_t), dtype=torch.float32, device=dev).contiguous()
+            qp = M.QPTA(num_envs=m, device=dev)
+            qp.previous_thruster_state = np.tile(prev_np, reps_t)
+            t = timed(lambda: qp.solve_QP(tau_t), 5)
+            extra["qp_allocate"] = {"workload": "BASELINE configs[0] demand law tiled to 1 Mi allocations (QPTA.solve_QP)",
+                                    "value": m / t, "unit": "allocations/s", "ms_per_launch": t * 1e3,
+                                    "achieved_GBs": QP_BYTES * m / t / 1e9, "bound": "issue/latency (~1e4 instr per solve)"}
+            del qp, tau_t
+        except Exception as e:  # noqa: BLE001
+            extra["qp_allocate"] = {"error": repr(e)}
+        # K4: actor/critic 64x64 forward (configs[3]) stand-alone, and fused with the env step
+        try:
+            m = 1 << 23
+            ac = M.ActorCritic(9, 7, (64, 64), "leaky_relu", device=dev, seed=3)
+            obs_t = torch.rand(9, m, device=dev, generator=gen) * 2 - 1
+            outp = (torch.empty(7, m, device=dev), torch.empty(m, device=dev), torch.empty(m, device=dev))
+            t = timed(lambda: ac.step(obs_t, out=outp), 10)
+            flop = 19712.0
+            extra["policy_forward"] = {"workload": "BASELINE configs[3] network: 9-64-64-7 + 9-64-64-1 leaky-ReLU actor/critic, "
+                                                   "8 Mi observations, tcgen05 fp16 operands / fp32 TMEM accumulators",
+                                       "value": m / t, "unit": "observations/s", "ms_per_launch": t * 1e3,
+                                       "achieved_GBs": POLICY_BYTES * m / t / 1e9, "achieved_TFLOPs": flop * m / t / 1e12}
+            env2 = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=m, device=dev, seed=4,
+                               auto_reset=True, env_id_offset=rank * m)
+            env2.reset(fraction=0.8)
+            buf = M.TrajectoryBuffer(9, 7, 4, m, device=dev)
+            state = {"t": 0}
+
+            def roll(fused):
+                M.rollout(env2, ac, buf, seed=3, start_step=state["t"], fused=fused)
+                state["t"] += buf.max_size
+            for fused in (False, True):
+                env2.reset(fraction=0.8)
+                t = timed(lambda: roll(fused), 5) / buf.max_size
+                extra["rollout_fused" if fused else "rollout_two_kernel"] = {
+                    "workload": "configs[3]: policy forward + env step + trajectory record, 8 Mi envs/GPU, training mode",
+                    "value": m / t, "unit": "env-steps/s", "ms_per_step": t * 1e3,
+                    "achieved_GBs": ROLLOUT_TRAIN_BYTES * m / t / 1e9}
+            # K5: GAE-lambda over the [T, n] buffer
+            Tg = 64
+            mg = 1 << 21
+            gbuf = M.TrajectoryBuffer(1, 1, Tg, mg, gamma=0.99, lam=0.97, device=dev)
+            gbuf.rew_buf.normal_(generator=gen); gbuf.val_buf.normal_(generator=gen)
+            t = timed(lambda: gbuf.finish_path(), 5)
+            extra["gae"] = {"workload": "TrajectoryBuffer.finish_path, T=64 x 2 Mi envs", "value": Tg * mg / t,
+                            "unit": "steps/s", "ms_per_launch": t * 1e3, "achieved_GBs": GAE_BYTES * Tg * mg / t / 1e9}
+            del env2, buf, gbuf, ac
+        except Exception as e:  # noqa: BLE001
+            extra["policy_rollout"] = {"error": repr(e)}
+
     sampler.stop_flag.set()
     sampler.join(timeout=1.0)
     clocks = sampler.summary()
@@ -313,7 +382,7 @@ def run_b200(args, rank, local_rank, world):
             "cpu_baseline": {"value": cpu_val, "unit": "env-steps/s", "cores": cpu_cores, "kind": "port",
                              "sample": cpu_sample},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "note": "pinned host actions in, obs+reward+done out, every step"},
+                    "steps": e2e_steps, "note": "RevoltFinal.step_host: pinned host actions in, obs+reward+done out, every step, chunked H2D|kernel|D2H pipeline"},
             "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
         }
         print(json.dumps(line), flush=True)
@@ -329,6 +398,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 24)
     ap.add_argument("--skip-cpu", action="store_true", help="omit the CPU baseline leg (used for ncu captures)")
+    ap.add_argument("--skip-extra", action="store_true", help="omit the secondary-kernel figures under 'extra'")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -85,6 +85,14 @@ ML4CA_API int ml4ca_env_reset_to(ml4ca_env* env, const uint8_t* mask, const floa
 ML4CA_API int ml4ca_env_set_ref(ml4ca_env* env, const float* ref, void* stream);
 /* Revolt.step(action) (customEnv.py:92-133): action [act_dim, n] -> obs [obs_dim, n], rew [n], done [n] flags. */
 ML4CA_API int ml4ca_env_step(ml4ca_env* env, const float* action, float* obs, float* rew, uint8_t* done, void* stream);
+/* The same step for callers whose buffers live in HOST memory (the reference's callers hold NumPy arrays:
+ * ppo.py:291-293 feeds `a[0]` to env.step and reads o, r, d back).  action_host [act_dim, n], obs_host [obs_dim, n],
+ * rew_host [n], done_host [n]; page-locked buffers give full overlap.  The batch is cut into chunks that run through
+ * a three-stage pipeline on library-owned streams (host->device copy | kernel | device->host copy), so that both
+ * PCIe directions and the SMs are busy at once.  Ordered after the work already queued on `stream`; `stream`
+ * resumes when the last result bytes have landed (synchronise it before reading the host buffers). */
+ML4CA_API int ml4ca_env_step_host(ml4ca_env* env, const float* action_host, float* obs_host, float* rew_host,
+                                  uint8_t* done_host, void* stream);
 /* Copies of the SoA state (any pointer may be NULL): eta [3,n], nu [3,n], prev_thrust [3,n] (env order bow, port,
  * star), angles [3,n] (current_angles, customEnv.py:71), ep_len [n].  Also EF.get_NED_pos (errorFrame.py:19). */
 ML4CA_API int ml4ca_env_get_state(ml4ca_env* env, float* eta, float* nu, float* prev_thrust, float* angles, int32_t* ep_len,

@@ -45,8 +45,26 @@ struct EnvParams {
   int32_t auto_reset, pad0;
   uint64_t seed;
   int64_t env_off;
+  // one launch may cover a slice [first, first + count) of the batch (host-buffer pipeline, env_step.cu): the state
+  // pointers above are then advanced by `first` (row stride stays n) and the caller's action / obs rows have
+  // their own stride io_stride.  Whole-batch launches: count = io_stride = n.
+  int64_t count, io_stride;
 };
 
+}  // namespace ml4ca
+
+namespace ml4ca {
+// Device staging and streams of ml4ca_env_step_host (created on first use).
+struct HostPipe {
+  int64_t chunk = 0;           // envs per pipeline stage
+  void* slab = nullptr;
+  float* act[2];
+  float* obs[2];
+  float* rew[2];
+  uint8_t* done[2];
+  cudaStream_t s_in, s_k, s_out;
+  cudaEvent_t ev_start, ev_in[2], ev_k[2], ev_out[2];
+};
 }  // namespace ml4ca
 
 struct ml4ca_env {
@@ -54,6 +72,7 @@ struct ml4ca_env {
   int64_t n;
   int32_t device;
   void* slab;
+  ml4ca::HostPipe* pipe = nullptr;
   bool tail_valid;     // obs_tail rows describe the last returned observation (reset / fused steps keep it so)
   ml4ca::EnvParams p;
 };
@@ -134,14 +153,14 @@ __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : (VEC ==
                                                        float* __restrict__ obs, float* __restrict__ rew,
                                                        uint8_t* __restrict__ done) {
   using T = EnvTraits<KIND, CONT>;
-  const int64_t n = p.n;
+  const int64_t n = p.n, ios = p.io_stride;
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-  if (i0 >= n) return;
+  if (i0 >= p.count) return;
 
   // ---- loads: issue everything up front so that ~20 independent 128-bit requests are in flight per thread ----
   float a[T::ACT][VEC];
 #pragma unroll
-  for (int c = 0; c < T::ACT; ++c) ld_row_nc<VEC>(action + (int64_t)c * n, i0, a[c]);
+  for (int c = 0; c < T::ACT; ++c) ld_row_nc<VEC>(action + (int64_t)c * ios, i0, a[c]);
   float eta[3][VEC], nu[3][VEC], ref[3][VEC], pth[3][VEC], ang[3][VEC];
   int32_t ep[VEC];
 #pragma unroll
@@ -269,7 +288,7 @@ __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : (VEC ==
   }
   st_irow<VEC>(p.ep_len, i0, ep);
 #pragma unroll
-  for (int c = 0; c < (EXT ? 9 : 6); ++c) st_row<VEC>(obs + (int64_t)c * n, i0, o[c]);
+  for (int c = 0; c < (EXT ? 9 : 6); ++c) st_row<VEC>(obs + (int64_t)c * ios, i0, o[c]);
   st_row<VEC>(rew, i0, rw);
   st_flags<VEC>(done, i0, flags);
 }

@@ -1,5 +1,7 @@
 // env_step.cu -- host side of K3: handle life cycle and the extern "C" entry points of the env.
 // Kernels: env_kernels.cuh; per-class instantiations: env_step_inst.cu.
+#include <stdlib.h>
+
 #include <new>
 
 #include "env_kernels.cuh"
@@ -60,7 +62,7 @@ static void make_reset_scale(const ml4ca_env_cfg& c, float fraction, float (&sca
 }
 
 #define ML4CA_DECL_UNIT(name)                                                                                   \
-  int launch_step_##name(const ml4ca_env*, const float*, float*, float*, uint8_t*, cudaStream_t);                \
+  int launch_step_##name(const ml4ca_env*, const EnvParams&, const float*, float*, float*, uint8_t*, cudaStream_t); \
   int launch_reset_##name(const ml4ca_env*, const EnvParams&, const uint8_t*, const float*, const float*, float*, \
                           cudaStream_t);
 ML4CA_DECL_UNIT(full)
@@ -70,15 +72,22 @@ ML4CA_DECL_UNIT(final_wrap)
 ML4CA_DECL_UNIT(final_cont)
 #undef ML4CA_DECL_UNIT
 
-static int launch_step(const ml4ca_env* e, const float* action, float* obs, float* rew, uint8_t* done,
-                       cudaStream_t st) {
+// Step the slice [first, first + count) of the batch; action / obs rows have stride io_stride.
+static int launch_step(const ml4ca_env* e, int64_t first, int64_t count, int64_t io_stride, const float* action,
+                       float* obs, float* rew, uint8_t* done, cudaStream_t st) {
+  EnvParams p = e->p;
+  p.eta += first, p.nu += first, p.ref += first, p.prev_thrust += first, p.angles += first, p.obs_tail += first;
+  p.ep_len += first;
+  p.env_off += first;
+  p.count = count;
+  p.io_stride = io_stride;
   switch (e->cfg.kind) {
-    case ML4CA_ENV_FULL: return launch_step_full(e, action, obs, rew, done, st);
-    case ML4CA_ENV_SIMPLE: return launch_step_simple(e, action, obs, rew, done, st);
-    case ML4CA_ENV_LIMITED: return launch_step_limited(e, action, obs, rew, done, st);
+    case ML4CA_ENV_FULL: return launch_step_full(e, p, action, obs, rew, done, st);
+    case ML4CA_ENV_SIMPLE: return launch_step_simple(e, p, action, obs, rew, done, st);
+    case ML4CA_ENV_LIMITED: return launch_step_limited(e, p, action, obs, rew, done, st);
     default:
-      return e->cfg.cont_ang ? launch_step_final_cont(e, action, obs, rew, done, st)
-                             : launch_step_final_wrap(e, action, obs, rew, done, st);
+      return e->cfg.cont_ang ? launch_step_final_cont(e, p, action, obs, rew, done, st)
+                             : launch_step_final_wrap(e, p, action, obs, rew, done, st);
   }
 }
 
@@ -200,6 +209,8 @@ int ml4ca_env_create(const ml4ca_env_cfg* cfg, int64_t n_env, int32_t device, ml
   p.pad0 = 0;
   p.seed = cfg->seed;
   p.env_off = cfg->env_id_offset;
+  p.count = n_env;
+  p.io_stride = n_env;
   *out = e;
   return ML4CA_OK;
 }
@@ -207,6 +218,15 @@ int ml4ca_env_create(const ml4ca_env_cfg* cfg, int64_t n_env, int32_t device, ml
 int ml4ca_env_destroy(ml4ca_env* env) {
   if (env == nullptr) return ML4CA_OK;
   DeviceGuard guard(env->device);
+  if (env->pipe != nullptr) {
+    HostPipe* hp = env->pipe;
+    cudaStreamSynchronize(hp->s_out);
+    cudaStreamDestroy(hp->s_in), cudaStreamDestroy(hp->s_k), cudaStreamDestroy(hp->s_out);
+    cudaEventDestroy(hp->ev_start);
+    for (int s = 0; s < 2; ++s) cudaEventDestroy(hp->ev_in[s]), cudaEventDestroy(hp->ev_k[s]), cudaEventDestroy(hp->ev_out[s]);
+    cudaFree(hp->slab);
+    delete hp;
+  }
   cudaFree(env->slab);
   delete env;
   return ML4CA_OK;
@@ -246,7 +266,76 @@ int ml4ca_env_step(ml4ca_env* env, const float* action, float* obs, float* rew, 
                 "action, obs, rew and done are required");
   DeviceGuard guard(env->device);
   env->tail_valid = false;   // the tail of the returned observation now lives in the caller's obs buffer only
-  return launch_step(env, action, obs, rew, done, static_cast<cudaStream_t>(stream));
+  return launch_step(env, 0, env->n, env->n, action, obs, rew, done, static_cast<cudaStream_t>(stream));
+}
+
+// ---- host-buffer step: chunked three-stage pipeline (H2D | kernel | D2H on three streams, two slots) -------------
+int ml4ca_env_step_host(ml4ca_env* env, const float* action_host, float* obs_host, float* rew_host,
+                        uint8_t* done_host, void* stream) {
+  ML4CA_REQUIRE(env != nullptr, "env is NULL");
+  ML4CA_REQUIRE(action_host != nullptr && obs_host != nullptr && rew_host != nullptr && done_host != nullptr,
+                "action, obs, rew and done host buffers are required");
+  DeviceGuard guard(env->device);
+  int32_t act_dim = 0, obs_dim = 0;
+  ml4ca_env_dims(&env->cfg, &act_dim, &obs_dim);
+  HostPipe*& hp = env->pipe;
+  const int64_t n = env->n;
+  if (hp == nullptr) {
+    hp = new (std::nothrow) HostPipe();
+    ML4CA_REQUIRE(hp != nullptr, "out of host memory");
+    static const int64_t chunk_pref = [] {   // tuning knob: envs per pipeline chunk
+      const char* e = getenv("ML4CA_HOST_CHUNK");
+      return e ? (int64_t)atoll(e) : (int64_t)1 << 20;
+    }();
+    hp->chunk = n < chunk_pref ? ((n + 3) / 4) * 4 : chunk_pref;
+    const size_t per_slot = (size_t)hp->chunk * ((size_t)(act_dim + obs_dim + 1) * sizeof(float) + 1) + 64;
+    ML4CA_CUDA(cudaMalloc(&hp->slab, 2 * per_slot));
+    for (int s = 0; s < 2; ++s) {
+      uint8_t* base = static_cast<uint8_t*>(hp->slab) + s * per_slot;
+      hp->act[s] = reinterpret_cast<float*>(base);
+      hp->obs[s] = hp->act[s] + (size_t)act_dim * hp->chunk;
+      hp->rew[s] = hp->obs[s] + (size_t)obs_dim * hp->chunk;
+      hp->done[s] = reinterpret_cast<uint8_t*>(hp->rew[s] + hp->chunk);
+      ML4CA_CUDA(cudaEventCreateWithFlags(&hp->ev_in[s], cudaEventDisableTiming));
+      ML4CA_CUDA(cudaEventCreateWithFlags(&hp->ev_k[s], cudaEventDisableTiming));
+      ML4CA_CUDA(cudaEventCreateWithFlags(&hp->ev_out[s], cudaEventDisableTiming));
+    }
+    ML4CA_CUDA(cudaEventCreateWithFlags(&hp->ev_start, cudaEventDisableTiming));
+    ML4CA_CUDA(cudaStreamCreateWithFlags(&hp->s_in, cudaStreamNonBlocking));
+    ML4CA_CUDA(cudaStreamCreateWithFlags(&hp->s_k, cudaStreamNonBlocking));
+    ML4CA_CUDA(cudaStreamCreateWithFlags(&hp->s_out, cudaStreamNonBlocking));
+  }
+  cudaStream_t user = static_cast<cudaStream_t>(stream);
+  ML4CA_CUDA(cudaEventRecord(hp->ev_start, user));          // everything queued on the caller's stream comes first
+  ML4CA_CUDA(cudaStreamWaitEvent(hp->s_in, hp->ev_start, 0));
+  ML4CA_CUDA(cudaStreamWaitEvent(hp->s_k, hp->ev_start, 0));
+  env->tail_valid = false;
+  const int64_t C = hp->chunk;
+  const size_t hpitch = (size_t)n * sizeof(float), dpitch = (size_t)C * sizeof(float);
+  int64_t k = 0;
+  for (int64_t first = 0; first < n; first += C, ++k) {
+    const int s = (int)(k & 1);
+    const int64_t cnt = n - first < C ? n - first : C;
+    if (k >= 2) ML4CA_CUDA(cudaStreamWaitEvent(hp->s_in, hp->ev_k[s], 0));      // kernel k-2 has consumed act[s]
+    ML4CA_CUDA(cudaMemcpy2DAsync(hp->act[s], dpitch, action_host + first, hpitch, (size_t)cnt * sizeof(float),
+                                 (size_t)act_dim, cudaMemcpyHostToDevice, hp->s_in));
+    ML4CA_CUDA(cudaEventRecord(hp->ev_in[s], hp->s_in));
+    ML4CA_CUDA(cudaStreamWaitEvent(hp->s_k, hp->ev_in[s], 0));
+    if (k >= 2) ML4CA_CUDA(cudaStreamWaitEvent(hp->s_k, hp->ev_out[s], 0));     // copy-out k-2 has drained obs[s]
+    int rc = launch_step(env, first, cnt, C, hp->act[s], hp->obs[s], hp->rew[s], hp->done[s], hp->s_k);
+    if (rc != ML4CA_OK) return rc;
+    ML4CA_CUDA(cudaEventRecord(hp->ev_k[s], hp->s_k));
+    ML4CA_CUDA(cudaStreamWaitEvent(hp->s_out, hp->ev_k[s], 0));
+    ML4CA_CUDA(cudaMemcpy2DAsync(obs_host + first, hpitch, hp->obs[s], dpitch, (size_t)cnt * sizeof(float),
+                                 (size_t)obs_dim, cudaMemcpyDeviceToHost, hp->s_out));
+    ML4CA_CUDA(cudaMemcpyAsync(rew_host + first, hp->rew[s], (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost,
+                               hp->s_out));
+    ML4CA_CUDA(cudaMemcpyAsync(done_host + first, hp->done[s], (size_t)cnt, cudaMemcpyDeviceToHost, hp->s_out));
+    ML4CA_CUDA(cudaEventRecord(hp->ev_out[s], hp->s_out));
+  }
+  // the caller's stream resumes when the last copies have landed (the other slot finished earlier on s_out)
+  ML4CA_CUDA(cudaStreamWaitEvent(user, hp->ev_out[(int)((k - 1) & 1)], 0));
+  return ML4CA_OK;
 }
 
 int ml4ca_env_get_state(ml4ca_env* env, float* eta, float* nu, float* prev_thrust, float* angles, int32_t* ep_len,

@@ -39,11 +39,11 @@ namespace ml4ca {
 #endif
 
 template <int KIND, bool CONT, bool EXT>
-static int launch_step_vec(const ml4ca_env* e, const float* action, float* obs, float* rew, uint8_t* done,
-                           cudaStream_t st) {
-  const int64_t n = e->n;
-  const bool vec4 = (n % 4 == 0) && aligned16(action) && aligned16(obs) && aligned16(rew) &&
-                    ((reinterpret_cast<uintptr_t>(done) & 3u) == 0);
+static int launch_step_vec(const ml4ca_env* e, const EnvParams& p, const float* action, float* obs, float* rew,
+                           uint8_t* done, cudaStream_t st) {
+  const int64_t n = p.count;
+  const bool vec4 = (p.n % 4 == 0) && (n % 4 == 0) && (p.io_stride % 4 == 0) && aligned16(p.eta) && aligned16(action) &&
+                    aligned16(obs) && aligned16(rew) && ((reinterpret_cast<uintptr_t>(done) & 3u) == 0);
   static const int threads = [] {   // tuning knob: ML4CA_ENV_THREADS=64|128|256
     const char* e = getenv("ML4CA_ENV_THREADS");
     const int t = e ? atoi(e) : 256;
@@ -56,7 +56,6 @@ static int launch_step_vec(const ml4ca_env* e, const float* action, float* obs, 
     const char* e = getenv("ML4CA_ENV_VEC");
     return e ? atoi(e) : 2;
   }();
-  const EnvParams& p = e->p;
   const int vec = (vec4 && (vec_pref == 4 || vec_pref == 2)) ? vec_pref : 1;
   if (vec == 4) {
     const int64_t blocks = (n / 4 + threads - 1) / threads;
@@ -71,15 +70,16 @@ static int launch_step_vec(const ml4ca_env* e, const float* action, float* obs, 
   return check_launch("env_step_kernel");
 }
 
-int UNIT_NAME(const ml4ca_env* e, const float* action, float* obs, float* rew, uint8_t* done, cudaStream_t st) {
+int UNIT_NAME(const ml4ca_env* e, const EnvParams& p, const float* action, float* obs, float* rew, uint8_t* done,
+              cudaStream_t st) {
   if (e->cfg.extended_state) {
 #if ML4CA_STEP_UNIT == 1
     return ML4CA_ERR_UNSUPPORTED;
 #else
-    return launch_step_vec<UNIT_KIND, UNIT_CONT, true>(e, action, obs, rew, done, st);
+    return launch_step_vec<UNIT_KIND, UNIT_CONT, true>(e, p, action, obs, rew, done, st);
 #endif
   }
-  return launch_step_vec<UNIT_KIND, UNIT_CONT, false>(e, action, obs, rew, done, st);
+  return launch_step_vec<UNIT_KIND, UNIT_CONT, false>(e, p, action, obs, rew, done, st);
 }
 
 int UNIT_RESET(const ml4ca_env* e, const EnvParams& p, const uint8_t* mask, const float* eta, const float* nu,

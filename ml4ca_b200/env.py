@@ -231,6 +231,16 @@ class Revolt(object):
         _lib.check(_lib.lib().ml4ca_env_step(self._handle, _lib.ptr(action), _lib.ptr(obs), _lib.ptr(rew),
                                              _lib.ptr(done), self._stream()), "ml4ca_env_step")
 
+    def step_host(self, action, obs, rew, done):
+        """``step`` for HOST buffers (float32 CPU tensors, ideally pinned): ``action [act_dim, n]`` in, ``obs``,
+        ``rew``, ``done`` (uint8 flag byte) out, through the chunked copy/compute pipeline of
+        ml4ca_env_step_host.  Asynchronous: synchronise the current stream before reading the outputs."""
+        for t, dt in ((action, torch.float32), (obs, torch.float32), (rew, torch.float32), (done, torch.uint8)):
+            assert t.device.type == "cpu" and t.dtype == dt and t.is_contiguous(), "host buffers: contiguous CPU tensors"
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ml4ca_env_step_host(self._handle, action.data_ptr(), obs.data_ptr(), rew.data_ptr(),
+                                                      done.data_ptr(), self._stream()), "ml4ca_env_step_host")
+
     # -- gym API -------------------------------------------------------------------------------------
     def step(self, action, new_ref=None, out=None):
         """customEnv.py:92-133 -> (state, reward, done, info).

@@ -203,6 +203,26 @@ def test_full_size_properties(cuda_device):
     assert bool((o2[6:9] == st['prev_thrust'] / hundred).all())         # obs tail = previous step's thrust / 100
 
 
+@pytest.mark.parametrize("n", [1001, 4096, 3 * (1 << 20) + 1000])
+def test_step_host_pipeline_equals_device_step(cuda_device, n):
+    """ml4ca_env_step_host (chunked H2D | kernel | D2H pipeline) returns exactly what the device-buffer step returns."""
+    envA = make_env('final', True, True, n, seed=11, auto_reset=True, max_ep_len=12)
+    envB = make_env('final', True, True, n, seed=11, auto_reset=True, max_ep_len=12)
+    envA.reset(); envB.reset()
+    g = torch.Generator(); g.manual_seed(n)
+    h_obs, h_rew = torch.empty(9, n).pin_memory(), torch.empty(n).pin_memory()
+    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    for t in range(8):
+        h_act = (torch.rand(7, n, generator=g) * 2.4 - 1.2).pin_memory()
+        envA.step_host(h_act, h_obs, h_rew, h_done)
+        o, r, d, info = envB.step(h_act.to(cuda_device))
+        torch.cuda.synchronize()
+        assert torch.equal(h_obs, o.cpu()) and torch.equal(h_rew, r.cpu()) and torch.equal(h_done, info['flags'].cpu())
+    sA, sB = envA.get_state(), envB.get_state()
+    for k in sA:
+        assert torch.equal(sA[k], sB[k]), k
+
+
 def test_bad_arguments_raise(cuda_device):
     import ml4ca_b200.env as E
     with pytest.raises(AssertionError):
