@@ -31,6 +31,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ENV_STEP_BYTES = 177      # read 60 state + 28 action, write 48 state + 36 obs + 4 rew + 1 done
+ENV_STEP_TRAFFIC = 3.0087e9  # measured DRAM bytes of one 16 Mi-env launch (profiles/env_step_r1.md); algorithmic: 2.9696e9
 PINV_PID_BYTES = 80       # read eta, nu, ref, integ (48) + write integ, n, alpha (32)
 QP_BYTES = 68             # read tau 3 + prev 5 words, write x 8 + status 1
 POLICY_BYTES = 72         # read obs 36, write action 28 + value 4 + logp 4
@@ -376,8 +377,9 @@ def run_b200(args, rank, local_rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
-                         "kernel": "env_step_kernel<FINAL,cont,ext,vec4>", "bytes_per_env_step": ENV_STEP_BYTES,
+                         "frac": achieved / peak_gbs, "traffic": ENV_STEP_TRAFFIC, "peak_source": peak_src,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/env_step_r1.md",
+                         "kernel": "env_step_kernel<FINAL,cont,ext,2 envs/thread>", "bytes_per_env_step": ENV_STEP_BYTES,
                          "kernel_ms": kernel_ms},
             "cpu_baseline": {"value": cpu_val, "unit": "env-steps/s", "cores": cpu_cores, "kind": "port",
                              "sample": cpu_sample},
