@@ -93,6 +93,9 @@ ML4CA_API int ml4ca_env_step(ml4ca_env* env, const float* action, float* obs, fl
  * resumes when the last result bytes have landed (synchronise it before reading the host buffers). */
 ML4CA_API int ml4ca_env_step_host(ml4ca_env* env, const float* action_host, float* obs_host, float* rew_host,
                                   uint8_t* done_host, void* stream);
+/* Revolt.state() / state_extended() (customEnv.py:196-205) of the current state: obs [obs_dim, n].  With the extended
+ * state this needs the previous-thrust tail, which the library keeps after reset and ml4ca_rollout_step only. */
+ML4CA_API int ml4ca_env_observe(ml4ca_env* env, float* obs, void* stream);
 /* Copies of the SoA state (any pointer may be NULL): eta [3,n], nu [3,n], prev_thrust [3,n] (env order bow, port,
  * star), angles [3,n] (current_angles, customEnv.py:71), ep_len [n].  Also EF.get_NED_pos (errorFrame.py:19). */
 ML4CA_API int ml4ca_env_get_state(ml4ca_env* env, float* eta, float* nu, float* prev_thrust, float* angles, int32_t* ep_len,
@@ -150,6 +153,8 @@ ML4CA_API int ml4ca_policy_create(const ml4ca_policy_cfg* cfg, const float* para
 ML4CA_API int ml4ca_policy_destroy(ml4ca_policy* p);
 /* device pointer of the fp32 master parameters (an optimizer updates them in place) ... */
 ML4CA_API float* ml4ca_policy_params(ml4ca_policy* p);
+/* the cfg a policy was created with, and its device */
+ML4CA_API int ml4ca_policy_describe(const ml4ca_policy* p, ml4ca_policy_cfg* cfg, int32_t* device);
 /* ... and re-derives the operand image afterwards */
 ML4CA_API int ml4ca_policy_refresh(ml4ca_policy* p, void* stream);
 /* get_action_ops = [pi, v, logp_pi] of ppo.py:221,291: obs [obs_dim, n] -> act [act_dim, n] = mu + eps * exp(log_std)
@@ -175,6 +180,23 @@ ML4CA_API int ml4ca_gae(int64_t n, int32_t T, const float* rew, const float* val
 ML4CA_API int ml4ca_stats(int64_t m, const float* x, double* out3, void* stream);
 /* advantage normalisation x <- (x - mean) / (std + 1e-8) (ppo.py:103). */
 ML4CA_API int ml4ca_normalize(int64_t m, float* x, float mean, float std, void* stream);
+
+/* ---- PPO update (ppo.py:234-250,260-280; mpi_tf.py:45-80) --------------------------------------------------------------
+ * Gradient of ONE loss over a whole trajectory buffer: net 0 = pi_loss = -mean(min(ratio adv, clip(ratio) adv)) w.r.t. the
+ * pi variables and log_std, net 1 = v_loss = mean((ret - v)^2) w.r.t. the v variables.  obs [T, obs_dim, n],
+ * act [T, act_dim, n], adv / ret / logp_old [T, n] (the layout ml4ca_rollout_step records).  SUM convention: grad
+ * (flat, parameter order, overwritten: the other net's block is zero) and stats hold sums over the LOCAL samples; the
+ * caller all-reduces them over ranks and divides by the global sample count -- Allreduce(SUM) / num_procs of
+ * mpi_tf.py:59-62 with equal shards.  stats (8 doubles, device): [0] sum min(ratio adv, min_adv) (= -N pi_loss),
+ * [1] sum (ret - v)^2, [2] sum 0.5 (logp_old - logp)^2 (approx_kl), [3] sum -logp (approx_ent), [4] clipped count,
+ * [5] sample count.  Supported network: hidden 64 x 64 (the BASELINE training config). */
+ML4CA_API int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const float* obs, const float* act,
+                             const float* adv, const float* ret, const float* logp_old, float clip_ratio, float* grad,
+                             double* stats, void* stream);
+/* tf.train.AdamOptimizer step (beta1 0.9, beta2 0.999, eps 1e-8 in the reference) on m parameters:
+ * g = grad * grad_scale; m1, m2 moment buffers; t = 1-based step count of this optimizer. */
+ML4CA_API int ml4ca_adam_step(int64_t m, float* params, const float* grad, float* m1, float* m2, float lr, float beta1,
+                              float beta2, float eps, int32_t t, float grad_scale, void* stream);
 
 ML4CA_API const char* ml4ca_last_error(void);
 /* "ml4ca_b200 <version> sm_100a" */

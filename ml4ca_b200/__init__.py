@@ -15,6 +15,7 @@ from .env import ErrorFrame, Revolt, RevoltFinal, RevoltLimited, RevoltSimple  #
 from .pinv import pinv_allocate, pinv_pid  # noqa: F401
 from .qp_allocator import QPTA  # noqa: F401
 from .core import ActorCritic, mlp_actor_critic  # noqa: F401
-from .ppo import TrajectoryBuffer, rollout  # noqa: F401
+from .ppo import PPOUpdater, TrajectoryBuffer, ppo, rollout  # noqa: F401
+from .env import StandInHull  # noqa: F401
 
 __version__ = "0.1.0"

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "ml4ca_env_reset_to": (ctypes.c_int, [ctypes.c_void_p, c_u8p, c_f32p, c_f32p, c_f32p, c_stream]),
     "ml4ca_env_set_ref": (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_stream]),
     "ml4ca_env_step": (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_u8p, c_stream]),
+    "ml4ca_env_observe": (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_stream]),
     "ml4ca_env_step_host": (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_u8p, c_stream]),
     "ml4ca_env_get_state": (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_stream]),
     "ml4ca_env_size": (ctypes.c_int64, [ctypes.c_void_p]),
@@ -70,6 +71,11 @@ _SIGNATURES = {
                                  c_f32p, c_f32p, c_stream]),
     "ml4ca_stats": (ctypes.c_int, [ctypes.c_int64, c_f32p, ctypes.c_void_p, c_stream]),
     "ml4ca_normalize": (ctypes.c_int, [ctypes.c_int64, c_f32p, ctypes.c_float, ctypes.c_float, c_stream]),
+    "ml4ca_policy_describe": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PolicyCfg), ctypes.POINTER(ctypes.c_int32)]),
+    "ml4ca_ppo_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_f32p,
+                                      c_f32p, c_f32p, ctypes.c_float, c_f32p, ctypes.c_void_p, c_stream]),
+    "ml4ca_adam_step": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_float, ctypes.c_float,
+                                       ctypes.c_float, ctypes.c_float, ctypes.c_int32, ctypes.c_float, c_stream]),
     "ml4ca_last_error": (ctypes.c_char_p, []),
     "ml4ca_version": (ctypes.c_char_p, []),
     "ml4ca_launch_count": (ctypes.c_int64, []),

@@ -17,6 +17,17 @@ __global__ void __launch_bounds__(256) error_frame_kernel(int64_t n, const float
   err[i] = xb, err[n + i] = yb, err[2 * n + i] = pb;
 }
 
+// Revolt.state() / state_extended() (customEnv.py:196-205) from the state in HBM.
+__global__ void __launch_bounds__(256) observe_kernel(const EnvParams p, int ext, float* __restrict__ obs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n = p.n;
+  if (i >= n) return;
+  float xb, yb, pb;
+  error_frame(p.eta[i], p.eta[n + i], p.eta[2 * n + i], p.ref[i], p.ref[n + i], p.ref[2 * n + i], xb, yb, pb);
+  obs[i] = xb, obs[n + i] = yb, obs[2 * n + i] = pb;
+  obs[3 * n + i] = p.nu[i], obs[4 * n + i] = p.nu[n + i], obs[5 * n + i] = p.nu[2 * n + i];
+  if (ext) obs[6 * n + i] = p.obs_tail[i], obs[7 * n + i] = p.obs_tail[n + i], obs[8 * n + i] = p.obs_tail[2 * n + i];
+}
+
 __global__ void __launch_bounds__(256) unpack_ep_len_kernel(int64_t n, const int32_t* __restrict__ word,
                                                             int32_t* __restrict__ ep_len) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -336,6 +347,17 @@ int ml4ca_env_step_host(ml4ca_env* env, const float* action_host, float* obs_hos
   // the caller's stream resumes when the last copies have landed (the other slot finished earlier on s_out)
   ML4CA_CUDA(cudaStreamWaitEvent(user, hp->ev_out[(int)((k - 1) & 1)], 0));
   return ML4CA_OK;
+}
+
+int ml4ca_env_observe(ml4ca_env* env, float* obs, void* stream) {
+  ML4CA_REQUIRE(env != nullptr && obs != nullptr, "env and obs are required");
+  ML4CA_REQUIRE(!env->cfg.extended_state || env->tail_valid,
+                "the previous-thrust tail of the observation is only kept by reset and ml4ca_rollout_step; after "
+                "ml4ca_env_step the observation lives in the caller's obs buffer");
+  DeviceGuard guard(env->device);
+  observe_kernel<<<(unsigned)((env->n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      env->p, env->cfg.extended_state, obs);
+  return check_launch("observe_kernel");
 }
 
 int ml4ca_env_get_state(ml4ca_env* env, float* eta, float* nu, float* prev_thrust, float* angles, int32_t* ep_len,

@@ -616,6 +616,14 @@ int ml4ca_policy_destroy(ml4ca_policy* p) {
 
 float* ml4ca_policy_params(ml4ca_policy* p) { return p ? p->params : nullptr; }
 
+int ml4ca_policy_describe(const ml4ca_policy* p, ml4ca_policy_cfg* cfg, int32_t* device) {
+  ML4CA_REQUIRE(p != nullptr && cfg != nullptr, "policy and cfg are required");
+  cfg->obs_dim = p->d.obs, cfg->act_dim = p->d.act, cfg->hidden = p->d.H, cfg->n_hidden = p->d.NL;
+  cfg->activation = p->d.activation, cfg->reserved = 0;
+  if (device) *device = p->device;
+  return ML4CA_OK;
+}
+
 int ml4ca_policy_refresh(ml4ca_policy* p, void* stream) {
   ML4CA_REQUIRE(p != nullptr, "policy is NULL");
   return repack(p, static_cast<cudaStream_t>(stream));

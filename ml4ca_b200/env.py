@@ -325,6 +325,13 @@ class Revolt(object):
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().ml4ca_env_set_ref(self._handle, _lib.ptr(self._ref), self._stream()))
 
+    def observe(self):
+        """state() / state_extended() (customEnv.py:196-205) of the current device-side state."""
+        obs = torch.empty_like(self._obs)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ml4ca_env_observe(self._handle, _lib.ptr(obs), self._stream()), "ml4ca_env_observe")
+        return obs
+
     def get_state(self):
         n = self.num_envs
         f = lambda rows: torch.empty(rows, n, dtype=torch.float32, device=self.device)

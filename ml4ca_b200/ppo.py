@@ -90,3 +90,118 @@ def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, fused=False
         obs, nxt = nxt, obs
     env._obs = obs
     return obs
+
+
+class PPOUpdater(object):
+    """The update() closure of ppo.py:260-280 for a device-resident buffer: full-batch gradient of pi_loss / v_loss by
+    one kernel launch each (ml4ca_ppo_grad), ONE all-reduce of the flat gradient with the loss statistics in its tail
+    (MpiAdamOptimizer.compute_gradients, mpi_tf.py:59-62), TF-1 Adam on the flat master parameters (ml4ca_adam_step),
+    early stopping of the policy iterations on the rank-averaged approx-KL (ppo.py:268-271)."""
+
+    def __init__(self, ac, clip_ratio=0.2, pi_lr=3e-4, vf_lr=1e-3, train_pi_iters=80, train_v_iters=80, target_kl=0.01):
+        self.ac = ac
+        self.clip_ratio, self.pi_lr, self.vf_lr = float(clip_ratio), float(pi_lr), float(vf_lr)
+        self.train_pi_iters, self.train_v_iters, self.target_kl = int(train_pi_iters), int(train_v_iters), float(target_kl)
+        dev, P = ac.device, ac.num_params
+        self.n_pi = ac.var_counts[0]                 # pi variables + log_std come first in the flat vector
+        self.flat = torch.zeros(P + 8, dtype=torch.float32, device=dev)      # gradient | 5 statistics (+ pad)
+        self.stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.m1 = torch.zeros(P, dtype=torch.float32, device=dev)
+        self.m2 = torch.zeros(P, dtype=torch.float32, device=dev)
+        self.t_pi = self.t_v = 0
+
+    # -- one gradient pass: returns the rank-summed statistics as a list of 5 floats and the global sample count ------
+    def _grad(self, net, data, T, n):
+        obs, act, adv, ret, logp = data
+        L, ac = _lib.lib(), self.ac
+        with torch.cuda.device(ac.device):
+            _lib.check(L.ml4ca_ppo_grad(ac._handle, int(net), int(n), int(T), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(adv),
+                                        _lib.ptr(ret), _lib.ptr(logp), self.clip_ratio, _lib.ptr(self.flat),
+                                        _lib.ptr(self.stats), _lib.current_stream()), "ml4ca_ppo_grad")
+        from . import mpi_tools
+        P = ac.num_params
+        self.flat[P:P + 5].copy_(self.stats[:5])
+        mpi_tools.allreduce_sum_(self.flat)
+        count = float(T) * float(n) * mpi_tools.num_procs()   # equal shards (mpi_tools.shard_bounds differ by <= 1 env)
+        return self.flat[P:P + 5].tolist(), count
+
+    def _adam(self, net, count):
+        ac, L = self.ac, _lib.lib()
+        lo, hi = (0, self.n_pi) if net == 0 else (self.n_pi, ac.num_params)
+        if net == 0:
+            self.t_pi += 1
+        else:
+            self.t_v += 1
+        t, lr = (self.t_pi, self.pi_lr) if net == 0 else (self.t_v, self.vf_lr)
+        params = ac.parameters()
+        with torch.cuda.device(ac.device):
+            _lib.check(L.ml4ca_adam_step(hi - lo, _lib.ptr(params[lo:hi]), _lib.ptr(self.flat[lo:hi]), _lib.ptr(self.m1[lo:hi]),
+                                         _lib.ptr(self.m2[lo:hi]), lr, 0.9, 0.999, 1e-8, t, 1.0 / count,
+                                         _lib.current_stream()), "ml4ca_adam_step")
+        ac.refresh()
+
+    def losses(self, data, T, n):
+        """pi_loss, v_loss, approx_kl, approx_ent, clipfrac at the current parameters (ppo.py:262,275)."""
+        s, c = self._grad(0, data, T, n)
+        out = {"LossPi": -s[0] / c, "KL": s[2] / c, "Entropy": s[3] / c, "ClipFrac": s[4] / c}
+        s, c = self._grad(1, data, T, n)
+        out["LossV"] = s[1] / c
+        return out
+
+    def update(self, buf):
+        """ppo.py:260-280.  ``buf`` = a TrajectoryBuffer after finish_path(); returns the logger's dictionary."""
+        data = buf.get()
+        T, n = buf.max_size, buf.num_envs
+        info, stop = {}, 0
+        for i in range(self.train_pi_iters):
+            s, c = self._grad(0, data, T, n)          # loss statistics belong to the parameters BEFORE this step
+            if i == 0:
+                info.update(LossPi=-s[0] / c, Entropy=s[3] / c)
+            self._adam(0, c)
+            stop = i
+            if s[2] / c > 1.5 * self.target_kl:       # kl = mpi_avg(kl), :268-271 (the step of this iteration is applied)
+                break
+        info["StopIter"] = stop
+        for i in range(self.train_v_iters):
+            s, c = self._grad(1, data, T, n)
+            if i == 0:
+                info["LossV"] = s[1] / c
+            self._adam(1, c)
+        new = self.losses(data, T, n)
+        info.update(KL=new["KL"], ClipFrac=new["ClipFrac"], DeltaLossPi=new["LossPi"] - info.get("LossPi", new["LossPi"]),
+                    DeltaLossV=new["LossV"] - info.get("LossV", new["LossV"]))
+        return info
+
+
+def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2, pi_lr=3e-4, vf_lr=1e-3,
+        train_pi_iters=80, train_v_iters=80, lam=0.97, target_kl=0.01, seed=0, hidden_sizes=(64, 64),
+        activation="leaky_relu", fused=False, logger=None):
+    """ppo.py:107-346 for a batched env: every epoch = ``steps_per_epoch`` steps of EVERY environment of ``env``
+    (rollout), GAE-lambda (finish_path), advantage normalisation over all ranks, then the PPO update.
+    Hyper-parameter defaults are the reference's config.json.  Returns (ac, list of per-epoch dictionaries)."""
+    from . import mpi_tools
+    from .core import ActorCritic
+    n = env.num_envs
+    if ac is None:
+        ac = ActorCritic(env.num_states, env.num_actions, hidden_sizes, activation, device=env.device, seed=seed)
+    params = ac.parameters()
+    mpi_tools.sync_all_params(params)             # ppo.py:255
+    ac.refresh()
+    buf = TrajectoryBuffer(env.num_states, env.num_actions, steps_per_epoch, n, gamma, lam, device=env.device)
+    upd = PPOUpdater(ac, clip_ratio, pi_lr, vf_lr, train_pi_iters, train_v_iters, target_kl)
+    env.reset(fraction=0.8)
+    history, step = [], 0
+    for epoch in range(epochs):
+        o_last = rollout(env, ac, buf, seed=seed, start_step=step, fused=fused)
+        step += steps_per_epoch
+        if o_last is None:                        # fused path: the observation is rebuilt from the env state
+            o_last = env.observe()
+        _, v_last, _ = ac.step(o_last, deterministic=True, step=step)
+        buf.finish_path(last_val=v_last)          # ppo.py:311 for the envs still running at the epoch end
+        rew_mean = float(mpi_tools.mpi_avg(buf.rew_buf.mean().item()))
+        info = upd.update(buf)
+        info.update(Epoch=epoch, AverageStepReward=rew_mean, TotalEnvInteracts=(epoch + 1) * steps_per_epoch * n * mpi_tools.num_procs())
+        history.append(info)
+        if logger is not None:
+            logger(info)
+    return ac, history

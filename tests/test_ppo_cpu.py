@@ -68,3 +68,50 @@ def test_collectives_world_size_2_gloo():
         assert o['grad'] == [1.5] * 7                 # mean of 1 and 2: Allreduce(SUM) / num_procs (mpi_tf.py:59-62)
         assert o['params'] == [0.0] * 5               # broadcast from rank 0 (mpi_tf.py:24-27)
         assert abs(o['kl'] - 0.015) < 1e-15           # mpi_avg (mpi_tools.py:67-69)
+
+
+def test_gradient_oracle_matches_torch_autograd():
+    """oracle.ppo_oracle.ppo_gradients (analytic, float64) == torch autograd of the losses written as in ppo.py:234-237
+    with core.py's gaussian_likelihood: pins the checker the GPU update kernel is compared with."""
+    from oracle import mlp_oracle as MO
+    dims = dict(obs_dim=9, act_dim=7, hidden=64, n_hidden=2)
+    for actn in ("leaky_relu", "tanh"):
+        rng = np.random.default_rng(0)
+        N = 300
+        base = MO.glorot_params(dims, 3).astype(np.float64)
+        flat = base + rng.normal(size=base.size) * 0.05
+        obs, act = rng.normal(size=(N, 9)), rng.normal(size=(N, 7))
+        adv, ret = rng.normal(size=N), rng.normal(size=N) * 3
+        fo = MO.forward(flat * 1.02, dims, obs.T, actn)
+        lpo = MO.gaussian_likelihood(act, fo["mu"].T, fo["log_std"])
+        g, info = PO.ppo_gradients(flat, dims, obs, act, adv, ret, lpo, 0.2, actn)
+        p = torch.tensor(flat, requires_grad=True)
+        pos = [0]
+
+        def take(*shape):
+            k = int(np.prod(shape))
+            t = p[pos[0]:pos[0] + k].reshape(*shape)
+            pos[0] += k
+            return t
+
+        def net(o):
+            sizes = [9, 64, 64, o]
+            return [(take(sizes[i], sizes[i + 1]), take(sizes[i + 1])) for i in range(3)]
+
+        pi, ls, vl = net(7), take(7), net(1)
+        f = (lambda z: torch.where(z > 0, z, 0.2 * z)) if actn == "leaky_relu" else torch.tanh
+
+        def mlp(x, L):
+            for W, b in L[:-1]:
+                x = f(x @ W + b)
+            return x @ L[-1][0] + L[-1][1]
+
+        x = torch.tensor(obs)
+        mu, v = mlp(x, pi), mlp(x, vl)[:, 0]
+        logp = (-0.5 * (((torch.tensor(act) - mu) / (torch.exp(ls) + 1e-8)) ** 2 + 2 * ls + np.log(2 * np.pi))).sum(1)
+        ratio, a = torch.exp(logp - torch.tensor(lpo)), torch.tensor(adv)
+        pi_loss = -torch.minimum(ratio * a, torch.where(a > 0, 1.2 * a, 0.8 * a)).mean()
+        v_loss = ((torch.tensor(ret) - v) ** 2).mean()
+        (pi_loss + v_loss).backward()
+        np.testing.assert_allclose(p.grad.numpy(), g, rtol=0, atol=1e-12)
+        assert abs(pi_loss.item() - info["pi_loss"]) < 1e-12 and abs(v_loss.item() - info["v_loss"]) < 1e-12

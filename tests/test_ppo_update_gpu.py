@@ -1,0 +1,98 @@
+"""GPU parity of K6 (PPO gradients, loss statistics, Adam) against the float64 restatement of ppo.py:234-250, which is
+itself cross-checked against torch autograd in tests/test_ppo_cpu.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mlp_oracle as MO
+from oracle import ppo_oracle as PO
+
+pytestmark = pytest.mark.gpu
+
+DIMS = dict(obs_dim=9, act_dim=7, hidden=64, n_hidden=2)
+
+
+def _batch(T, n, seed):
+    rng = np.random.default_rng(seed)
+    obs = rng.normal(size=(T, 9, n)).astype(np.float32) * np.array([2, 2, .3, .5, .1, .2, .5, .5, .5], dtype=np.float32)[None, :, None]
+    act = rng.normal(size=(T, 7, n)).astype(np.float32)
+    adv = rng.normal(size=(T, n)).astype(np.float32)
+    ret = (rng.normal(size=(T, n)) * 3).astype(np.float32)
+    return obs, act, adv, ret
+
+
+def _flatten(x):          # [T, c, n] -> [T * n, c] in (t, i) order
+    return np.ascontiguousarray(np.moveaxis(x, 1, 2).reshape(-1, x.shape[1])).astype(np.float64)
+
+
+@pytest.mark.parametrize("activation", ["leaky_relu", "tanh"])
+@pytest.mark.parametrize("T,n", [(1, 128), (3, 1000), (2, 40000)])
+def test_gradients_and_statistics(cuda_device, activation, T, n):
+    import ml4ca_b200 as M
+    flat = MO.glorot_params(DIMS, seed=5)
+    flat = (flat + np.random.default_rng(1).normal(size=flat.size).astype(np.float32) * 0.05).astype(np.float32)   # non-zero biases
+    ac = M.ActorCritic(9, 7, (64, 64), activation, params=flat, device=cuda_device)
+    obs, act, adv, ret = _batch(T, n, seed=T * n)
+    # logp_old from a slightly different policy, so that ratios spread around 1 and some samples clip
+    fo = MO.forward((flat * 1.02).astype(np.float32), DIMS, _flatten(obs).T, activation)
+    logp_old = MO.gaussian_likelihood(_flatten(act), fo["mu"].T, fo["log_std"]).astype(np.float32).reshape(T, n)
+    g64, info = PO.ppo_gradients(flat.astype(np.float64), DIMS, _flatten(obs), _flatten(act), adv.reshape(-1).astype(np.float64),
+                                 ret.reshape(-1).astype(np.float64), logp_old.reshape(-1).astype(np.float64), 0.2, activation)
+    upd = M.PPOUpdater(ac)
+    dev = lambda x: torch.as_tensor(x, device=cuda_device).contiguous()
+    data = (dev(obs), dev(act), dev(adv), dev(ret), dev(logp_old))
+    n_pi = ac.var_counts[0]
+    N = float(T * n)
+    s, c = upd._grad(0, data, T, n)
+    assert c == N
+    g_pi = upd.flat[:ac.num_params].cpu().numpy().astype(np.float64) / N
+    assert (g_pi[n_pi:] == 0).all()                     # the v block is untouched by the pi pass
+    scale = np.abs(g64[:n_pi]).max()
+    np.testing.assert_allclose(g_pi[:n_pi], g64[:n_pi], rtol=0, atol=2e-4 * scale)
+    assert abs(-s[0] / N - info["pi_loss"]) < 1e-5 * max(1, abs(info["pi_loss"]))
+    assert abs(s[2] / N - info["approx_kl"]) < 1e-5 * max(1e-3, info["approx_kl"]) + 1e-7
+    assert abs(s[3] / N - info["approx_ent"]) < 1e-5 * abs(info["approx_ent"])
+    assert abs(s[4] / N - info["clipfrac"]) <= 2.0 / N + 1e-4      # a ratio within fp32 rounding of the clip edge may flip
+    s, c = upd._grad(1, data, T, n)
+    g_v = upd.flat[:ac.num_params].cpu().numpy().astype(np.float64) / N
+    assert (g_v[:n_pi] == 0).all()
+    scale = np.abs(g64[n_pi:]).max()
+    np.testing.assert_allclose(g_v[n_pi:], g64[n_pi:], rtol=0, atol=2e-4 * scale)
+    assert abs(s[1] / N - info["v_loss"]) < 1e-5 * info["v_loss"]
+
+
+def test_adam_step_matches_tf1_formula(cuda_device):
+    from ml4ca_b200 import _lib
+    rng = np.random.default_rng(0)
+    m = 5001
+    p = rng.normal(size=m).astype(np.float32); g = rng.normal(size=m).astype(np.float32) * 123.0
+    p64, m1, m2 = p.astype(np.float64), np.zeros(m), np.zeros(m)
+    tp, tg = torch.as_tensor(p, device=cuda_device), torch.as_tensor(g, device=cuda_device)
+    t1, t2 = torch.zeros(m, device=cuda_device), torch.zeros(m, device=cuda_device)
+    for t in range(1, 6):
+        _lib.check(_lib.lib().ml4ca_adam_step(m, _lib.ptr(tp), _lib.ptr(tg), _lib.ptr(t1), _lib.ptr(t2), 3e-4, 0.9, 0.999, 1e-8, t,
+                                              1.0 / 123.0, _lib.current_stream()))
+        p64, m1, m2 = PO.adam_step(p64, g.astype(np.float64) / 123.0, m1, m2, 3e-4, t)
+    np.testing.assert_allclose(tp.cpu().numpy(), p64, rtol=0, atol=2e-6)
+
+
+def test_update_improves_the_surrogate_and_stops_on_kl(cuda_device):
+    """PPOUpdater.update on a synthetic buffer: the v-loss falls, the pi iterations stop once approx-KL > 1.5 target,
+    and the parameters actually used by the tensor-core forward follow the fp32 master copy (refresh)."""
+    import ml4ca_b200 as M
+    T, n = 4, 8192
+    ac = M.ActorCritic(9, 7, (64, 64), "leaky_relu", device=cuda_device, seed=1)
+    obs, act, adv, ret = _batch(T, n, seed=9)
+    buf = M.TrajectoryBuffer(9, 7, T, n, device=cuda_device)
+    buf.obs_buf.copy_(torch.as_tensor(obs)); buf.act_buf.copy_(torch.as_tensor(act))
+    buf.adv_buf.copy_(torch.as_tensor(adv)); buf.ret_buf.copy_(torch.as_tensor(ret))
+    flat0 = ac.parameters().clone()
+    fo = MO.forward(flat0.cpu().numpy(), DIMS, _flatten(obs).T, "leaky_relu")
+    buf.logp_buf.copy_(torch.as_tensor(MO.gaussian_likelihood(_flatten(act), fo["mu"].T, fo["log_std"]).reshape(T, n), dtype=torch.float32))
+    mu_before = ac.step(buf.obs_buf[0], deterministic=True)[0].clone()
+    upd = M.PPOUpdater(ac, train_pi_iters=80, train_v_iters=20, target_kl=1e-4)
+    info = upd.update(buf)
+    assert info["DeltaLossV"] < 0 and info["DeltaLossPi"] < 0
+    assert 0 < info["StopIter"] < 79 and info["KL"] > 1.5e-4      # stopped by the KL rule, with that step applied
+    assert not torch.equal(flat0, ac.parameters())
+    assert not torch.equal(mu_before, ac.step(buf.obs_buf[0], deterministic=True)[0])
