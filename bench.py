@@ -362,6 +362,30 @@ def run_b200(args, rank, local_rank, world):
         except Exception as e:  # noqa: BLE001
             extra["policy_rollout"] = {"error": repr(e)}
 
+    if not args.skip_extra:
+        # config 5: full PPO training (rollout, GAE, update with the gradient all-reduce over all ranks)
+        try:
+            ne, Tp = 1 << 14, 400
+            env3 = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=ne, device=dev, seed=5,
+                               auto_reset=True, env_id_offset=rank * ne)
+            ac3 = M.ActorCritic(9, 7, (64, 64), "leaky_relu", device=dev, seed=5)
+            M.ppo(env3, ac3, steps_per_epoch=Tp, epochs=1, seed=5)          # warm-up epoch (also syncs parameters)
+            barrier()
+            t0 = time.perf_counter()
+            _, hist = M.ppo(env3, ac3, steps_per_epoch=Tp, epochs=2, seed=6)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0) / 2
+            passes = sum(h["StopIter"] + 1 + 80 + 2 for h in hist) / 2.0
+            extra["ppo_train"] = {"workload": "BASELINE configs[4]: PPO epoch = 400-step rollout of 16 Ki envs/GPU + GAE + update "
+                                              "(config.json hyper-parameters: <= 80 pi + 80 v full-batch Adam iterations, target_kl 0.01), "
+                                              "NCCL all-reduce of the flat gradient per iteration",
+                                  "value": ne * world * Tp / dt, "unit": "env-steps/s incl. update", "s_per_epoch": dt,
+                                  "gradient_passes_per_epoch": passes,
+                                  "sample_passes_per_s": passes * ne * world * Tp / dt, "last_epoch": {k: hist[-1][k] for k in ("StopIter", "KL", "LossV", "AverageStepReward")}}
+            del env3, ac3
+        except Exception as e:  # noqa: BLE001
+            extra["ppo_train"] = {"error": repr(e)}
+
     sampler.stop_flag.set()
     sampler.join(timeout=1.0)
     clocks = sampler.summary()
