@@ -16,6 +16,15 @@ def _on():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+def _comm_device(t=None):
+    """Where a scalar must live for the collective: NCCL reduces CUDA tensors only (gloo takes CPU tensors)."""
+    if t is not None and t.is_cuda:
+        return t.device
+    if _on() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
 def proc_id():
     return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
 
@@ -42,13 +51,14 @@ def allreduce_sum_(t):
 
 def mpi_avg(x):
     """Average a scalar / tensor over ranks (:67-69)."""
-    t = x if torch.is_tensor(x) else torch.tensor(float(x), dtype=torch.float64)
     if not _on():
         return x
-    t = t.clone()
+    t = x if torch.is_tensor(x) else torch.tensor(float(x), dtype=torch.float64)
+    src = t.device
+    t = t.to(_comm_device(t), copy=True)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     t /= num_procs()
-    return t if torch.is_tensor(x) else float(t.item())
+    return t.to(src) if torch.is_tensor(x) else float(t.item())
 
 
 def average_gradients_(flat_grad):
@@ -79,6 +89,7 @@ def statistics_from_sums(sums3):
 def mpi_statistics_scalar(x, with_min_and_max=False):
     """mpi_statistics_scalar (:71-93) for a tensor on any device."""
     x = torch.as_tensor(x).to(torch.float64).reshape(-1)
+    x = x.to(_comm_device(x))
     sums = torch.stack([x.sum(), (x * x).sum(), torch.tensor(float(x.numel()), dtype=torch.float64, device=x.device)])
     allreduce_sum_(sums)
     mean, std = statistics_from_sums(sums.tolist())
