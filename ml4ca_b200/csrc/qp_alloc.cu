@@ -106,7 +106,7 @@ __device__ __forceinline__ bool cholesky5(float (&H)[5][5]) {
     for (int k = 0; k < j; ++k) d = fmaf(-H[j][k], H[j][k], d);
     ok = ok && (d > 1e-7f * fabsf(H[j][j]) + 1e-20f);
     const float inv = rsqrtf(fmaxf(d, 1e-30f));
-    H[j][j] = d * inv;  // sqrt(d)
+    H[j][j] = inv;  // the factor's diagonal is kept as 1 / sqrt(pivot): the solves multiply instead of dividing
 #pragma unroll
     for (int i = j + 1; i < 5; ++i) {
       float v = H[i][j];
@@ -118,7 +118,7 @@ __device__ __forceinline__ bool cholesky5(float (&H)[5][5]) {
   return ok;
 }
 
-// v = H^-1 a with the Cholesky factor L (lower, L[j][j] = sqrt pivot).
+// v = H^-1 a with the Cholesky factor L (lower, L[j][j] = 1 / sqrt pivot).
 __device__ __forceinline__ void chol_solve5(const float (&L)[5][5], const float (&a)[5], float (&v)[5]) {
   float y[5];
 #pragma unroll
@@ -126,14 +126,14 @@ __device__ __forceinline__ void chol_solve5(const float (&L)[5][5], const float 
     float t = a[i];
 #pragma unroll
     for (int k = 0; k < i; ++k) t = fmaf(-L[i][k], y[k], t);
-    y[i] = t / L[i][i];
+    y[i] = t * L[i][i];
   }
 #pragma unroll
   for (int i = 4; i >= 0; --i) {
     float t = y[i];
 #pragma unroll
     for (int k = i + 1; k < 5; ++k) t = fmaf(-L[k][i], v[k], t);
-    v[i] = t / L[i][i];
+    v[i] = t * L[i][i];
   }
 }
 
