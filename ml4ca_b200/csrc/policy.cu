@@ -18,10 +18,10 @@
 // the epilogue threads themselves; accumulators are fp32 in tensor memory.  Weights (<= 72 KB) are packed once per
 // parameter update into that layout and stay resident in shared memory for the life of the persistent CTA.
 //
-// Warp roles (288 threads, 1 CTA per SM, grid = #SMs): warps 0-3 and 4-7 are two tile groups (thread = one
-// observation = one TMEM lane), warp 8 holds the single MMA-issuing thread.  While one group runs its epilogue on
-// the CUDA cores the tensor core runs the other group's MMA chain; mbarriers carry both directions
-// (a_ready: 128 arrivals after the operand rows are in shared memory; d_ready: tcgen05.commit).
+// Thread roles (1 CTA per SM, grid = #SMs): 4 tile groups of 128 threads for H = 64 (2 for H = 80), thread = one
+// observation = one TMEM lane; thread 0 of a group issues that group's MMA chains after a group-local named
+// barrier (operand rows complete), tcgen05.commit signals the group's mbarrier.  The groups drift out of phase:
+// while some run their epilogue on the CUDA cores the tensor core runs the chains of the others.
 //
 // Numerics: fp16 operands (10-bit mantissa), fp32 accumulation: mu and v carry ~1e-3 relative error against the float64 oracle
 // (stated in tests/test_policy_gpu.py); logp_pi depends only on eps and log_std and is fp32-exact.
@@ -168,7 +168,7 @@ struct PolicySmem {
 };
 
 #ifndef ML4CA_POLICY_G64
-#define ML4CA_POLICY_G64 3   // 4 groups would fit TMEM/smem but cap the kernel at 96 registers (spills): measured slower
+#define ML4CA_POLICY_G64 4   // 4 x 128 accumulator columns = all 512 TMEM columns; 512 threads -> 128 registers each
 #endif
 
 // Tile groups in flight per CTA: limited by tensor memory (512 columns / 2H) and by shared memory.
@@ -176,7 +176,7 @@ template <int H>
 struct PolicyGroups {
   static constexpr int G = (H == 64) ? ML4CA_POLICY_G64 : 2;
   static constexpr int TMEM_STRIDE = (H == 64) ? 128 : 256;
-  static constexpr int THREADS = (4 * G + 1) * 32;
+  static constexpr int THREADS = 4 * G * 32;
 };
 
 struct RolloutOut {   // trajectory slice of one time step (any pointer may be NULL = not recorded)
@@ -199,7 +199,6 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
               float* __restrict__ logp_out, float* __restrict__ mu_out, const EnvParams ep, const RolloutOut ro) {
   using namespace tc05;
   constexpr int G = PolicyGroups<H>::G;
-  constexpr int MMA_WARP = 4 * G;
   extern __shared__ __align__(128) uint8_t smem[];
   const PolicyDims d = pp.d;
   constexpr int KP = H + 16;
@@ -245,7 +244,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
     }
     fence_barrier_init();
   }
-  if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -255,64 +254,51 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
   const int64_t num_tiles = (n + 127) / 128;
   const int64_t tiles_per_round = (int64_t)gridDim.x * G;
   const int64_t rounds = (num_tiles + tiles_per_round - 1) / tiles_per_round;
-  constexpr int kSteps = NL + 1;  // MMA chains per tile
 
-  if (warp == MMA_WARP) {
-    // ===== MMA issuer: one thread =====
-    if (lane == 0) {
-      const uint32_t sb = smem_u32(smem);
-      const uint32_t idesc_l1 = instr_desc_f16(128, 2 * H);
-      const uint32_t idesc_h = instr_desc_f16(128, H);
-      const uint32_t idesc_o = instr_desc_f16(128, 16);
-      const uint32_t b1 = sb + L.blob;
-      const uint32_t bh0 = b1 + d.b1_elems() * 2;
-      const uint32_t bo = bh0 + (NL - 1) * 2 * d.bh_elems() * 2;
-      // Work-conserving service loop: whichever group has its operand rows ready gets its next MMA chain, so the
-      // groups drift apart and the CUDA-core epilogues of some overlap the tensor-core chains of the others.
-      uint32_t phase[G];
-      int sstep[G];
-      int64_t rnd[G];
+  // ===== tile groups: thread = one observation / environment = one TMEM lane.  Thread 0 of a group issues that
+  // group's MMA chains: operand rows -> fence -> group-local named barrier -> tcgen05.mma x k -> commit -> every
+  // thread of the group waits on the mbarrier.  The groups run out of phase, so the CUDA-core epilogue of some
+  // overlaps the tensor-core chains of the others without a dedicated issuing warp (which capped the CTA at
+  // 3 groups: 4 x 128 + 32 threads leave only 96 registers per thread).
+  {
+    const uint32_t sb = smem_u32(smem);
+    const uint32_t idesc_l1 = instr_desc_f16(128, 2 * H);
+    const uint32_t idesc_h = instr_desc_f16(128, H);
+    const uint32_t idesc_o = instr_desc_f16(128, 16);
+    const uint32_t b1 = sb + L.blob;
+    const uint32_t bh0 = b1 + d.b1_elems() * 2;
+    const uint32_t bo = bh0 + (NL - 1) * 2 * d.bh_elems() * 2;
+    auto issue_chain = [&](int g, int s) {   // one elected thread
+      const uint32_t dt = tmem_base + g * PolicyGroups<H>::TMEM_STRIDE;
+      if (s == 0) {
+        mma_f16(dt, smem_desc(sb + L.a0[g], 128, 16 * 16), smem_desc(b1, 128, 16 * 16), idesc_l1, false);
+      } else if (s < NL) {
+        for (int net = 0; net < 2; ++net) {
+          const uint32_t a = sb + L.act[g] + net * (KP / 8) * 128;
+          const uint32_t b = bh0 + ((s - 1) * 2 + net) * d.bh_elems() * 2;
 #pragma unroll
-      for (int g = 0; g < G; ++g) phase[g] = 0, sstep[g] = 0, rnd[g] = 0;
-      int remaining = G;
-      if (rounds == 0) remaining = 0;
-      while (remaining > 0) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          if (rnd[g] >= rounds) continue;
-          if (!mbar_test(&bars[g], phase[g])) continue;
-          phase[g] ^= 1;
-          fence_after_sync();
-          const int s = sstep[g];
-          const uint32_t dt = tmem_base + g * PolicyGroups<H>::TMEM_STRIDE;
-          if (s == 0) {
-            mma_f16(dt, smem_desc(sb + L.a0[g], 128, 16 * 16), smem_desc(b1, 128, 16 * 16), idesc_l1, false);
-          } else if (s < NL) {
-            for (int net = 0; net < 2; ++net) {
-              const uint32_t a = sb + L.act[g] + net * (KP / 8) * 128;
-              const uint32_t b = bh0 + ((s - 1) * 2 + net) * d.bh_elems() * 2;
-#pragma unroll
-              for (int ks = 0; ks < KP / 16; ++ks)
-                mma_f16(dt + net * H, smem_desc(a + ks * 256, 128, 2 * KP * 16), smem_desc(b + ks * 256, 128, KP * 16),
-                        idesc_h, ks > 0);
-            }
-          } else {
-            const uint32_t a = sb + L.act[g];
-#pragma unroll
-            for (int ks = 0; ks < 2 * KP / 16; ++ks)
-              mma_f16(dt, smem_desc(a + ks * 256, 128, 2 * KP * 16), smem_desc(bo + ks * 256, 128, 2 * KP * 16), idesc_o,
-                      ks > 0);
-          }
-          mma_commit(&bars[4 + g]);
-          if (++sstep[g] == kSteps) {
-            sstep[g] = 0;
-            if (++rnd[g] >= rounds) --remaining;
-          }
+          for (int ks = 0; ks < KP / 16; ++ks)
+            mma_f16(dt + net * H, smem_desc(a + ks * 256, 128, 2 * KP * 16), smem_desc(b + ks * 256, 128, KP * 16),
+                    idesc_h, ks > 0);
         }
+      } else {
+        const uint32_t a = sb + L.act[g];
+#pragma unroll
+        for (int ks = 0; ks < 2 * KP / 16; ++ks)
+          mma_f16(dt, smem_desc(a + ks * 256, 128, 2 * KP * 16), smem_desc(bo + ks * 256, 128, 2 * KP * 16), idesc_o,
+                  ks > 0);
       }
-    }
-  } else {
-    // ===== tile groups: thread = one observation / environment = one TMEM lane =====
+      mma_commit(&bars[4 + g]);
+    };
+    // operand rows of this group are complete and visible to the async proxy -> start MMA chain s
+    auto hand_over = [&](int g, int row, int s) {
+      fence_async_smem();
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      if (row == 0) {
+        fence_after_sync();
+        issue_chain(g, s);
+      }
+    };
     const int g = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + g * PolicyGroups<H>::TMEM_STRIDE;
@@ -362,8 +348,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
         *reinterpret_cast<uint4*>(a0 + canon_off(row, 0, 16)) = make_uint4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<uint4*>(a0 + canon_off(row, 8, 16)) = make_uint4(w[4], w[5], w[6], w[7]);
       }
-      fence_async_smem();
-      mbar_arrive(&bars[g]);
+      hand_over(g, row, 0);
       // ---- hidden layers: TMEM -> activation -> fp16 operand rows (TMEM loads prefetched one chunk ahead) -------
       for (int s = 0; s < NL; ++s) {
         mbar_wait(&bars[4 + g], dphase);
@@ -395,8 +380,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
           if (c0 + 32 < 2 * H) wait_ld();
         }
         fence_before_sync();
-        fence_async_smem();
-        mbar_arrive(&bars[g]);
+        hand_over(g, row, s + 1);
       }
       // ---- output layer: mu, v -> sample, log-likelihood (-> env step) ---------------------------------------------
       mbar_wait(&bars[4 + g], dphase);
@@ -501,7 +485,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
     }
   }
   __syncthreads();
-  if (warp == MMA_WARP) tmem_dealloc(tmem_base, 512);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace ml4ca

@@ -59,10 +59,27 @@ struct Eval {
   float E[3][2];  // d B[:, j] / d a_j
 };
 
+// sin / cos for the azimuths of the programme, |a| <= 2 pi + pi/12 by the box: two-constant Cody-Waite reduction to
+// [-pi/4, pi/4] and the Cephes single-precision kernels (~1 ulp), without the large-argument path of sincosf (whose
+// inlined Payne-Hanek code at six call sites was 10 % of the kernel's instruction footprint).
+__device__ __forceinline__ void sincos_azimuth(float x, float* sp, float* cp) {
+  const float k = rintf(x * 0.63661977236758134f);
+  float r = fmaf(-k, 1.5707962512969971f, x);
+  r = fmaf(-k, 7.5497894158615964e-08f, r);
+  const float z = r * r;
+  const float s = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), z * r, r);
+  const float c = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f), z * z,
+                       fmaf(-0.5f, z, 1.0f));
+  const int q = (int)k;
+  const float sv = (q & 1) ? c : s, cv = (q & 1) ? s : c;
+  *sp = (q & 2) ? -sv : sv;
+  *cp = ((q + 1) & 2) ? -cv : cv;
+}
+
 __device__ __forceinline__ void evaluate(const float (&z)[5], const float (&tau)[3], Eval& e) {
   float s0, c0, s1, c1;
-  sincosf(z[3], &s0, &c0);
-  sincosf(z[4], &s1, &c1);
+  sincos_azimuth(z[3], &s0, &c0);
+  sincos_azimuth(z[4], &s1, &c1);
   const float lx0 = (float)ML4CA_LX_PORT, ly0 = (float)ML4CA_LY_PORT, lx1 = (float)ML4CA_LX_STAR,
               ly1 = (float)ML4CA_LY_STAR, lx2 = (float)ML4CA_LX_BOW;
   e.W[0][0] = c0, e.W[0][1] = c1, e.W[0][2] = 0.f;
@@ -78,8 +95,8 @@ __device__ __forceinline__ void evaluate(const float (&z)[5], const float (&tau)
 // Reduced objective Phi(z) and the l1 constraint violation, for the merit function.
 __device__ __forceinline__ void objective(const float (&z)[5], const Problem& P, float& phi, float& viol) {
   float s0, c0, s1, c1;
-  sincosf(z[3], &s0, &c0);
-  sincosf(z[4], &s1, &c1);
+  sincos_azimuth(z[3], &s0, &c0);
+  sincos_azimuth(z[4], &s1, &c1);
   const float r0 = fmaf(c0, z[0], fmaf(c1, z[1], -P.tau[0]));
   const float r1 = fmaf(s0, z[0], fmaf(s1, z[1], z[2] - P.tau[1]));
   const float r2 = fmaf((float)ML4CA_LX_PORT * s0 - (float)ML4CA_LY_PORT * c0, z[0],
@@ -275,10 +292,10 @@ __device__ void solve_group(const qp::Problem& P, float* __restrict__ Gs /* [8][
     int q = 0;
     bool is_act = false;
     float relaxed = 0.f;
-    const float scale = 1.0f + fmaxf(fabsf(qlo), fabsf(qhi));
+    const float inv_scale = __fdividef(1.0f, 1.0f + fmaxf(fabsf(qlo), fabsf(qhi)));   // ranks violations only
     for (int gi = 0; gi < kMaxGi; ++gi) {
       const float vhi = p - qhi, vlo = qlo - p;
-      float viol = is_act ? -1e30f : fmaxf(vhi, vlo) / scale;
+      float viol = is_act ? -1e30f : fmaxf(vhi, vlo) * inv_scale;
       int arg = b;
 #pragma unroll
       for (int off = 4; off >= 1; off >>= 1) {   // argmax over the 8 constraints of the group
@@ -406,7 +423,7 @@ __device__ void solve_group(const qp::Problem& P, float* __restrict__ Gs /* [8][
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
       const float zn = fminf(fmaxf(fmaf(alpha, d[j], z[j]), P.lo[j]), P.hi[j]);
-      step = fmaxf(step, fabsf(d[j]) / (1.0f + fabsf(zn)));
+      step = fmaxf(step, __fdividef(fabsf(d[j]), 1.0f + fabsf(zn)));   // convergence measure only
       z[j] = zn;
     }
 #pragma unroll
