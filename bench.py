@@ -139,6 +139,32 @@ def cpu_env_steps_per_s(n_total=1 << 16, steps=8, cores=None):
         per * cores, steps, cores)
 
 
+def _cpu_qp_worker(args):
+    lo, hi = args
+    from ml4ca_b200 import synth
+    from oracle import qp_oracle as QO
+    tau, prev = synth.qp_batch(4096, seed=0)
+    t0 = time.perf_counter()
+    for j in range(lo, hi):
+        QO.solve_stock(tau[:, j], prev[:, j])
+    return time.perf_counter() - t0
+
+
+def cpu_qp_allocations_per_s(n_solves=512, cores=None):
+    """The reference NLP on SciPy SLSQP (oracle restatement of QPTA.solve_QP, bit-identical to the reference code in the
+    build container) on the first n_solves demands of the config-1 batch, split over `cores` processes."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    per = max(1, n_solves // cores)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        busy = pool.map(_cpu_qp_worker, [(i * per, (i + 1) * per) for i in range(cores)])
+    wall = max(busy)          # slowest worker's solve loop (process start-up and imports excluded)
+    return {"value": per * cores / wall, "unit": "allocations/s", "cores": cores, "kind": "port",
+            "single_core_ms_per_solve": 1e3 * sum(busy) / (per * cores),
+            "sample": "first %d demands of the 4096-sample config-1 batch, SciPy SLSQP (reference defaults), %d processes" % (per * cores, cores)}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path, timed on the host cores.
     The reference is Python and cannot travel to the GPU box, so this is the oracle port (kind 'port')."""
@@ -397,6 +423,13 @@ def run_b200(args, rank, local_rank, world):
             cpu_val, cpu_cores, cpu_sample = None, 0, "skipped (--skip-cpu)"
         else:
             cpu_val, cpu_cores, cpu_sample = cpu_env_steps_per_s(1 << 16, 8)
+            try:
+                if "qp_allocate" in extra and "error" not in extra["qp_allocate"]:
+                    extra["qp_allocate"]["cpu_baseline"] = cpu_qp_allocations_per_s(512)
+                one = cpu_env_steps_per_s(1 << 13, 8, cores=1)
+                extra["cpu_env_single_core"] = {"value": one[0], "unit": "env-steps/s", "cores": 1, "sample": one[2]}
+            except Exception as e:  # noqa: BLE001
+                extra["cpu_baselines_error"] = repr(e)
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
