@@ -181,6 +181,21 @@ ML4CA_API int ml4ca_stats(int64_t m, const float* x, double* out3, void* stream)
 /* advantage normalisation x <- (x - mean) / (std + 1e-8) (ppo.py:103). */
 ML4CA_API int ml4ca_normalize(int64_t m, float* x, float mean, float std, void* stream);
 
+/* ---- deployment-side adapters (src/rl/ROS/rl_allocator/src/rl_allocator.py, utils.py, errorFrame.py) -----------------
+ * State vector of the ROS node (rl_allocator.py:165-206,215-217,252-273; ROS-twin ErrorFrame errorFrame.py:52-58, which
+ * wraps radians to [-pi, pi)): eta [3, n] NED pose (yaw in rad), nu [3, n], ref [3, n], prev_u [6, n] = previous action in
+ * ROS order [n_port, n_star, n_bow, a_port, a_star, a_bow] -> state [9, n] = [surge, sway, yaw error, u, v, r,
+ * n_bow/100, n_port/100, n_star/100].  integ [3, n] + t_inside [n] (both nullable together) = the optional body-frame
+ * integrator and the seconds spent inside its activation box (the node compares wall-clock time; h = callback period). */
+ML4CA_API int ml4ca_ros_state(int64_t n, const float* eta, const float* nu, const float* ref, const float* prev_u,
+                              float* integ, float* t_inside, float h, float* state, void* stream);
+/* RLTA.get_action after the actor (rl_allocator.py:222-250,275-283) and create_publishable_messages (utils.py:88-115):
+ * network action [act_dim, n] of env class `kind` -> u [6, n] in ROS order with the class defaults filled in, and
+ * msg [7, n] (nullable) = [pod_angle.port deg, pod_angle.star deg, port_effort, star_effort, throttle_bow,
+ * position_bow, lin_act_bow]; simulation = 0 is the shipped setting (bow throttle x 2.5 clipped, position 45). */
+ML4CA_API int ml4ca_ros_action(int32_t kind, int32_t cont_ang, int32_t simulation, int64_t n, const float* action,
+                               float* u, float* msg, void* stream);
+
 /* ---- PPO update (ppo.py:234-250,260-280; mpi_tf.py:45-80) --------------------------------------------------------------
  * Gradient of ONE loss over a whole trajectory buffer: net 0 = pi_loss = -mean(min(ratio adv, clip(ratio) adv)) w.r.t. the
  * pi variables and log_std, net 1 = v_loss = mean((ret - v)^2) w.r.t. the v variables.  obs [T, obs_dim, n],

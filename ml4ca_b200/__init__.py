@@ -14,6 +14,7 @@ from . import _lib  # noqa: F401
 from .env import ErrorFrame, Revolt, RevoltFinal, RevoltLimited, RevoltSimple  # noqa: F401
 from .pinv import pinv_allocate, pinv_pid  # noqa: F401
 from .qp_allocator import QPTA  # noqa: F401
+from .rl_allocator import RLTA  # noqa: F401
 from .core import ActorCritic, mlp_actor_critic  # noqa: F401
 from .ppo import PPOUpdater, TrajectoryBuffer, ppo, rollout  # noqa: F401
 from .env import StandInHull  # noqa: F401

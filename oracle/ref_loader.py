@@ -12,6 +12,7 @@ Stubbed third-party modules (absent here, and irrelevant to the arithmetic on th
 qp_allocator.py:209 and makes ``solve_QP`` deterministic.
 """
 import importlib
+import importlib.util
 import os
 import sys
 import types
@@ -124,6 +125,59 @@ def load_qp_module():
     if _QP_ROOT not in sys.path:
         sys.path.insert(0, _QP_ROOT)
     return importlib.import_module("qp_allocator")
+
+
+def load_rl_allocator_module():
+    """-> the reference deployment node module ``rl_allocator`` (class RLTA) with its siblings ``errorFrame`` and
+    ``utils`` (src/rl/ROS/rl_allocator/src).  TensorFlow, ROS messages and the policy loader are stubbed; construct
+    ``RLTA()`` after setting ``module.load_policy`` to a function returning the actor stub."""
+    if not available():
+        raise RuntimeError("reference checkout not present at %s" % REFERENCE_ROOT)
+    _install_stubs()
+    cmsg = sys.modules["custom_msgs.msg"]
+    if not hasattr(cmsg, "NorthEastHeading"):
+        fields = ["pos_north", "pos_east", "pos_heading", "vel_north", "vel_east", "vel_heading"]
+
+        def _init(self):
+            for f in fields:
+                setattr(self, f, 0.0)
+        cmsg.NorthEastHeading = type("NorthEastHeading", (), {"__init__": _init})
+    gmsg = sys.modules["geometry_msgs.msg"]
+    if not hasattr(gmsg, "Twist"):
+        class Twist(object):
+            def __init__(self, x=0.0, y=0.0, az=0.0):
+                self.linear = types.SimpleNamespace(x=x, y=y, z=0.0)
+                self.angular = types.SimpleNamespace(x=0.0, y=0.0, z=az)
+        gmsg.Twist = Twist
+        gmsg.Pose2D = type("Pose2D", (), {})
+    if "std_msgs" not in sys.modules:
+        std = types.ModuleType("std_msgs")
+        smsg = types.ModuleType("std_msgs.msg")
+        smsg.Float64 = type("Float64", (), {})
+        std.msg = smsg
+        sys.modules["std_msgs"] = std
+        sys.modules["std_msgs.msg"] = smsg
+    if "tensorflow" not in sys.modules:
+        sys.modules["tensorflow"] = types.ModuleType("tensorflow")     # utils.py:7, only used by the (stubbed) loader
+    rospy = sys.modules["rospy"]
+    if not hasattr(rospy, "logerr"):
+        rospy.logerr = lambda *a, **k: None
+        rospy.on_shutdown = lambda *a, **k: None
+    root = os.path.join(REFERENCE_ROOT, "src", "rl", "ROS", "rl_allocator", "src")
+    saved = {k: sys.modules.get(k) for k in ("errorFrame", "utils")}
+    try:
+        for name in ("errorFrame", "utils", "rl_allocator"):
+            spec = importlib.util.spec_from_file_location(name, os.path.join(root, name + ".py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+        return sys.modules["rl_allocator"]
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
 
 
 def wrench(fx, fy, tz):

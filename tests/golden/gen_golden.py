@@ -13,6 +13,8 @@ qp_config1.npz        : reference QPTA.solve_QP + tau_controller_callback_func p
                         SURVEY.md section 8(d) config-1 demand distribution (container SciPy, see
                         oracle/qp_oracle.py header), rospy.get_time() pinned to 0.
 policy_*.npz          : the shipped TF1 checkpoints' actor/critic weights, read by ml4ca_b200/tf_checkpoint.py
+ros_adapter.npz       : the deployment node RLTA (src/rl/ROS/rl_allocator/src/rl_allocator.py) driven message by message
+                        with a stub actor: state vector, ROS-order action, published message fields.
 gae.npz               : reference core.discount_cumsum formulation (scipy.signal.lfilter) and the
                         TrajectoryBuffer.finish_path arithmetic (ppo.py:82-91).
 """
@@ -133,8 +135,55 @@ def gen_policy():
         print('wrote policy_%s.npz' % tag, dims, flat.shape)
 
 
+def gen_ros_adapter(K=96, seed=21):
+    """The deployment node itself (src/rl/ROS/rl_allocator/src/rl_allocator.py, class RLTA) driven message by message:
+    eta / nu / desired-state callbacks with a stub actor returning a prescribed network action.  Records the state the
+    actor saw, the ROS-order action u, the published message fields and the state tail after the step."""
+    import sys as _sys
+    mod = ref_loader.load_rl_allocator_module()
+    mod.load_policy = lambda fpath, num_hidden_layers=None: (lambda s: np.zeros(7))
+    Twist = _sys.modules["geometry_msgs.msg"].Twist
+    NEH = _sys.modules["custom_msgs.msg"].NorthEastHeading
+    rng = np.random.default_rng(seed)
+    out = {}
+    for tag, env, cont, act_dim in (("final_cont", "final", True, 7), ("final_wrap", "final", False, 5),
+                                    ("limited", "limited", False, 5), ("full", "full", False, 6)):
+        node = mod.RLTA()
+        node.env, node.cont_ang = env, cont
+        rec = {k: [] for k in ("eta_deg", "nu", "ref_deg", "action", "state_seen", "u", "msg", "state_after", "prev_u")}
+        for k in range(K):
+            eta = rng.uniform(-1, 1, 3) * np.array([8.0, 8.0, 400.0])          # heading in degrees, beyond +-180 too
+            nu = rng.uniform(-1, 1, 3) * np.array([1.4, 0.3, 0.52])
+            ref = rng.uniform(-1, 1, 3) * np.array([8.0, 8.0, 200.0])
+            a = rng.uniform(-1.4, 1.4, act_dim)
+            seen = {}
+
+            def actor(state, a=a, seen=seen):
+                seen["s"] = np.array(state, dtype=np.float64)
+                return a.copy()
+            node.actor = actor
+            rec["prev_u"].append(np.array(node.prev_thrust_state, dtype=np.float64))
+            node.eta_obs_callback(Twist(eta[0], eta[1], eta[2]))
+            node.nu_obs_callback(Twist(nu[0], nu[1], nu[2]))
+            d = NEH()
+            d.pos_north, d.pos_east, d.pos_heading = ref
+            node.state_desired_callback(d)
+            pa, st, bc = node.pub_stern_angles.last, node.pub_stern_thruster_setpoints.last, node.pub_bow_control.last
+            rec["eta_deg"].append(eta); rec["nu"].append(nu); rec["ref_deg"].append(ref); rec["action"].append(a)
+            rec["state_seen"].append(seen["s"]); rec["u"].append(np.array(node.prev_thrust_state, dtype=np.float64))
+            rec["msg"].append([pa.port, pa.star, st.port_effort, st.star_effort, bc.throttle_bow, bc.position_bow, bc.lin_act_bow])
+            rec["state_after"].append(np.array(node.state, dtype=np.float64))
+        for k, v in rec.items():
+            out["%s__%s" % (tag, k)] = np.array(v, dtype=np.float64)
+    return out
+
+
 def main():
     assert ref_loader.available(), "reference checkout not found"
+    if "--only-ros" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, 'ros_adapter.npz'), **gen_ros_adapter())
+        print('wrote ros_adapter.npz')
+        return
     cases = [
         ('final_cont_ext', 'final', 'RevoltFinal', dict(cont_ang=True, extended_state=True), 32, 40),
         ('final_wrap_ext', 'final', 'RevoltFinal', dict(cont_ang=False, extended_state=True), 8, 20),
@@ -158,6 +207,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'gae.npz'), **gen_gae(7))
     print('wrote gae.npz')
     gen_policy()
+    np.savez_compressed(os.path.join(HERE, 'ros_adapter.npz'), **gen_ros_adapter())
+    print('wrote ros_adapter.npz')
 
 
 if __name__ == '__main__':
