@@ -196,6 +196,13 @@ ML4CA_API int ml4ca_ros_state(int64_t n, const float* eta, const float* nu, cons
 ML4CA_API int ml4ca_ros_action(int32_t kind, int32_t cont_ang, int32_t simulation, int64_t n, const float* action,
                                float* u, float* msg, void* stream);
 
+/* Evaluation metrics of the thesis' comparison (results/all_plots/common.py:60-74, box_test/plot_pos.py:174,
+ * box_test/plot_act.py:128-135,184-207,320-391) for n recorded runs of T samples at period dt: eta [T, 3, n] NED pose
+ * (yaw rad), ref [3, n], thrust [T, 3, n] (bow, port, star in %), angles [T, 2, n] (port, star in rad) ->
+ * out [3, n] = IAE (pose error scaled by [5 m, 5 m, 25 deg], trapezoidal), W* (propeller energy, J), IADC. */
+ML4CA_API int ml4ca_eval_metrics(int64_t n, int32_t T, float dt, const float* eta, const float* ref, const float* thrust,
+                                 const float* angles, float* out, void* stream);
+
 /* ---- PPO update (ppo.py:234-250,260-280; mpi_tf.py:45-80) --------------------------------------------------------------
  * Gradient of ONE loss over a whole trajectory buffer: net 0 = pi_loss = -mean(min(ratio adv, clip(ratio) adv)) w.r.t. the
  * pi variables and log_std, net 1 = v_loss = mean((ret - v)^2) w.r.t. the v variables.  obs [T, obs_dim, n],

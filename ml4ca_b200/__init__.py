@@ -18,5 +18,6 @@ from .rl_allocator import RLTA  # noqa: F401
 from .core import ActorCritic, mlp_actor_critic  # noqa: F401
 from .ppo import PPOUpdater, TrajectoryBuffer, ppo, rollout  # noqa: F401
 from .env import StandInHull  # noqa: F401
+from . import evaluate  # noqa: F401
 
 __version__ = "0.1.0"

@@ -15,6 +15,7 @@ pinv_oracle.py float64 restatement of this build's stated pseudoinverse + PID eq
 mlp_oracle.py  NumPy restatement of spinup/algos/tf1/ppo/core.py (MLP, Gaussian policy, logp)
 ppo_oracle.py  GAE / discounted cumsum / PPO losses restated (ppo.py:65-105,234-249)
 ros_oracle.py  state assembly / action post-processing of the deployment node (rl_allocator.py, utils.py)
+eval_oracle.py IAE / W* / IADC of results/all_plots (common.py, box_test/plot_act.py)
 ref_loader.py  imports the UNMODIFIED reference modules from /root/reference behind stub modules
                (only usable in the build container; used to pin the restatements and to
                generate tests/golden/*.npz)
