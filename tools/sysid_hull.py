@@ -1,0 +1,181 @@
+"""System identification of the DECLARED stand-in hull against the reference's recorded Cybersea box tests
+(SURVEY.md 8f rank 1).  Build-container tool: reads /root/reference/results/all_plots/box_test/bagfile__*.csv.
+
+Model (oracle/vessel.py):  m11 du = tau_x + m22 v r - (Xu + Xuu|u|) u ;  m22 dv = tau_y - m11 u r - (Yv + Yvv|v|) v ;
+                           m33 dr = tau_n - (m22 - m11) u v - (Nr + Nrr|r|) r
+with tau from the reference thruster model (B(alpha), F = K n|n|, qp_allocator.py:51-55,69-70) applied to the RECORDED
+commands (zero-order hold, optional first-order actuator lag).  Equation-error least squares on body accelerations
+obtained from the recorded pose (20 Hz observer output), then a simulation-error check: replay each run open loop in
+windows and report the pose RMS error of the fitted and of the declared parameters.
+"""
+import sys
+import numpy as np
+import pandas as pd
+from scipy.signal import savgol_filter
+
+D = '/root/reference/results/all_plots/box_test/'
+LX = np.array([-1.12, -1.12, 1.08]); LY = np.array([-0.15, 0.15, 0.0]); K = np.array([0.00205, 0.00205, 0.0009])
+DECLARED = dict(m11=264.0, m22=306.0, m33=322.0, Xu=10.0, Xuu=13.8, Yv=100.0, Yvv=222.0, Nr=60.0, Nrr=90.3)
+
+
+def load(method, fs=20.0):
+    eta = pd.read_csv(D + 'bagfile__%s_observer_eta_ned.csv' % method)
+    bow = pd.read_csv(D + 'bagfile__%s_bow_control.csv' % method)
+    st = pd.read_csv(D + 'bagfile__%s_thrusterAllocation_stern_thruster_setpoints.csv' % method)
+    pod = pd.read_csv(D + 'bagfile__%s_thrusterAllocation_pod_angle_input.csv' % method)
+    t0 = eta['%time'][0]
+    te = (eta['%time'].values - t0) / 1e9
+    t = np.arange(0.0, te[-1], 1.0 / fs)
+    N, E = np.interp(t, te, eta['field.linear.x'].values), np.interp(t, te, eta['field.linear.y'].values)
+    psi = np.deg2rad(np.interp(t, te, np.rad2deg(np.unwrap(np.deg2rad(eta['field.angular.z'].values)))))
+    zoh = lambda tc, v: v[np.clip(np.searchsorted(tc, t, side='right') - 1, 0, len(v) - 1)]
+    tb, ts, tp = [(x['%time'].values - t0) / 1e9 for x in (bow, st, pod)]
+    n = np.stack([zoh(ts, st['field.port_effort'].values), zoh(ts, st['field.star_effort'].values), zoh(tb, bow['field.throttle_bow'].values)])
+    a = np.deg2rad(np.stack([zoh(tp, pod['field.port'].values), zoh(tp, pod['field.star'].values), zoh(tb, bow['field.position_bow'].values.astype(float))]))
+    return t, np.stack([N, E, psi]), n, a
+
+
+def wrench(n, a):
+    F = K[:, None] * n * np.abs(n)
+    return np.stack([(F * np.cos(a)).sum(0), (F * np.sin(a)).sum(0), (F * (LX[:, None] * np.sin(a) - LY[:, None] * np.cos(a))).sum(0)])
+
+
+def lag(x, t, T):
+    if T <= 0:
+        return x
+    y = np.empty_like(x); y[..., 0] = x[..., 0]
+    h = t[1] - t[0]; k = h / (T + h)
+    for i in range(1, x.shape[-1]):
+        y[..., i] = y[..., i - 1] + k * (x[..., i] - y[..., i - 1])
+    return y
+
+
+def body_rates(t, eta):
+    h = t[1] - t[0]
+    sm = lambda x, d: savgol_filter(x, 41, 3, deriv=d, delta=h)
+    dN, dE, r = sm(eta[0], 1), sm(eta[1], 1), sm(eta[2], 1)
+    psi = sm(eta[2], 0)
+    u, v = np.cos(psi) * dN + np.sin(psi) * dE, -np.sin(psi) * dN + np.cos(psi) * dE
+    du, dv, dr = sm(u, 1), sm(v, 1), sm(r, 1)
+    return np.stack([u, v, r]), np.stack([du, dv, dr])
+
+
+def simulate(p, eta0, nu0, tau, h):
+    N, E, psi = eta0; u, v, r = nu0
+    out = np.empty((3, tau.shape[1]))
+    for i in range(tau.shape[1]):
+        out[:, i] = (N, E, psi)
+        du = (tau[0, i] + p['m22'] * v * r - (p['Xu'] + p['Xuu'] * abs(u)) * u) / p['m11']
+        dv = (tau[1, i] - p['m11'] * u * r - (p['Yv'] + p['Yvv'] * abs(v)) * v) / p['m22']
+        dr = (tau[2, i] - (p['m22'] - p['m11']) * u * v - (p['Nr'] + p['Nrr'] * abs(r)) * r) / p['m33']
+        u, v, r = u + h * du, v + h * dv, r + h * dr
+        N, E, psi = N + h * (np.cos(psi) * u - np.sin(psi) * v), E + h * (np.sin(psi) * u + np.cos(psi) * v), psi + h * r
+    return out
+
+
+def main():
+    runs = {m: load(m) for m in ('RL', 'QP', 'pseudo', 'RLintegral')}
+    best = None
+    for Tlag in (0.0, 0.2, 0.4, 0.6, 0.8, 1.0, 1.5):
+        rows = {0: [], 1: [], 2: []}; rhs = {0: [], 1: [], 2: []}
+        for m, (t, eta, n, a) in runs.items():
+            nu, dnu = body_rates(t, eta)
+            tau = wrench(lag(n, t, Tlag), lag(a, t, Tlag))
+            u, v, r = nu
+            sl = slice(60, -60)
+            # surge:  m11 du - m22 v r + Xu u + Xuu |u| u = tau_x   (m22 taken from the sway fit: iterate twice)
+            rows[0].append(np.stack([dnu[0], -v * r, u, np.abs(u) * u], 1)[sl]); rhs[0].append(tau[0][sl])
+            rows[1].append(np.stack([dnu[1], u * r, v, np.abs(v) * v], 1)[sl]); rhs[1].append(tau[1][sl])
+            rows[2].append(np.stack([dnu[2], u * v, r, np.abs(r) * r], 1)[sl]); rhs[2].append(tau[2][sl])
+        fit, r2 = {}, {}
+        for k in range(3):
+            A, b = np.concatenate(rows[k]), np.concatenate(rhs[k])
+            x, *_ = np.linalg.lstsq(A, b, rcond=None)
+            fit[k] = x
+            r2[k] = 1 - ((A @ x - b) ** 2).sum() / ((b - b.mean()) ** 2).sum()
+        score = sum(r2.values())
+        print('lag %.1f s  R2 surge %.3f sway %.3f yaw %.3f | surge [m11, m22c, Xu, Xuu] %s | sway [m22, m11c, Yv, Yvv] %s | yaw [m33, dm, Nr, Nrr] %s' % (
+            Tlag, r2[0], r2[1], r2[2], np.round(fit[0], 1), np.round(fit[1], 1), np.round(fit[2], 1)))
+        if best is None or score > best[0]:
+            best = (score, Tlag, fit, r2)
+    _, Tlag, fit, r2 = best
+    p = dict(m11=fit[0][0], m22=fit[1][0], m33=fit[2][0], Xu=fit[0][2], Xuu=fit[0][3], Yv=fit[1][2], Yvv=fit[1][3], Nr=fit[2][2], Nrr=fit[2][3])
+    print('best lag', Tlag, 'fitted', {k: round(v, 1) for k, v in p.items()})
+    # simulation-error check: 10 s open-loop windows re-initialised from the record
+    for name, par in (('declared', DECLARED), ('fitted', p)):
+        errs = []
+        for m, (t, eta, n, a) in runs.items():
+            nu, _ = body_rates(t, eta)
+            tau = wrench(lag(n, t, Tlag), lag(a, t, Tlag))
+            h = t[1] - t[0]; W = int(10 / h)
+            for s in range(100, len(t) - W - 100, W):
+                sim = simulate(par, eta[:, s], nu[:, s], tau[:, s:s + W], h)
+                d = sim - eta[:, s:s + W]
+                errs.append([np.sqrt((d[0] ** 2 + d[1] ** 2).mean()), np.sqrt((d[2] ** 2).mean())])
+        e = np.array(errs)
+        print('%-9s 10 s open-loop windows: position RMS %.3f m (median %.3f), heading RMS %.2f deg (median %.2f)' % (
+            name, e[:, 0].mean(), np.median(e[:, 0]), np.rad2deg(e[:, 1].mean()), np.rad2deg(np.median(e[:, 1]))))
+
+
+if __name__ == '__main__':
+    main()
+
+
+def fit_simulation_error(window_s=10.0):
+    """Output-error fit: minimise the open-loop replay error of `window_s` windows over the nine hull parameters and
+    the actuator lag, with physical bounds (all positive)."""
+    from scipy.optimize import least_squares
+    runs = {m: load(m) for m in ('RL', 'QP', 'pseudo', 'RLintegral')}
+    segs = []
+    for m, (t, eta, n, a) in runs.items():
+        nu, _ = body_rates(t, eta)
+        h = t[1] - t[0]; W = int(window_s / h)
+        for s in range(100, len(t) - W - 100, W):
+            segs.append((eta[:, s:s + W], nu[:, s], n[:, max(0, s - 200):s + W], a[:, max(0, s - 200):s + W], min(s, 200)))
+    h = 0.05
+    names = ['m11', 'm22', 'm33', 'Xu', 'Xuu', 'Yv', 'Yvv', 'Nr', 'Nrr']
+
+    def replay(x):
+        p = dict(zip(names, x[:9])); Tl = x[9]
+        res = []
+        tt = np.arange(segs[0][2].shape[1]) * h
+        # vectorised over windows
+        eta0 = np.stack([s[0][:, 0] for s in segs], 1); nu0 = np.stack([s[1] for s in segs], 1)
+        W = segs[0][0].shape[1]
+        taus = []
+        for (e, v0, n, a, pre) in segs:
+            tl = np.arange(n.shape[1]) * h
+            tau = wrench(lag(n, tl, Tl), lag(a, tl, Tl))[:, pre:pre + W]
+            taus.append(tau)
+        tau = np.stack(taus, 2)          # [3, W, nwin]
+        N, E, psi = eta0.copy(); u, v, r = nu0.copy()
+        out = np.empty((3, W, len(segs)))
+        for i in range(W):
+            out[:, i] = (N, E, psi)
+            du = (tau[0, i] + p['m22'] * v * r - (p['Xu'] + p['Xuu'] * np.abs(u)) * u) / p['m11']
+            dv = (tau[1, i] - p['m11'] * u * r - (p['Yv'] + p['Yvv'] * np.abs(v)) * v) / p['m22']
+            dr = (tau[2, i] - (p['m22'] - p['m11']) * u * v - (p['Nr'] + p['Nrr'] * np.abs(r)) * r) / p['m33']
+            u, v, r = u + h * du, v + h * dv, r + h * dr
+            N, E, psi = N + h * (np.cos(psi) * u - np.sin(psi) * v), E + h * (np.sin(psi) * u + np.cos(psi) * v), psi + h * r
+        ref = np.stack([s[0] for s in segs], 2)
+        d = out - ref
+        return d
+
+    def resid(x):
+        d = replay(x)
+        return np.concatenate([d[0].ravel(), d[1].ravel(), 3.0 * d[2].ravel()])    # 1 rad ~ 3 m weighting
+
+    x0 = np.array([DECLARED[k] for k in names] + [0.4])
+    lo = np.array([100, 100, 50, 0, 0, 0, 0, 0, 0, 0.0]); hi = np.array([600, 900, 900, 200, 200, 600, 900, 400, 600, 2.0])
+    for tag, x in (('declared', x0),):
+        d = replay(x)
+        print('%-9s pos RMS %.3f m  heading RMS %.2f deg' % (tag, np.sqrt((d[0] ** 2 + d[1] ** 2).mean()), np.rad2deg(np.sqrt((d[2] ** 2).mean()))))
+    sol = least_squares(resid, x0, bounds=(lo, hi), x_scale=np.maximum(np.abs(x0), 1.0), max_nfev=60)
+    d = replay(sol.x)
+    print('fitted    pos RMS %.3f m  heading RMS %.2f deg' % (np.sqrt((d[0] ** 2 + d[1] ** 2).mean()), np.rad2deg(np.sqrt((d[2] ** 2).mean()))))
+    print({k: round(float(v), 2) for k, v in zip(names + ['lag'], sol.x)})
+    return sol.x
+
+
+if __name__ == '__main__' and '--output-error' in sys.argv:
+    fit_simulation_error()
