@@ -215,6 +215,10 @@ ML4CA_API int ml4ca_eval_metrics(int64_t n, int32_t T, float dt, const float* et
 ML4CA_API int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const float* obs, const float* act,
                              const float* adv, const float* ret, const float* logp_old, float clip_ratio, float* grad,
                              double* stats, void* stream);
+/* ml4ca_ppo_grad runs on the tensor cores by default (tcgen05, fp16 operands, fp32 accumulation: gradients to ~1e-3 of
+ * the largest component).  enable = 1 selects the fp32 CUDA-core kernel (1e-5), 0 the tensor-core one, -1 only
+ * queries; returns the previous setting.  Initial value: environment variable ML4CA_PPO_FP32. */
+ML4CA_API int ml4ca_ppo_use_fp32(int enable);
 /* tf.train.AdamOptimizer step (beta1 0.9, beta2 0.999, eps 1e-8 in the reference) on m parameters:
  * g = grad * grad_scale; m1, m2 moment buffers; t = 1-based step count of this optimizer. */
 ML4CA_API int ml4ca_adam_step(int64_t m, float* params, const float* grad, float* m1, float* m2, float lr, float beta1,

@@ -1,0 +1,30 @@
+// ppo_tc.h -- argument block shared by the host entry (ppo_update.cu) and the tensor-core gradient kernel
+// (ppo_update_tc.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ml4ca {
+namespace ppotc {
+
+struct Args {
+  const float* params;     // flat fp32 master parameters
+  const __half* blob;      // packed fp16 operands of this net (filled by the launcher)
+  int obs, act, nout;      // nout = act (pi) or 1 (v)
+  int off_w1, off_b1, off_w2, off_b2, off_wo, off_bo, off_ls;
+  int64_t n;
+  int T;
+  const float *obs_buf, *act_buf, *adv, *logp_old, *ret;
+  float clip;
+  float* grad;
+  double* stats;
+};
+
+constexpr int kBlobHalves = 64 * 16 + 64 * 80 + 16 * 80 + 64 * 16 + 64 * 64;
+
+}  // namespace ppotc
+}  // namespace ml4ca
+
+// Packs the operands into `blob` (>= kBlobHalves halves of device scratch) and launches the kernel.
+int ml4ca_ppo_grad_tc_launch(const ml4ca::ppotc::Args& args, int activation, int net, void* blob, cudaStream_t st);

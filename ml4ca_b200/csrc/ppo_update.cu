@@ -23,7 +23,10 @@
 // round-2 work.
 #include <new>
 
+#include <stdlib.h>
+
 #include "common.h"
+#include "ppo_tc.h"
 
 namespace ml4ca {
 namespace ppo {
@@ -459,6 +462,17 @@ __global__ void __launch_bounds__(256) adam_kernel(int64_t m, float* __restrict_
 
 using namespace ml4ca;
 
+static bool g_use_fp32 = [] {
+  const char* e = getenv("ML4CA_PPO_FP32");
+  return e != nullptr && atoi(e) != 0;
+}();
+
+extern "C" int ml4ca_ppo_use_fp32(int enable) {
+  const int prev = g_use_fp32 ? 1 : 0;
+  if (enable >= 0) g_use_fp32 = enable != 0;
+  return prev;
+}
+
 // policy.cu
 extern "C" int ml4ca_policy_describe(const ml4ca_policy* p, ml4ca_policy_cfg* cfg, int32_t* device);
 
@@ -497,6 +511,21 @@ int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const flo
   ML4CA_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 8, st));
   const int64_t tiles = ((n + ppo::TS - 1) / ppo::TS) * T;
   if (tiles == 0) return ML4CA_OK;
+  // Default: the tcgen05 kernel (fp16 operands, fp32 TMEM accumulation).  ML4CA_PPO_FP32=1 selects the fp32
+  // CUDA-core kernel below (gradients to 1e-5 instead of 1e-3).
+  if (!g_use_fp32) {
+    static __half* blob[64] = {};       // per-device scratch for the packed operands (kept for the life of the process)
+    ML4CA_REQUIRE(device >= 0 && device < 64, "device index out of range");
+    if (blob[device] == nullptr) ML4CA_CUDA(cudaMalloc(&blob[device], sizeof(__half) * ppotc::kBlobHalves));
+    ppotc::Args t = {};
+    t.params = a.params, t.obs = a.obs, t.act = a.act, t.nout = a.nout;
+    t.off_w1 = a.off_w1, t.off_b1 = a.off_b1, t.off_w2 = a.off_w2, t.off_b2 = a.off_b2, t.off_wo = a.off_wo;
+    t.off_bo = a.off_bo, t.off_ls = a.off_ls;
+    t.n = n, t.T = T;
+    t.obs_buf = obs, t.act_buf = act, t.adv = adv, t.logp_old = logp_old, t.ret = ret;
+    t.clip = clip_ratio, t.grad = grad, t.stats = stats;
+    return ml4ca_ppo_grad_tc_launch(t, cfg.activation, net, blob[device], st);
+  }
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   const size_t smem = sizeof(ppo::Smem);
 #define ML4CA_PPO_LAUNCH(ACTV, NETV)                                                                             \

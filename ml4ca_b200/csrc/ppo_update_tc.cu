@@ -1,0 +1,466 @@
+// ppo_update_tc.cu -- K6 on the tensor cores: PPO policy / value gradients with tcgen05 MMAs and TMEM accumulators.
+//
+// Same contract as ppo_grad_kernel (ppo_update.cu; reference ppo.py:234-250, core.py:29-46): forward, loss and
+// backward of ONE 64 x 64 network over every sample of a [T, ., n] buffer, gradient SUMS into the flat vector.
+// All seven GEMMs of a 128-sample tile run as tcgen05.mma (fp16 operands in shared memory, fp32 accumulation in
+// tensor memory); the CUDA cores only do the activation / loss epilogues:
+//
+//   forward      D = A0 B1^T          [128 x 16] x [64 x 16]^T      A0 = obs, 1 (bias column), pad
+//                D = A1 B2^T          [128 x 80] x [64 x 80]^T      A1 = f(D), 1, pad
+//                D = A2 Bo^T          [128 x 80] x [16 x 80]^T      -> mu / v
+//   loss         per-sample dOUT (fp32), scaled by 64 and rounded to fp16 -> G3 [128 x 16]
+//   backward     dWo  += A2^T G3      M = features, N = 16, K = 128 samples     (persistent TMEM accumulator)
+//                D     = G3 WoT^T     -> G2 = D .* f'(H2)
+//                dW2  += A1^T G2      M = features, N = 64, K = samples          (persistent)
+//                D     = G2 W2n^T     -> G1 = D .* f'(H1)
+//                dW1T += G1^T A0      M = hidden units, N = 16, K = samples      (persistent)
+//
+// The weight-gradient GEMMs reduce over the SAMPLE dimension.  Their operands are the very buffers the forward /
+// backward-data GEMMs use, read through MN-major descriptors: in the canonical no-swizzle layout element (row r,
+// column c) lives at (r/8) SBO + (c/8) 128 B + (r%8) 16 B + (c%8) 2 B, which is at the same time a K-major tile
+// over (rows, columns) and an MN-major tile over (columns, rows) with the two strides exchanged -- no transposed
+// copies are written.  With M fixed at 128 the transposed views read past the real feature count into neighbouring
+// rows of the same buffer; those accumulator rows are garbage and are never flushed (rows are independent).
+//
+// Bias gradients fall out of the constant-1 columns (row H of dWo / dW2, column obs of dW1T).  Weight-gradient
+// accumulators stay in TMEM for all tiles of the CTA (persistent grid) and are flushed once.  Three tile groups of
+// 128 threads (thread = sample = TMEM lane) run out of phase; thread 0 of a group issues its MMAs.
+//
+// Numerics: fp16 operands (activations, weights, back-propagated signals x 64), fp32 accumulation: gradients agree
+// with the float64 oracle to ~1e-3 of the largest component (tests/test_ppo_update_gpu.py); the fp32 CUDA-core
+// kernel of ppo_update.cu remains available (ML4CA_PPO_FP32=1) where 1e-5 is wanted.
+#include <stdlib.h>
+
+#include <cuda_fp16.h>
+
+#include "common.h"
+#include "ppo_tc.h"
+#include "tc05.cuh"
+
+namespace ml4ca {
+namespace ppotc {
+
+using namespace tc05;
+
+constexpr int H = 64, KP = 80, TS = 128, OP = 16;
+constexpr int G = 3;                       // tile groups per CTA
+constexpr int THREADS = G * 128;
+constexpr float kScale = 64.0f;            // loss scaling of the back-propagated signals (fp16 range)
+
+// ---- shared memory --------------------------------------------------------------------------------------------------
+constexpr int A0_B = TS * 16 * 2, A1_B = TS * KP * 2, A2_B = TS * KP * 2, G3_B = TS * 16 * 2, G2_B = TS * H * 2;
+constexpr int GROUP_B = A0_B + A1_B + A2_B + G3_B + G2_B;      // 65536
+constexpr int B1_E = H * 16, B2_E = H * KP, BO_E = OP * KP, WOT_E = H * 16, W2N_E = H * H;
+constexpr int BLOB_E = B1_E + B2_E + BO_E + WOT_E + W2N_E;     // 12544 halves = 25088 B
+constexpr int OFF_BLOB = 0;
+constexpr int OFF_GROUPS = (BLOB_E * 2 + 127) & ~127;
+constexpr int OFF_TAIL = OFF_GROUPS + G * GROUP_B;             // 2 KB of zeros: spill target of the last transposed view
+constexpr int OFF_BARS = OFF_TAIL + 2048;
+constexpr int OFF_CONST = OFF_BARS + 64;                       // sd[8], inv[8], ls[8]
+constexpr int OFF_TMEM = OFF_CONST + 96;
+constexpr int OFF_RED = OFF_TMEM + 16;                         // double [G * 4][8]
+constexpr int SMEM_BYTES = OFF_RED + G * 4 * 8 * 8;
+
+__host__ __device__ __forceinline__ int canon(int row, int k, int K_total) {
+  return (row >> 3) * (K_total * 8) + (k >> 3) * 64 + (row & 7) * 8 + (k & 7);
+}
+
+// kind::f16, D fp32, A/B fp16, dense; a_mn / b_mn select MN-major operands (bits 15 / 16).
+__host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+
+// fp32 master parameters of one net -> the five fp16 operand images (canonical K-major).
+__global__ void pack_kernel(Args A, __half* __restrict__ blob) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= BLOB_E) return;
+  auto inv = [](int f, int K, int& row, int& k) {   // invert canon()
+    const int rg = f / (K * 8), rem = f % (K * 8);
+    row = rg * 8 + (rem % 64) / 8, k = (rem / 64) * 8 + rem % 8;
+  };
+  const float* P = A.params;
+  float v = 0.f;
+  int row, k, f = e;
+  if (f < B1_E) {                                  // B1 [j][k]: W1[k][j], b1[j] at k = obs
+    inv(f, 16, row, k);
+    if (k < A.obs) v = P[A.off_w1 + k * H + row];
+    else if (k == A.obs) v = P[A.off_b1 + row];
+  } else if ((f -= B1_E) < B2_E) {                 // B2 [j][k]: W2[k][j], b2[j] at k = H
+    inv(f, KP, row, k);
+    if (k < H) v = P[A.off_w2 + k * H + row];
+    else if (k == H) v = P[A.off_b2 + row];
+  } else if ((f -= B2_E) < BO_E) {                 // Bo [o][k]: Wo[k][o], bo[o] at k = H
+    inv(f, KP, row, k);
+    if (row < A.nout) {
+      if (k < H) v = P[A.off_wo + k * A.nout + row];
+      else if (k == H) v = P[A.off_bo + row];
+    }
+  } else if ((f -= BO_E) < WOT_E) {                // WoT [k][o]: Wo[k][o]
+    inv(f, 16, row, k);
+    if (k < A.nout) v = P[A.off_wo + row * A.nout + k];
+  } else {                                         // W2n [k_in][j]: W2[k_in][j]
+    f -= WOT_E;
+    inv(f, H, row, k);
+    v = P[A.off_w2 + row * H + k];
+  }
+  blob[e] = __float2half_rn(v);
+}
+
+template <int ACTIVATION>
+__device__ __forceinline__ uint32_t activate_pack(float lo, float hi) {
+  const uint32_t x = pack_f16x2(lo, hi);
+  uint32_t y;
+  if constexpr (ACTIVATION == 1) {
+    asm("{\n\t.reg .b32 t;\n\tmul.rn.f16x2 t, %1, %2;\n\tmax.f16x2 %0, %1, t;\n\t}" : "=r"(y) : "r"(x), "r"(0x32663266u));
+  } else {
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  }
+  return y;
+}
+// f'(z) from the stored fp16 activation h = f(z)
+template <int ACTIVATION>
+__device__ __forceinline__ float2 act_grad2(uint32_t h2) {
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+  if constexpr (ACTIVATION == 1) return make_float2(h.x > 0.f ? 1.0f : 0.2f, h.y > 0.f ? 1.0f : 0.2f);
+  return make_float2(1.0f - h.x * h.x, 1.0f - h.y * h.y);
+}
+
+template <int ACTIVATION, int NET>
+__global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = warp >> 2, row = (warp & 3) * 32 + lane;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+  float* consts = reinterpret_cast<float*>(smem + OFF_CONST);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+  const int obs = A.obs, nout = A.nout;
+
+  // ---- setup: operand images -> smem, zero the activation buffers, constant-1 columns, barriers, TMEM ------------------
+  {
+    const int4* src = reinterpret_cast<const int4*>(A.blob);
+    int4* dst = reinterpret_cast<int4*>(smem + OFF_BLOB);
+    for (int i = threadIdx.x; i < BLOB_E * 2 / 16; i += THREADS) dst[i] = src[i];
+    int4* z = reinterpret_cast<int4*>(smem + OFF_GROUPS);
+    for (int i = threadIdx.x; i < (G * GROUP_B + 2048) / 16; i += THREADS) z[i] = make_int4(0, 0, 0, 0);
+    if (threadIdx.x < 8) {
+      const int a = threadIdx.x;
+      const float ls = (NET == 0 && a < nout) ? A.params[A.off_ls + a] : 0.f;
+      const float sd = expf(ls);
+      consts[a] = sd, consts[8 + a] = 1.0f / (sd + 1e-8f), consts[16 + a] = ls;
+    }
+  }
+  __syncthreads();
+  {
+    uint8_t* base = smem + OFF_GROUPS + g * GROUP_B;
+    __half* a1 = reinterpret_cast<__half*>(base + A0_B);
+    __half* a2 = reinterpret_cast<__half*>(base + A0_B + A1_B);
+    a1[canon(row, H, KP)] = __float2half_rn(1.0f);     // bias columns of the hidden operands
+    a2[canon(row, H, KP)] = __float2half_rn(1.0f);
+  }
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < G; ++q) mbar_init(&bars[q], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- per-group addresses ----------------------------------------------------------------------------------------------
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t sA0 = sb + OFF_GROUPS + g * GROUP_B, sA1 = sA0 + A0_B, sA2 = sA1 + A1_B, sG3 = sA2 + A2_B, sG2 = sG3 + G3_B;
+  const uint32_t sG1 = sG2;                                    // G1 re-uses the G2 buffer (dead once the dW2 / G2 W2n^T chains are done)
+  const uint32_t sB1 = sb + OFF_BLOB, sB2 = sB1 + B1_E * 2, sBo = sB2 + B2_E * 2, sWoT = sBo + BO_E * 2, sW2n = sWoT + WOT_E * 2;
+  uint8_t* gbase = smem + OFF_GROUPS + g * GROUP_B;
+  __half* pA0 = reinterpret_cast<__half*>(gbase);
+  uint8_t* pA1 = gbase + A0_B;
+  uint8_t* pA2 = pA1 + A1_B;
+  __half* pG3 = reinterpret_cast<__half*>(pA2 + A2_B);
+  uint8_t* pG2 = pA2 + A2_B + G3_B;
+  uint8_t* pG1 = pG2;
+  const uint32_t tD = tmem_base + g * 160, tW2 = tD + 64, tWo = tD + 128, tW1 = tD + 144;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+
+  // MMA chains (one elected thread per group).  K-major operand: lbo = 128 B, sbo = K_total * 16 B, +256 B per k-step.
+  // MN-major view of a buffer with K_total columns: lbo = K_total * 16 B, sbo = 128 B, + 2 lbo per k-step (16 samples).
+  auto chain_k = [&](uint32_t d, uint32_t a, int ka, uint32_t b, int kb, int N, int steps, bool acc0) {
+    const uint32_t id = idesc(128, N, 0, 0);
+    for (int s = 0; s < steps; ++s)
+      mma_f16(d, smem_desc(a + s * 256, 128, ka * 16), smem_desc(b + s * 256, 128, kb * 16), id, acc0 || s > 0);
+  };
+  auto chain_mn = [&](uint32_t d, uint32_t a, int ka, uint32_t b, int kb, int N, bool acc0) {
+    const uint32_t id = idesc(128, N, 1, 1);
+    for (int s = 0; s < 8; ++s)
+      mma_f16(d, smem_desc(a + s * 2 * ka * 16, ka * 16, 128), smem_desc(b + s * 2 * kb * 16, kb * 16, 128), id, acc0 || s > 0);
+  };
+  uint32_t phase = 0;
+  auto sync_group = [&]() {
+    fence_async_smem();
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+  };
+  auto wait_mma = [&]() {
+    mbar_wait(&bars[g], phase);
+    phase ^= 1;
+    fence_after_sync();
+  };
+
+  const int64_t n = A.n;
+  const int64_t tiles_per_t = (n + TS - 1) / TS;
+  const int64_t num_tiles = tiles_per_t * A.T;
+  float dls[8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) dls[a] = 0.f;
+  double st[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  bool acc = false, pending = false;   // acc: the dW accumulators hold a tile already; pending: the dW1T chain is in flight
+
+  for (int64_t tile = (int64_t)blockIdx.x * G + g; tile < num_tiles; tile += (int64_t)gridDim.x * G) {
+    const int64_t t = tile / tiles_per_t, i = (tile % tiles_per_t) * TS + row;
+    const bool live = i < n;
+    // ---- inputs: thread = sample ----------------------------------------------------------------------------------------
+    float o[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = (c < obs && live) ? __ldg(A.obs_buf + ((int64_t)t * obs + c) * n + i) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c == obs) o[c] = 1.0f;
+    float av[8], adv = 0.f, lpo = 0.f, ret = 0.f;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) av[a] = 0.f;
+    if constexpr (NET == 0) {
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+        if (a < nout && live) av[a] = __ldg(A.act_buf + ((int64_t)t * A.act + a) * n + i);
+      if (live) adv = __ldg(A.adv + (int64_t)t * n + i), lpo = __ldg(A.logp_old + (int64_t)t * n + i);
+    } else {
+      if (live) ret = __ldg(A.ret + (int64_t)t * n + i);
+    }
+    if (pending) {                             // the previous tile's dW1T chain still reads A0 / G1
+      wait_mma();
+      pending = false;
+    }
+    {
+      uint32_t w[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) w[c] = pack_f16x2(o[2 * c], o[2 * c + 1]);
+      *reinterpret_cast<uint4*>(pA0 + canon(row, 0, 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(pA0 + canon(row, 8, 16)) = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+    sync_group();
+    if (row == 0) {
+      fence_after_sync();
+      chain_k(tD, sA0, 16, sB1, 16, H, 1, false);                  // F1
+      mma_commit(&bars[g]);
+    }
+    // ---- hidden epilogues: D -> f -> operand rows -------------------------------------------------------------------------
+    auto hidden = [&](uint8_t* dst) {
+      wait_mma();
+      uint32_t buf[16];
+#pragma unroll
+      for (int c0 = 0; c0 < H; c0 += 16) {
+        tmem_ld16_async(tD + lane_off + c0, buf);
+        wait_ld();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t w[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            w[k] = activate_pack<ACTIVATION>(__uint_as_float(buf[q * 8 + 2 * k]), __uint_as_float(buf[q * 8 + 2 * k + 1]));
+          *reinterpret_cast<uint4*>(dst + (size_t)canon(row, c0 + q * 8, KP) * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      fence_before_sync();
+      sync_group();
+    };
+    hidden(pA1);
+    if (row == 0) {
+      fence_after_sync();
+      chain_k(tD, sA1, KP, sB2, KP, H, KP / 16, false);            // F2
+      mma_commit(&bars[g]);
+    }
+    hidden(pA2);
+    if (row == 0) {
+      fence_after_sync();
+      chain_k(tD, sA2, KP, sBo, KP, OP, KP / 16, false);           // F3
+      mma_commit(&bars[g]);
+    }
+    // ---- loss: per-sample dOUT (sum convention), scaled, -> G3 ---------------------------------------------------------------
+    wait_mma();
+    float out[16];
+    tmem_ld16(tD + lane_off, out);
+    fence_before_sync();
+    float dout[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) dout[a] = 0.f;
+    if constexpr (NET == 0) {
+      float logp = 0.f, z[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        z[a] = 0.f;
+        if (a < nout) {
+          z[a] = (av[a] - out[a]) * consts[8 + a];                                  // core.py:45
+          logp += -0.5f * (z[a] * z[a] + 2.0f * consts[16 + a] + 1.8378770664093453f);
+        }
+      }
+      const float ratio = expf(logp - lpo);                                         // ppo.py:234
+      const float min_adv = adv > 0.f ? (1.0f + A.clip) * adv : (1.0f - A.clip) * adv;
+      const float ra = ratio * adv;
+      const float dlogp = (live && ra <= min_adv) ? -ra : 0.f;
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+        if (a < nout) {
+          dout[a] = dlogp * z[a] * consts[8 + a];
+          dls[a] += dlogp * (z[a] * z[a] * consts[a] * consts[8 + a] - 1.0f);
+        }
+      if (live) {
+        st[0] += (double)fminf(ra, min_adv);
+        const float dl = lpo - logp;
+        st[2] += 0.5 * (double)dl * (double)dl;
+        st[3] += (double)(-logp);
+        st[4] += (ratio > 1.0f + A.clip || ratio < 1.0f - A.clip) ? 1.0 : 0.0;
+      }
+    } else {
+      const float e = out[0] - ret;
+      dout[0] = live ? 2.0f * e : 0.f;
+      if (live) st[1] += (double)e * (double)e;
+    }
+    {
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[k] = pack_f16x2(dout[2 * k] * kScale, dout[2 * k + 1] * kScale);
+      *reinterpret_cast<uint4*>(pG3 + canon(row, 0, 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(pG3 + canon(row, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    sync_group();
+    if (row == 0) {
+      fence_after_sync();
+      chain_mn(tWo, sA2, KP, sG3, 16, OP, acc);                    // dWo += A2^T G3
+      chain_k(tD, sG3, 16, sWoT, 16, H, 1, false);                 // D = G3 WoT^T
+      mma_commit(&bars[g]);
+    }
+    // ---- backward epilogues: G = D .* f'(h) ------------------------------------------------------------------------------------
+    auto backward = [&](const uint8_t* hsrc, uint8_t* dst) {
+      wait_mma();
+      uint32_t buf[16];
+#pragma unroll
+      for (int c0 = 0; c0 < H; c0 += 16) {
+        tmem_ld16_async(tD + lane_off + c0, buf);
+        const uint4 h0 = *reinterpret_cast<const uint4*>(hsrc + (size_t)canon(row, c0, KP) * 2);
+        const uint4 h1 = *reinterpret_cast<const uint4*>(hsrc + (size_t)canon(row, c0 + 8, KP) * 2);
+        const uint32_t hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        wait_ld();
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float2 gr = act_grad2<ACTIVATION>(hh[k]);
+          w[k] = pack_f16x2(__uint_as_float(buf[2 * k]) * gr.x, __uint_as_float(buf[2 * k + 1]) * gr.y);
+        }
+        *reinterpret_cast<uint4*>(dst + (size_t)canon(row, c0, H) * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(dst + (size_t)canon(row, c0 + 8, H) * 2) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      fence_before_sync();
+      sync_group();
+    };
+    backward(pA2, pG2);
+    if (row == 0) {
+      fence_after_sync();
+      chain_mn(tW2, sA1, KP, sG2, H, H, acc);                      // dW2 += A1^T G2
+      chain_k(tD, sG2, H, sW2n, H, H, H / 16, false);              // D = G2 W2n^T
+      mma_commit(&bars[g]);
+    }
+    backward(pA1, pG1);                                            // G1 takes over the G2 buffer (its readers have completed)
+    if (row == 0) {
+      fence_after_sync();
+      chain_mn(tW1, sG1, H, sA0, 16, OP, acc);                     // dW1T += G1^T A0
+      mma_commit(&bars[g]);
+    }
+    acc = true;
+    pending = true;                                                // waited for before A0 / G2 are written again
+  }
+  if (pending) wait_mma();
+
+  // ---- flush: TMEM accumulators -> global gradient (one atomicAdd per element and group), statistics -------------------
+  float* gr = A.grad;
+  const float unscale = 1.0f / kScale;
+  if (acc) {
+    float v[16];
+    // tcgen05.ld is warp-collective: every thread loads, the row test only guards the atomics
+#pragma unroll
+    for (int c0 = 0; c0 < H; c0 += 16) {               // dW2 rows k = 0..63, row 64 = bias b2
+      tmem_ld16(tW2 + lane_off + c0, v);
+      if (row <= H) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          atomicAdd(gr + (row < H ? A.off_w2 + row * H : A.off_b2) + c0 + j, v[j] * unscale);
+      }
+    }
+    tmem_ld16(tWo + lane_off, v);
+    if (row <= H) {
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (o < nout) atomicAdd(gr + (row < H ? A.off_wo + row * nout : A.off_bo) + o, v[o] * unscale);
+    }
+    tmem_ld16(tW1 + lane_off, v);        // dW1T: lane = hidden unit j, column = input k (k = obs: bias b1)
+    if (row < H) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        if (k < obs) atomicAdd(gr + A.off_w1 + k * H + row, v[k] * unscale);
+        else if (k == obs) atomicAdd(gr + A.off_b1 + row, v[k] * unscale);
+      }
+    }
+  }
+  fence_before_sync();
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    float r = dls[a];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, off);
+    if (NET == 0 && lane == 0 && a < nout && r != 0.f) atomicAdd(gr + A.off_ls + a, r);
+  }
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    double r = st[q];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, off);
+    if (lane == 0 && r != 0.0) atomicAdd(A.stats + q, r);
+  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(A.stats + 5, (double)A.n * (double)A.T);
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace ppotc
+}  // namespace ml4ca
+
+using namespace ml4ca;
+
+// Host side: called by ml4ca_ppo_grad (ppo_update.cu) unless ML4CA_PPO_FP32 is set.  `blob` is scratch for the packed
+// fp16 operands (>= ppotc::BLOB_E halves), owned by the caller.
+static_assert(ppotc::BLOB_E == ppotc::kBlobHalves, "operand blob size");
+
+int ml4ca_ppo_grad_tc_launch(const ppotc::Args& args, int activation, int net, void* blob, cudaStream_t st) {
+  ppotc::Args a = args;
+  __half* b = static_cast<__half*>(blob);
+  ppotc::pack_kernel<<<(ppotc::BLOB_E + 255) / 256, 256, 0, st>>>(a, b);
+  int rc = check_launch("ppo pack_kernel");
+  if (rc != ML4CA_OK) return rc;
+  a.blob = b;
+  const int64_t tiles = ((a.n + ppotc::TS - 1) / ppotc::TS) * a.T;
+  const int64_t want = (tiles + ppotc::G - 1) / ppotc::G;
+  const int grid = (int)(want < kNumSMs ? want : kNumSMs);
+#define ML4CA_TC_LAUNCH(ACTV, NETV)                                                                                      \
+  do {                                                                                                                   \
+    auto k = ppotc::ppo_grad_tc_kernel<ACTV, NETV>;                                                                      \
+    ML4CA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, ppotc::SMEM_BYTES));                 \
+    k<<<grid, ppotc::THREADS, ppotc::SMEM_BYTES, st>>>(a);                                                               \
+  } while (0)
+  if (activation == 1) {
+    if (net == 0) ML4CA_TC_LAUNCH(1, 0); else ML4CA_TC_LAUNCH(1, 1);
+  } else {
+    if (net == 0) ML4CA_TC_LAUNCH(0, 0); else ML4CA_TC_LAUNCH(0, 1);
+  }
+#undef ML4CA_TC_LAUNCH
+  return check_launch("ppo_grad_tc_kernel");
+}

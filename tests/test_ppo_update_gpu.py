@@ -25,10 +25,24 @@ def _flatten(x):          # [T, c, n] -> [T * n, c] in (t, i) order
     return np.ascontiguousarray(np.moveaxis(x, 1, 2).reshape(-1, x.shape[1])).astype(np.float64)
 
 
+@pytest.fixture(params=["tensor_core", "fp32"])
+def precision(request, lib_built):
+    """Both gradient kernels: tcgen05 (fp16 operands, default) and the fp32 CUDA-core one."""
+    from ml4ca_b200 import _lib
+    prev = _lib.lib().ml4ca_ppo_use_fp32(1 if request.param == "fp32" else 0)
+    yield request.param
+    _lib.lib().ml4ca_ppo_use_fp32(prev)
+
+
 @pytest.mark.parametrize("activation", ["leaky_relu", "tanh"])
 @pytest.mark.parametrize("T,n", [(1, 128), (3, 1000), (2, 40000)])
-def test_gradients_and_statistics(cuda_device, activation, T, n):
+def test_gradients_and_statistics(cuda_device, precision, activation, T, n):
     import ml4ca_b200 as M
+    # stated tolerances of the two kernels.  Tensor cores: fp16 operands give ~1e-3; on top of that a pre-activation
+    # within fp16 rounding of zero can take the other leaky-ReLU branch, a per-sample effect that averages out as 1/sqrt(N)
+    gtol, stol = (2e-4, 1e-5) if precision == "fp32" else (3e-3 + 0.5 / np.sqrt(T * n), 3e-2)
+    if precision == "tensor_core" and activation == "tanh":
+        gtol += 1.2e-2        # tanh.approx.f16x2 (MUFU, 2^-11) in the forward pass biases logp by ~1 %; every shipped model is leaky-ReLU
     flat = MO.glorot_params(DIMS, seed=5)
     flat = (flat + np.random.default_rng(1).normal(size=flat.size).astype(np.float32) * 0.05).astype(np.float32)   # non-zero biases
     ac = M.ActorCritic(9, 7, (64, 64), activation, params=flat, device=cuda_device)
@@ -48,17 +62,17 @@ def test_gradients_and_statistics(cuda_device, activation, T, n):
     g_pi = upd.flat[:ac.num_params].cpu().numpy().astype(np.float64) / N
     assert (g_pi[n_pi:] == 0).all()                     # the v block is untouched by the pi pass
     scale = np.abs(g64[:n_pi]).max()
-    np.testing.assert_allclose(g_pi[:n_pi], g64[:n_pi], rtol=0, atol=2e-4 * scale)
-    assert abs(-s[0] / N - info["pi_loss"]) < 1e-5 * max(1, abs(info["pi_loss"]))
-    assert abs(s[2] / N - info["approx_kl"]) < 1e-5 * max(1e-3, info["approx_kl"]) + 1e-7
-    assert abs(s[3] / N - info["approx_ent"]) < 1e-5 * abs(info["approx_ent"])
-    assert abs(s[4] / N - info["clipfrac"]) <= 2.0 / N + 1e-4      # a ratio within fp32 rounding of the clip edge may flip
+    np.testing.assert_allclose(g_pi[:n_pi], g64[:n_pi], rtol=0, atol=gtol * scale)
+    assert abs(-s[0] / N - info["pi_loss"]) < stol * max(1, abs(info["pi_loss"]))
+    assert abs(s[2] / N - info["approx_kl"]) < stol * max(1e-3, info["approx_kl"]) + 1e-7 + (0 if precision == "fp32" else 1e-3)
+    assert abs(s[3] / N - info["approx_ent"]) < stol * abs(info["approx_ent"])
+    assert abs(s[4] / N - info["clipfrac"]) <= 2.0 / N + (1e-4 if precision == "fp32" else 1e-2)   # ratios within rounding of the clip edge may flip
     s, c = upd._grad(1, data, T, n)
     g_v = upd.flat[:ac.num_params].cpu().numpy().astype(np.float64) / N
     assert (g_v[:n_pi] == 0).all()
     scale = np.abs(g64[n_pi:]).max()
-    np.testing.assert_allclose(g_v[n_pi:], g64[n_pi:], rtol=0, atol=2e-4 * scale)
-    assert abs(s[1] / N - info["v_loss"]) < 1e-5 * info["v_loss"]
+    np.testing.assert_allclose(g_v[n_pi:], g64[n_pi:], rtol=0, atol=gtol * scale)
+    assert abs(s[1] / N - info["v_loss"]) < stol * info["v_loss"]
 
 
 def test_adam_step_matches_tf1_formula(cuda_device):
