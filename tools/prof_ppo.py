@@ -1,0 +1,16 @@
+import sys
+sys.path.insert(0, '.')
+import torch
+import ml4ca_b200 as M
+dev = torch.device('cuda', 0)
+T, n = 16, 1 << 16
+ac = M.ActorCritic(9, 7, (64, 64), 'leaky_relu', device=dev, seed=1)
+g = torch.Generator(device=dev); g.manual_seed(0)
+data = (torch.randn(T, 9, n, device=dev, generator=g), torch.randn(T, 7, n, device=dev, generator=g),
+        torch.randn(T, n, device=dev, generator=g), torch.randn(T, n, device=dev, generator=g),
+        torch.randn(T, n, device=dev, generator=g) - 9.0)
+upd = M.PPOUpdater(ac)
+for _ in range(3):
+    upd._grad(0, data, T, n)
+torch.cuda.synchronize()
+print('ok')
