@@ -156,26 +156,42 @@ __device__ __forceinline__ void chol_solve5(const float (&L)[5][5], const float 
 
 }  // namespace qp
 
-// One SQP solve.  GW lanes cooperate (lanes >= 8 of a group mirror lane (lane & 7)).  Returns the raw solution
-// x[8] = [z, s(z)] (identical in every lane of the group), success, the active-set mask and the iteration count.
+// State of one SQP solve between iterations (replicated in every lane of the group).
+struct SqpState {
+  float z[5];
+  float mu[3];
+  unsigned work;       // working set of the previous QP: bit c = constraint c was active
+  bool have_work, infeasible;
+  int it;
+  float last_step;
+};
+
+__device__ __forceinline__ void sqp_init(SqpState& S, const qp::Problem& P) {
+#pragma unroll
+  for (int i = 0; i < 5; ++i) S.z[i] = fminf(fmaxf(P.prev[i], P.lo[i]), P.hi[i]);
+  S.mu[0] = S.mu[1] = S.mu[2] = 0.f;
+  S.work = 0;
+  S.have_work = false, S.infeasible = false;
+  S.it = 0;
+  S.last_step = 1e30f;
+}
+
+// One SQP iteration for the group's current demand.  GW lanes cooperate (lanes >= 8 of a group mirror lane
+// (lane & 7)).  Returns true when the solve has finished (converged, declared infeasible, or out of iterations).
 template <int GW>
-__device__ void solve_group(const qp::Problem& P, float* __restrict__ Gs /* [8][8] shared, this group */,
-                            unsigned gmask, int lane_in_group, float (&x)[8], bool& success, unsigned& active_mask,
-                            int& iters) {
+__device__ __forceinline__ bool sqp_step(SqpState& S, const qp::Problem& P, float* __restrict__ Gs /* [8][8] shared, this group */,
+                                         unsigned gmask, int lane_in_group) {
   using namespace qp;
   const int b = lane_in_group & 7;  // constraint owned by this lane
   const float sb = (float)ML4CA_QP_SLACK_BOUND;
-  float z[5];
-#pragma unroll
-  for (int i = 0; i < 5; ++i) z[i] = fminf(fmaxf(P.prev[i], P.lo[i]), P.hi[i]);
-  float mu[3] = {0.f, 0.f, 0.f};
-  unsigned work = 0;        // working set of the previous QP: bit c = constraint c was active
-  bool have_work = false;
-  success = false;
-  bool infeasible = false;
-  int it = 0;
-  float last_step = 1e30f;
-  for (; it < kMaxSqp; ++it) {
+  float (&z)[5] = S.z;
+  float (&mu)[3] = S.mu;
+  unsigned& work = S.work;
+  bool& have_work = S.have_work;
+  bool& infeasible = S.infeasible;
+  int& it = S.it;
+  float& last_step = S.last_step;
+  {
     Eval e;
     evaluate(z, P.tau, e);
     float J[3][5];
@@ -390,7 +406,7 @@ __device__ void solve_group(const qp::Problem& P, float* __restrict__ Gs /* [8][
     if (relax_tot > 0.f) {
       if (relax_tot > kInfeasibleMargin || it >= kMaxRelaxedIters) {  // infeasible demand: success stays false
         infeasible = true;
-        break;
+        return true;
       }
       mu_new[0] = mu_new[1] = mu_new[2] = 0.f;
     }
@@ -431,10 +447,21 @@ __device__ void solve_group(const qp::Problem& P, float* __restrict__ Gs /* [8][
     last_step = step;
     if (step < kStepTol && relax_tot == 0.f) {
       ++it;
-      break;
+      return true;
     }
   }
-  iters = it;
+  ++it;
+  return it >= kMaxSqp;
+}
+
+// Raw solution x[8] = [z, s(z)] (identical in every lane of the group), success, the active-set mask.
+__device__ __forceinline__ void sqp_finalize(const SqpState& S, const qp::Problem& P, float (&x)[8], bool& success,
+                                             unsigned& active_mask) {
+  using namespace qp;
+  const float sb = (float)ML4CA_QP_SLACK_BOUND;
+  const float (&z)[5] = S.z;
+  const bool infeasible = S.infeasible;
+  const float last_step = S.last_step;
   Eval e;
   evaluate(z, P.tau, e);
   const float feas = fmaxf(fabsf(e.res[0]), fmaxf(fabsf(e.res[1]), fabsf(e.res[2])));
@@ -457,6 +484,18 @@ __device__ void solve_group(const qp::Problem& P, float* __restrict__ Gs /* [8][
   active_mask = m;
 }
 
+// One whole solve (the one-warp-per-demand layout uses this directly).
+template <int GW>
+__device__ void solve_group(const qp::Problem& P, float* __restrict__ Gs, unsigned gmask, int lane_in_group, float (&x)[8],
+                            bool& success, unsigned& active_mask, int& iters) {
+  SqpState S;
+  sqp_init(S, P);
+  while (!sqp_step<GW>(S, P, Gs, gmask, lane_in_group)) {
+  }
+  iters = S.it;
+  sqp_finalize(S, P, x, success, active_mask);
+}
+
 __device__ __forceinline__ float map_to_pi(float a) {  // qp_allocator.py:101-106
   const float two_pi = 2.0f * (float)ML4CA_PI;
   float m = fmodf(a + (float)ML4CA_PI, two_pi);
@@ -464,26 +503,11 @@ __device__ __forceinline__ float map_to_pi(float a) {  // qp_allocator.py:101-10
   return m - (float)ML4CA_PI;
 }
 
-// MODE 0: solve_QP -> x[8, n] (after the |x| < 0.01 clean-up, :232), status[n].
-// MODE 1: tau_controller_callback_func -> out[7, n] = n_port, n_star, n_bow (%), a_port, a_star, a_bow (rad,
-//         mapped to [-pi, pi)), bow throttle (2.5 n_bow clipped, SIMULATION = False); prev[5, n] updated in place
-//         (held on failure, :267-269,318-320).
-template <int GW, int MODE>
-__global__ void __launch_bounds__(256) qp_kernel(int64_t n, const float* __restrict__ tau, float* __restrict__ prev,
-                                                 float* __restrict__ out, uint32_t* __restrict__ status) {
-  __shared__ float Gs_all[(256 / GW) * 64];
-  const int lane = threadIdx.x & 31;
-  const int lane_in_group = lane % GW;
-  const int group_in_block = threadIdx.x / GW;
-  const int64_t env = (int64_t)blockIdx.x * (256 / GW) + group_in_block;
-  if (env >= n) return;  // whole groups leave together
-  const unsigned gmask = (GW == 32) ? 0xFFFFFFFFu : (((1u << GW) - 1u) << (lane - lane_in_group));
-  float* Gs = Gs_all + group_in_block * 64;
-
-  // lane b < 3 loads tau[b], lane 3..7 loads prev[b - 3]; then broadcast inside the group
-  const int b = lane_in_group & 7;
+// Load one demand: lane b < 3 loads tau[b], lanes 3..7 load prev[b - 3]; broadcast inside the group; box of the step.
+template <int GW>
+__device__ __forceinline__ void load_problem(int64_t n, int64_t env, int b, unsigned gmask, const float* __restrict__ tau,
+                                             const float* __restrict__ prev, qp::Problem& P) {
   const float mine = (b < 3) ? tau[(int64_t)b * n + env] : prev[(int64_t)(b - 3) * n + env];
-  qp::Problem P;
 #pragma unroll
   for (int i = 0; i < 3; ++i) P.tau[i] = __shfl_sync(gmask, mine, i, GW);
 #pragma unroll
@@ -497,11 +521,16 @@ __global__ void __launch_bounds__(256) qp_kernel(int64_t n, const float* __restr
     P.lo[i] = fmaxf(P.prev[i] - lim[i], -cap[i]);
     P.hi[i] = fminf(P.prev[i] + lim[i], cap[i]);
   }
-  float x[8];
-  bool ok;
-  unsigned amask;
-  int iters;
-  solve_group<GW>(P, Gs, gmask, lane_in_group, x, ok, amask, iters);
+}
+
+// MODE 0: solve_QP -> x[8, n] (after the |x| < 0.01 clean-up, :232), status[n].
+// MODE 1: tau_controller_callback_func -> out[7, n] = n_port, n_star, n_bow (%), a_port, a_star, a_bow (rad,
+//         mapped to [-pi, pi)), bow throttle (2.5 n_bow clipped, SIMULATION = False); prev[5, n] updated in place
+//         (held on failure, :267-269,318-320).
+template <int MODE>
+__device__ __forceinline__ void emit_result(int64_t n, int64_t env, int b, int lane_in_group, const qp::Problem& P,
+                                            float (&x)[8], bool ok, unsigned amask, int iters, float* __restrict__ prev,
+                                            float* __restrict__ out, uint32_t* __restrict__ status) {
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     if (fabsf(x[i]) < (float)ML4CA_QP_CLEAN_EPS) x[i] = 0.f;   // :232
@@ -552,18 +581,51 @@ __global__ void __launch_bounds__(256) qp_kernel(int64_t n, const float* __restr
   }
 }
 
+// One demand per group, one launch covers the batch (the literal layouts: 8 lanes or a whole warp per demand).
+template <int GW, int MODE>
+__global__ void __launch_bounds__(256) qp_kernel(int64_t n, const float* __restrict__ tau, float* __restrict__ prev,
+                                                 float* __restrict__ out, uint32_t* __restrict__ status) {
+  __shared__ float Gs_all[(256 / GW) * 64];
+  const int lane = threadIdx.x & 31;
+  const int lane_in_group = lane % GW;
+  const int group_in_block = threadIdx.x / GW;
+  const int64_t env = (int64_t)blockIdx.x * (blockDim.x / GW) + group_in_block;
+  if (env >= n) return;  // whole groups leave together
+  const unsigned gmask = (GW == 32) ? 0xFFFFFFFFu : (((1u << GW) - 1u) << (lane - lane_in_group));
+  float* Gs = Gs_all + group_in_block * 64;
+  const int b = lane_in_group & 7;
+  qp::Problem P;
+  load_problem<GW>(n, env, b, gmask, tau, prev, P);
+  float x[8];
+  bool ok;
+  unsigned amask;
+  int iters;
+  solve_group<GW>(P, Gs, gmask, lane_in_group, x, ok, amask, iters);
+  emit_result<MODE>(n, env, b, lane_in_group, P, x, ok, amask, iters, prev, out, status);
+}
+
 template <int MODE>
 static int launch_qp(int64_t n, const float* tau, float* prev, float* out, uint32_t* status, cudaStream_t st) {
   static const int lanes = [] {   // ML4CA_QP_LANES=8 (default, 4 envs per warp) | 32 (one warp per env)
     const char* e = getenv("ML4CA_QP_LANES");
     return e ? atoi(e) : 8;
   }();
+  // No block-wide barrier in the kernel: small CTAs retire as soon as their own demands have converged instead of
+  // waiting for the slowest of 32 (iteration counts differ 3..25).  ML4CA_QP_THREADS = 32 | 64 | 128 | 256.
+  // (A persistent variant in which every group fetched its next demand inside one common SQP-iteration loop was
+  // measured slower, 11.7 ms against 9.3 ms per Mi demands: the lane idling is inside the active-set loops, not in the
+  // iteration counts.)
+  static const int threads = [] {
+    const char* e = getenv("ML4CA_QP_THREADS");
+    const int t = e ? atoi(e) : 64;
+    return (t == 32 || t == 64 || t == 128 || t == 256) ? t : 64;
+  }();
   if (lanes == 32) {
-    const int64_t blocks = (n + 7) / 8;
-    qp_kernel<32, MODE><<<(unsigned)blocks, 256, 0, st>>>(n, tau, prev, out, status);
+    const int per = threads / 32;
+    qp_kernel<32, MODE><<<(unsigned)((n + per - 1) / per), threads, 0, st>>>(n, tau, prev, out, status);
   } else {
-    const int64_t blocks = (n + 31) / 32;
-    qp_kernel<8, MODE><<<(unsigned)blocks, 256, 0, st>>>(n, tau, prev, out, status);
+    const int per = threads / 8;
+    qp_kernel<8, MODE><<<(unsigned)((n + per - 1) / per), threads, 0, st>>>(n, tau, prev, out, status);
   }
   return check_launch("qp_kernel");
 }
