@@ -29,8 +29,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line: no NCCL version / debug banner (NCCL prints it to stdout when the box sets
+# NCCL_DEBUG=VERSION or INFO); set ML4CA_KEEP_NCCL_DEBUG=1 to keep the caller's setting
+if not os.environ.get("ML4CA_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 ENV_STEP_BYTES = 177      # read 60 state + 28 action, write 48 state + 36 obs + 4 rew + 1 done
 ENV_STEP_TRAFFIC = 3.0087e9  # measured DRAM bytes of one 16 Mi-env launch (profiles/env_step_r1.md); algorithmic: 2.9696e9

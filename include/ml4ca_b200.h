@@ -203,6 +203,13 @@ ML4CA_API int ml4ca_ros_action(int32_t kind, int32_t cont_ang, int32_t simulatio
 ML4CA_API int ml4ca_eval_metrics(int64_t n, int32_t T, float dt, const float* eta, const float* ref, const float* thrust,
                                  const float* angles, float* out, void* stream);
 
+/* Allocator output -> network-order env action, the inverse of the env's action map (customEnv.py:47-53,104-122), so
+ * that the QP / pseudoinverse allocators can drive the same env as the RL policy (the thesis' three-way comparison):
+ * n_pct [3, n] percent thrust port, star, bow; alpha [2, n] stern azimuths (rad) -> action [7, n] = thrusts / 100 and
+ * (sin, cos) pairs (cont_ang) or action [5, n] with azimuths / ang_bound. */
+ML4CA_API int ml4ca_alloc_to_action(int64_t n, int32_t cont_ang, float ang_bound, const float* n_pct, const float* alpha,
+                                    float* action, void* stream);
+
 /* ---- PPO update (ppo.py:234-250,260-280; mpi_tf.py:45-80) --------------------------------------------------------------
  * Gradient of ONE loss over a whole trajectory buffer: net 0 = pi_loss = -mean(min(ratio adv, clip(ratio) adv)) w.r.t. the
  * pi variables and log_std, net 1 = v_loss = mean((ret - v)^2) w.r.t. the v variables.  obs [T, obs_dim, n],

@@ -74,6 +74,7 @@ _SIGNATURES = {
     "ml4ca_ros_state": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_float, c_f32p, c_stream]),
     "ml4ca_ros_action": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_stream]),
     "ml4ca_eval_metrics": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_float, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_stream]),
+    "ml4ca_alloc_to_action": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_float, c_f32p, c_f32p, c_f32p, c_stream]),
     "ml4ca_policy_describe": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PolicyCfg), ctypes.POINTER(ctypes.c_int32)]),
     "ml4ca_ppo_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_f32p,
                                       c_f32p, c_f32p, ctypes.c_float, c_f32p, ctypes.c_void_p, c_stream]),

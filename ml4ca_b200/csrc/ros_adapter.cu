@@ -96,6 +96,29 @@ __global__ void __launch_bounds__(256) ros_action_kernel(int64_t n, int simulati
   }
 }
 
+// Allocator output -> the env's network-order action (inverse of the env's action map, customEnv.py:47-53,104-122):
+// n_pct [3, n] percent thrust in allocator order port, star, bow; alpha [2, n] stern azimuths (rad) ->
+// action [act_dim, n] = [n_bow, n_port, n_star] / 100 and the azimuths as (sin, cos) pairs (continuous angles) or / pi.
+__global__ void __launch_bounds__(256) alloc_to_action_kernel(int64_t n, int cont_ang, float ang_bound,
+                                                              const float* __restrict__ n_pct, const float* __restrict__ alpha,
+                                                              float* __restrict__ action) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  action[i] = n_pct[2 * n + i] * 0.01f;
+  action[n + i] = n_pct[i] * 0.01f;
+  action[2 * n + i] = n_pct[n + i] * 0.01f;
+  const float ap = alpha[i], as = alpha[n + i];
+  if (cont_ang) {
+    float s, c;
+    sincosf(ap, &s, &c);
+    action[3 * n + i] = s, action[4 * n + i] = c;
+    sincosf(as, &s, &c);
+    action[5 * n + i] = s, action[6 * n + i] = c;
+  } else {
+    action[3 * n + i] = ap / ang_bound, action[4 * n + i] = as / ang_bound;
+  }
+}
+
 }  // namespace ml4ca
 
 using namespace ml4ca;
@@ -110,6 +133,15 @@ int ml4ca_ros_state(int64_t n, const float* eta, const float* nu, const float* r
   ros_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, eta, nu, ref, prev_u, integ,
                                                                                              t_inside, h, state);
   return check_launch("ros_state_kernel");
+}
+
+int ml4ca_alloc_to_action(int64_t n, int32_t cont_ang, float ang_bound, const float* n_pct, const float* alpha, float* action,
+                          void* stream) {
+  ML4CA_REQUIRE(n >= 0 && n_pct && alpha && action && ang_bound > 0.f, "bad arguments");
+  if (n == 0) return ML4CA_OK;
+  alloc_to_action_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, cont_ang, ang_bound, n_pct,
+                                                                                                    alpha, action);
+  return check_launch("alloc_to_action_kernel");
 }
 
 int ml4ca_ros_action(int32_t kind, int32_t cont_ang, int32_t simulation, int64_t n, const float* action, float* u,

@@ -59,6 +59,46 @@ def run_RL_policy(env, ac, max_ep_len=None, new_ref=None, ref_change_at=None):
     return rec
 
 
+def run_allocator(env, method="qp", max_ep_len=None):
+    """The classical DP pipeline in the same batched env: PID on the body-frame error (ml4ca_pinv_pid) -> thrust
+    allocation by the SLSQP-equivalent kernel (``method='qp'``, QPTA.tau_controller_callback_func) or the fixed-matrix
+    pseudoinverse (``'pinv'``) -> env step.  Same records and metrics as run_RL_policy: with it, the thesis' comparison
+    RL vs QP vs IPI (results/all_plots) runs for thousands of poses at once."""
+    from .pinv import pinv_pid
+    from .qp_allocator import QPTA
+    n, dev = env.num_envs, env.device
+    assert env.name == 'revoltfinal', "the allocators command two rotating stern azimuths + the fixed bow thruster"
+    T = int(max_ep_len if max_ep_len is not None else env.max_ep_len)
+    eta0 = fixed_test_poses(n)
+    o = env.reset(**{'Hull.PosNED': eta0[0:2], 'Hull.PosAttitude': np.stack([np.zeros(n), np.zeros(n), eta0[2]]),
+                     'Hull.VelocityNu': np.zeros((6, n))})
+    f = dict(dtype=torch.float32, device=dev)
+    rec = {"rew": torch.zeros(T, n, **f), "eta": torch.empty(T + 1, 3, n, **f), "thrust": torch.zeros(T + 1, 3, n, **f),
+           "angles": torch.zeros(T + 1, 2, n, **f)}
+    st = env.get_state()
+    rec["eta"][0], rec["angles"][0] = st["eta"], st["angles"][1:3]
+    integ = torch.zeros(3, n, **f)
+    qp = QPTA(num_envs=n, device=dev) if method == "qp" else None
+    action = torch.empty(env.num_actions, n, **f)
+    ref = env._ref.clone()
+    for t in range(T):
+        n_pct, alpha, tau = pinv_pid(st["eta"], st["nu"], ref, integ, return_tau=True)
+        if qp is not None:
+            qp.tau_controller_callback_func(tau)
+            n_pct, alpha = qp.last_output[0:3].contiguous(), qp.last_output[3:5].contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ml4ca_alloc_to_action(n, int(env.cont_ang), float(env.real_action_bounds[3]), _lib.ptr(n_pct),
+                                                        _lib.ptr(alpha), _lib.ptr(action), _lib.current_stream()),
+                       "ml4ca_alloc_to_action")
+        o, r, d, _ = env.step(action)
+        st = env.get_state()
+        rec["rew"][t], rec["eta"][t + 1] = r, st["eta"]
+        rec["thrust"][t + 1], rec["angles"][t + 1] = st["prev_thrust"], st["angles"][1:3]
+    rec["ep_ret"] = rec["rew"].sum(dim=0)
+    rec["metrics"] = metrics(rec["eta"], ref, rec["thrust"], rec["angles"], env.dt)
+    return rec
+
+
 def metrics(eta, ref, thrust, angles, dt):
     """IAE, W*, IADC per run (ml4ca_eval_metrics): eta [T, 3, n], ref [3, n], thrust [T, 3, n], angles [T, 2, n]."""
     T, _, n = eta.shape

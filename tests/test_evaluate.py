@@ -75,3 +75,28 @@ def test_shipped_policy_from_fixed_test_poses(cuda_device):
     m = rec["metrics"].cpu().numpy()
     assert np.isfinite(m).all() and (m >= 0).all() and (m[0] > 0).all()
     assert rec["thrust"].abs().max() <= 100.0 and rec["ep_ret"].shape == (n,)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["pinv", "qp"])
+def test_classical_allocators_hold_station_in_the_batched_env(cuda_device, method):
+    """PID -> allocator -> env, closed loop from the fixed test poses: the vessel must approach the origin (the action
+    map inversion, the allocator order port/star/bow vs the env order bow/port/star and the thrust law all have to be
+    right for that), and the QP allocator's commands must respect its rate limits."""
+    import torch
+    import ml4ca_b200 as M
+    from ml4ca_b200 import evaluate
+    n = 12
+    env = M.RevoltFinal(M.StandInHull(), testing=True, extended_state=True, cont_ang=True, num_envs=n, device=cuda_device)
+    rec = evaluate.run_allocator(env, method=method, max_ep_len=300)
+    eta = rec["eta"].cpu().numpy()
+    d0, d1 = np.hypot(eta[0, 0], eta[0, 1]), np.hypot(eta[-1, 0], eta[-1, 1])
+    assert np.allclose(d0, 5.0, rtol=1e-6) and (d1 < 1.5).all(), d1            # 60 s of DP: within 1.5 m of the set-point
+    assert (np.abs(eta[-1, 2]) < np.deg2rad(10)).all()
+    m = rec["metrics"].cpu().numpy()
+    assert np.isfinite(m).all() and (m[0] > 0).all()
+    if method == "qp":
+        thr = rec["thrust"].cpu().numpy()
+        force = np.sign(thr) * thr ** 2 * np.array([0.0009, 0.00205, 0.00205])[None, :, None]      # env order bow, port, star
+        dF = np.abs(np.diff(force[1:], axis=0))
+        assert (dF[:, 0] <= 2.0 + 1e-2).all() and (dF[:, 1:] <= 5.0 + 1e-2).all()       # qp_allocator.py:57 rate limits
