@@ -237,26 +237,6 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
     } else {
       if (live) ret = __ldg(A.ret + (int64_t)t * n + i);
     }
-    {                                          // ask for the next tile's rows now: they arrive while this tile computes
-      const int64_t nt = tile + (int64_t)gridDim.x * G;
-      if (nt < num_tiles) {
-        const int64_t t2 = nt / tiles_per_t, i2 = (nt % tiles_per_t) * TS + row;
-        if (i2 < n) {
-          auto pf = [](const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); };
-#pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (c < obs) pf(A.obs_buf + ((int64_t)t2 * obs + c) * n + i2);
-          if constexpr (NET == 0) {
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-              if (a < nout) pf(A.act_buf + ((int64_t)t2 * A.act + a) * n + i2);
-            pf(A.adv + (int64_t)t2 * n + i2), pf(A.logp_old + (int64_t)t2 * n + i2);
-          } else {
-            pf(A.ret + (int64_t)t2 * n + i2);
-          }
-        }
-      }
-    }
     if (pending) {                             // the previous tile's dW1T chain still reads A0 / G1
       wait_mma();
       pending = false;

@@ -81,10 +81,27 @@ def run_allocator(env, method="qp", max_ep_len=None):
     qp = QPTA(num_envs=n, device=dev) if method == "qp" else None
     action = torch.empty(env.num_actions, n, **f)
     ref = env._ref.clone()
-    for t in range(T):
+    # The SLSQP programme only admits demands its rate limits can follow (|df| <= 5, 5, 2 N per call): on the vessel the
+    # reference filter feeds it smooth demands.  Stand-in: the demand is the wrench the thrusters deliver now plus the
+    # PID's request clipped to +-[4, 2, 2] -- the neighbourhood law of BASELINE config 1 (99.7 % success with the
+    # reference solver).
+    slew = torch.tensor([[4.0], [2.0], [2.0]], **f)
+    lx, ly = (-1.12, -1.12, 1.08), (-0.15, 0.15, 0.0)            # qp_allocator.py:69-70
+
+    def delivered(prev):                                           # B(alpha) f of the allocator's current state
+        f0, f1, f2, a0, a1 = prev
+        c0, s0, c1, s1 = torch.cos(a0), torch.sin(a0), torch.cos(a1), torch.sin(a1)
+        return torch.stack([f0 * c0 + f1 * c1, f0 * s0 + f1 * s1 + f2,
+                            f0 * (lx[0] * s0 - ly[0] * c0) + f1 * (lx[1] * s1 - ly[1] * c1) + f2 * lx[2]])
+    trust = torch.ones(n, **f)     # per-run scale of the clip: halved when the programme is infeasible (the allocator then
+    for t in range(T):             # holds its state, qp_allocator.py:267-269), restored step by step when it succeeds
         n_pct, alpha, tau = pinv_pid(st["eta"], st["nu"], ref, integ, return_tau=True)
         if qp is not None:
-            qp.tau_controller_callback_func(tau)
+            now = delivered(qp._prev)
+            lim = slew * trust[None, :]
+            qp.tau_controller_callback_func(now + torch.minimum(torch.maximum(tau - now, -lim), lim))
+            ok = (qp.last_status & 1).bool()
+            trust = torch.where(ok, (trust * 2).clamp(max=1.0), trust * 0.5)
             n_pct, alpha = qp.last_output[0:3].contiguous(), qp.last_output[3:5].contiguous()
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().ml4ca_alloc_to_action(n, int(env.cont_ang), float(env.real_action_bounds[3]), _lib.ptr(n_pct),
