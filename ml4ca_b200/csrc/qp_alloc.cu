@@ -42,7 +42,7 @@ namespace qp {
 constexpr int kMaxSqp = 25;
 constexpr int kMaxGi = 40;
 constexpr int kMaxRelaxedIters = 12;
-constexpr float kInfeasibleMargin = 4.0f;  // linearised constraints violated by more than this (N, Nm): give up
+constexpr float kInfeasibleMargin = 16.0f;  // linearised constraints violated by more than this (N, Nm): give up
 constexpr float kStepTol = 2e-6f;          // scaled step below which the iteration has converged
 constexpr float kActTol = 1e-5f;           // constraint within this of its bound counts as active in the status word
 

@@ -17,7 +17,7 @@ from oracle import constants as C
 
 LX, LY = C.LX, C.LY
 FIRST_IDENTITY = True
-INFEASIBLE_MARGIN = 4.0     # linearised constraints violated by more than this (N, Nm) -> infeasible
+INFEASIBLE_MARGIN = 16.0    # linearised constraints violated by more than this (N, Nm) -> infeasible
 MAX_RELAXED_ITERS = 12
 LS_MAX = 12
 
