@@ -205,18 +205,42 @@ def run_reference(args, rank, world):
     n_total, inner = 1 << 16, 8
     per = max(1, n_total // cores)
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_ref_init, initargs=(per, 4000)) as pool:
-        for _ in range(max(1, min(args.warmup, 2))):
-            pool.map(_ref_step, [1] * cores)
-        t0 = time.perf_counter()
-        done_steps = 0
-        budget_s = 120.0
-        for _ in range(args.steps):
-            pool.map(_ref_step, [inner] * cores)
-            done_steps += 1
-            if time.perf_counter() - t0 > budget_s:
+
+    def serve(conn, idx):                       # one dedicated process per core: exactly one task per core and step
+        _ref_init(per, 4000 + idx)
+        while True:
+            k = conn.recv()
+            if k <= 0:
                 break
-        wall = time.perf_counter() - t0
+            conn.send(_ref_step(k))
+
+    pipes, procs = [], []
+    for c in range(cores):
+        a, b = ctx.Pipe()
+        pr = ctx.Process(target=serve, args=(b, c), daemon=True)
+        pr.start()
+        pipes.append(a), procs.append(pr)
+
+    def step_all(k):
+        for a in pipes:
+            a.send(k)
+        return [a.recv() for a in pipes]
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_all(1)
+    t0 = time.perf_counter()
+    done_steps = 0
+    budget_s = 120.0
+    for _ in range(args.steps):
+        step_all(inner)
+        done_steps += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    wall = time.perf_counter() - t0
+    for a in pipes:
+        a.send(0)
+    for pr in procs:
+        pr.join(timeout=5)
     n_total = per * cores
     value = n_total * inner * done_steps / wall
     sample = "%d envs x %d env-steps per bench step, %d bench steps, %d persistent processes" % (n_total, inner, done_steps, cores)
