@@ -178,6 +178,13 @@ ML4CA_API int ml4ca_gae(int64_t n, int32_t T, const float* rew, const float* val
                         float gamma, float lam, float* adv, float* ret, void* stream);
 /* mpi_statistics_scalar (mpi_tools.py:71-93), local part: out3 (device, 3 doubles) = [sum, sum of squares, count]. */
 ML4CA_API int ml4ca_stats(int64_t m, const float* x, double* out3, void* stream);
+/* ... with_min_and_max=True: out5 (device, 5 doubles) = [sum, sum of squares, count, min, max] (min / max = +-1e300 if empty). */
+ML4CA_API int ml4ca_stats5(int64_t m, const float* x, double* out5, void* stream);
+/* The logger's EpRet / EpLen (ppo.py:296-297,317-318; logx.EpochLogger) from the [T, n] reward and done-flag records:
+ * run_ret [n], run_len [n] carry the episode in progress across epochs (in/out); ret5 / len5 as in ml4ca_stats5 over the
+ * episodes that ended inside the buffer. */
+ML4CA_API int ml4ca_episode_stats(int64_t n, int32_t T, const float* rew, const uint8_t* done, float* run_ret,
+                                  int32_t* run_len, double* ret5, double* len5, void* stream);
 /* advantage normalisation x <- (x - mean) / (std + 1e-8) (ppo.py:103). */
 ML4CA_API int ml4ca_normalize(int64_t m, float* x, float mean, float std, void* stream);
 

@@ -70,6 +70,9 @@ _SIGNATURES = {
     "ml4ca_gae": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_u8p, c_f32p, ctypes.c_float, ctypes.c_float,
                                  c_f32p, c_f32p, c_stream]),
     "ml4ca_stats": (ctypes.c_int, [ctypes.c_int64, c_f32p, ctypes.c_void_p, c_stream]),
+    "ml4ca_stats5": (ctypes.c_int, [ctypes.c_int64, c_f32p, ctypes.c_void_p, c_stream]),
+    "ml4ca_episode_stats": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, c_f32p, c_u8p, c_f32p, c_i32p, ctypes.c_void_p,
+                                           ctypes.c_void_p, c_stream]),
     "ml4ca_normalize": (ctypes.c_int, [ctypes.c_int64, c_f32p, ctypes.c_float, ctypes.c_float, c_stream]),
     "ml4ca_ros_state": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_float, c_f32p, c_stream]),
     "ml4ca_ros_action": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_stream]),

@@ -71,6 +71,92 @@ __global__ void __launch_bounds__(256) stats_kernel(int64_t m, const float* __re
   }
 }
 
+__device__ __forceinline__ void atomic_min_d(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (__longlong_as_double((long long)assumed) <= v) break;
+    old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+  } while (assumed != old);
+}
+__device__ __forceinline__ void atomic_max_d(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (__longlong_as_double((long long)assumed) >= v) break;
+    old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+  } while (assumed != old);
+}
+
+// Warp-then-block reduction of (sum, sum of squares, count, min, max) followed by one set of atomics per block.
+__device__ __forceinline__ void reduce5(double s, double q, double c, double lo, double hi, double* __restrict__ out5) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+    q += __shfl_xor_sync(0xFFFFFFFFu, q, off);
+    c += __shfl_xor_sync(0xFFFFFFFFu, c, off);
+    lo = fmin(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, off));
+    hi = fmax(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, off));
+  }
+  __shared__ double sh[5][8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) sh[0][w] = s, sh[1][w] = q, sh[2][w] = c, sh[3][w] = lo, sh[4][w] = hi;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
+      sh[0][0] += sh[0][k], sh[1][0] += sh[1][k], sh[2][0] += sh[2][k], sh[3][0] = fmin(sh[3][0], sh[3][k]), sh[4][0] = fmax(sh[4][0], sh[4][k]);
+    if (sh[2][0] > 0.0) {
+      atomicAdd(out5, sh[0][0]);
+      atomicAdd(out5 + 1, sh[1][0]);
+      atomicAdd(out5 + 2, sh[2][0]);
+      atomic_min_d(out5 + 3, sh[3][0]);
+      atomic_max_d(out5 + 4, sh[4][0]);
+    }
+  }
+}
+
+// mpi_statistics_scalar(x, with_min_and_max=True), local part: [sum, sum of squares, count, min, max].
+__global__ void __launch_bounds__(256) stats5_kernel(int64_t m, const float* __restrict__ x, double* __restrict__ out5) {
+  double s = 0.0, q = 0.0, c = 0.0, lo = 1e300, hi = -1e300;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = (double)x[i];
+    s += v, q += v * v, c += 1.0, lo = fmin(lo, v), hi = fmax(hi, v);
+  }
+  reduce5(s, q, c, lo, hi, out5);
+}
+
+// EpRet / EpLen of the logger (ppo.py:296-297,317-318): one thread per environment walks its column of the [T, n]
+// reward and done-flag records, carrying the running return and length of the episode in progress across epochs
+// (run_ret / run_len, in/out); every episode that ends inside the buffer contributes to the two statistics blocks.
+__global__ void __launch_bounds__(256) episode_stats_kernel(int64_t n, int T, const float* __restrict__ rew,
+                                                            const uint8_t* __restrict__ done, float* __restrict__ run_ret,
+                                                            int32_t* __restrict__ run_len, double* __restrict__ ret5,
+                                                            double* __restrict__ len5) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0, q = 0.0, c = 0.0, lo = 1e300, hi = -1e300, ls = 0.0, lq = 0.0, llo = 1e300, lhi = -1e300;
+  if (i < n) {
+    float acc = run_ret[i];
+    int len = run_len[i];
+    for (int t = 0; t < T; ++t) {
+      const int64_t k = (int64_t)t * n + i;
+      acc += rew[k];
+      len += 1;
+      if (done[k] != 0) {
+        const double v = (double)acc, l = (double)len;
+        s += v, q += v * v, c += 1.0, lo = fmin(lo, v), hi = fmax(hi, v);
+        ls += l, lq += l * l, llo = fmin(llo, l), lhi = fmax(lhi, l);
+        acc = 0.f, len = 0;
+      }
+    }
+    run_ret[i] = acc, run_len[i] = len;
+  }
+  reduce5(s, q, c, lo, hi, ret5);
+  __syncthreads();
+  reduce5(ls, lq, c, llo, lhi, len5);
+}
+
 // x <- (x - mean) / (std + 1e-8)   (ppo.py:103)
 __global__ void __launch_bounds__(256) normalize_kernel(int64_t m, float* __restrict__ x, float mean, float inv) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,6 +187,33 @@ int ml4ca_stats(int64_t m, const float* x, double* out3, void* stream) {
   const unsigned blocks = (unsigned)(want < 4 * kNumSMs ? want : 4 * kNumSMs);
   stats_kernel<<<blocks, 256, 0, st>>>(m, x, out3);
   return check_launch("stats_kernel");
+}
+
+static int init5(double* out5, cudaStream_t st) {
+  const double init[5] = {0.0, 0.0, 0.0, 1e300, -1e300};
+  ML4CA_CUDA(cudaMemcpyAsync(out5, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  return ML4CA_OK;
+}
+
+int ml4ca_stats5(int64_t m, const float* x, double* out5, void* stream) {
+  ML4CA_REQUIRE(m >= 0 && x && out5, "bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = init5(out5, st);
+  if (rc != ML4CA_OK || m == 0) return rc;
+  const int64_t want = (m + 255) / 256;
+  stats5_kernel<<<(unsigned)(want < 4 * kNumSMs ? want : 4 * kNumSMs), 256, 0, st>>>(m, x, out5);
+  return check_launch("stats5_kernel");
+}
+
+int ml4ca_episode_stats(int64_t n, int32_t T, const float* rew, const uint8_t* done, float* run_ret, int32_t* run_len,
+                        double* ret5, double* len5, void* stream) {
+  ML4CA_REQUIRE(n >= 0 && T >= 0 && rew && done && run_ret && run_len && ret5 && len5, "bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = init5(ret5, st);
+  if (rc == ML4CA_OK) rc = init5(len5, st);
+  if (rc != ML4CA_OK || n == 0 || T == 0) return rc;
+  episode_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, T, rew, done, run_ret, run_len, ret5, len5);
+  return check_launch("episode_stats_kernel");
 }
 
 int ml4ca_normalize(int64_t m, float* x, float mean, float std, void* stream) {

@@ -175,22 +175,37 @@ class PPOUpdater(object):
 
 def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2, pi_lr=3e-4, vf_lr=1e-3,
         train_pi_iters=80, train_v_iters=80, lam=0.97, target_kl=0.01, seed=0, hidden_sizes=(64, 64),
-        activation="leaky_relu", fused=False, logger=None):
+        activation="leaky_relu", fused=False, logger=None, logger_kwargs=None):
     """ppo.py:107-346 for a batched env: every epoch = ``steps_per_epoch`` steps of EVERY environment of ``env``
     (rollout), GAE-lambda (finish_path), advantage normalisation over all ranks, then the PPO update.
-    Hyper-parameter defaults are the reference's config.json.  Returns (ac, list of per-epoch dictionaries)."""
-    from . import mpi_tools
+    Hyper-parameter defaults are the reference's config.json.  ``logger_kwargs=dict(output_dir=..., exp_name=...)``
+    writes progress.txt / config.json in the reference's format (ppo.py:332-346, logx.py).  ``logger`` may be a callable
+    receiving each epoch's dictionary.  Returns (ac, list of per-epoch dictionaries)."""
+    import time as _time
+    from . import logx, mpi_tools
     from .core import ActorCritic
-    n = env.num_envs
+    n, dev = env.num_envs, env.device
     if ac is None:
-        ac = ActorCritic(env.num_states, env.num_actions, hidden_sizes, activation, device=env.device, seed=seed)
+        ac = ActorCritic(env.num_states, env.num_actions, hidden_sizes, activation, device=dev, seed=seed)
     params = ac.parameters()
     mpi_tools.sync_all_params(params)             # ppo.py:255
     ac.refresh()
-    buf = TrajectoryBuffer(env.num_states, env.num_actions, steps_per_epoch, n, gamma, lam, device=env.device)
+    buf = TrajectoryBuffer(env.num_states, env.num_actions, steps_per_epoch, n, gamma, lam, device=dev)
     upd = PPOUpdater(ac, clip_ratio, pi_lr, vf_lr, train_pi_iters, train_v_iters, target_kl)
+    flog = None
+    if logger_kwargs is not None:
+        flog = logx.Logger(rank=mpi_tools.proc_id(), **logger_kwargs)
+        flog.save_config(dict(steps_per_epoch=steps_per_epoch, epochs=epochs, gamma=gamma, clip_ratio=clip_ratio, pi_lr=pi_lr,
+                              vf_lr=vf_lr, train_pi_iters=train_pi_iters, train_v_iters=train_v_iters, lam=lam,
+                              target_kl=target_kl, seed=seed, max_ep_len=env.max_ep_len, num_envs=n,
+                              num_procs=mpi_tools.num_procs(), actor_critic="mlp_actor_critic",
+                              ac_kwargs=dict(hidden_sizes=list(ac.hidden_sizes), activation=ac.activation)))
+    run_ret = torch.zeros(n, dtype=torch.float32, device=dev)
+    run_len = torch.zeros(n, dtype=torch.int32, device=dev)
+    s5 = torch.zeros(3, 5, dtype=torch.float64, device=dev)       # EpRet, EpLen, VVals
+    L = _lib.lib()
     env.reset(fraction=0.8)
-    history, step = [], 0
+    history, step, start_time = [], 0, _time.time()
     for epoch in range(epochs):
         o_last = rollout(env, ac, buf, seed=seed, start_step=step, fused=fused)
         step += steps_per_epoch
@@ -198,10 +213,38 @@ def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2,
             o_last = env.observe()
         _, v_last, _ = ac.step(o_last, deterministic=True, step=step)
         buf.finish_path(last_val=v_last)          # ppo.py:311 for the envs still running at the epoch end
+        with torch.cuda.device(dev):
+            st = _lib.current_stream()
+            _lib.check(L.ml4ca_episode_stats(n, steps_per_epoch, _lib.ptr(buf.rew_buf), _lib.ptr(buf.done_buf), _lib.ptr(run_ret),
+                                             _lib.ptr(run_len), _lib.ptr(s5[0]), _lib.ptr(s5[1]), st), "ml4ca_episode_stats")
+            _lib.check(L.ml4ca_stats5(steps_per_epoch * n, _lib.ptr(buf.val_buf), _lib.ptr(s5[2]), st), "ml4ca_stats5")
+        red = s5.clone()
+        mpi_tools.allreduce_sum_(red[:, 0:3])
+        if mpi_tools.num_procs() > 1:
+            lo, hi = red[:, 3].clone(), red[:, 4].clone()
+            torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+            torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+            red[:, 3], red[:, 4] = lo, hi
+        red = red.tolist()
         rew_mean = float(mpi_tools.mpi_avg(buf.rew_buf.mean().item()))
         info = upd.update(buf)
-        info.update(Epoch=epoch, AverageStepReward=rew_mean, TotalEnvInteracts=(epoch + 1) * steps_per_epoch * n * mpi_tools.num_procs())
+        info.update(Epoch=epoch, AverageStepReward=rew_mean,
+                    TotalEnvInteracts=(epoch + 1) * steps_per_epoch * n * mpi_tools.num_procs(),
+                    AverageEpRet=logx.statistics_from5(red[0])[0], EpLen=logx.statistics_from5(red[1])[0],
+                    AverageVVals=logx.statistics_from5(red[2])[0], Episodes=int(red[0][2]))
         history.append(info)
+        if flog is not None:                      # the reference's columns, in its order (ppo.py:332-346)
+            flog.log_tabular('Epoch', epoch)
+            flog.log_stats('EpRet', red[0], with_min_and_max=True)
+            flog.log_stats('EpLen', red[1], average_only=True)
+            flog.log_stats('VVals', red[2], with_min_and_max=True)
+            flog.log_tabular('TotalEnvInteracts', info['TotalEnvInteracts'])
+            for k in ('LossPi', 'LossV', 'DeltaLossPi', 'DeltaLossV', 'Entropy', 'KL', 'ClipFrac', 'StopIter'):
+                flog.log_tabular(k, info[k])
+            flog.log_tabular('Time', _time.time() - start_time)
+            off = ac.var_counts[0] - ac.act_dim
+            flog.log_tabular('MeanLogStd', float(ac.parameters()[off:off + ac.act_dim].mean().item()))
+            flog.dump_tabular()
         if logger is not None:
             logger(info)
     return ac, history

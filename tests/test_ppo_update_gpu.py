@@ -110,3 +110,58 @@ def test_update_improves_the_surrogate_and_stops_on_kl(cuda_device):
     assert 0 < info["StopIter"] < 79 and info["KL"] > 1.5e-4      # stopped by the KL rule, with that step applied
     assert not torch.equal(flat0, ac.parameters())
     assert not torch.equal(mu_before, ac.step(buf.obs_buf[0], deterministic=True)[0])
+
+
+def test_training_run_writes_the_reference_log_format(cuda_device, tmp_path):
+    """ppo() with logger_kwargs: progress.txt carries exactly the columns of the reference's shipped runs
+    (tests/golden/progress_header.txt = first line of data/finalmodel/finconttothighbowder_s0/progress.txt), one row per
+    epoch, and the episode statistics agree with a NumPy scan of the recorded buffer."""
+    import json, os
+    import ml4ca_b200 as M
+    from conftest import GOLDEN
+    n, T = 4096, 60
+    env = M.RevoltFinal(M.StandInHull(), extended_state=True, cont_ang=True, num_envs=n, device=cuda_device, seed=3,
+                        auto_reset=True, max_ep_len=40)                       # 20-step episodes
+    seen = []
+    ac, hist = M.ppo(env, steps_per_epoch=T, epochs=2, train_pi_iters=3, train_v_iters=3, seed=3,
+                     logger_kwargs=dict(output_dir=str(tmp_path), exp_name="t"), logger=seen.append)
+    lines = open(os.path.join(tmp_path, "progress.txt")).read().splitlines()
+    assert lines[0] == open(os.path.join(GOLDEN, "progress_header.txt")).read().strip()
+    assert len(lines) == 3 and len(lines[1].split("\t")) == len(lines[0].split("\t"))
+    row = dict(zip(lines[0].split("\t"), map(float, lines[2].split("\t"))))
+    assert row["Epoch"] == 1 and row["TotalEnvInteracts"] == 2 * T * n and row["EpLen"] <= 20 + 1e-9
+    assert row["MinEpRet"] <= row["AverageEpRet"] <= row["MaxEpRet"] and row["StdVVals"] >= 0
+    cfg = json.load(open(os.path.join(tmp_path, "config.json")))
+    assert cfg["gamma"] == 0.99 and cfg["ac_kwargs"]["hidden_sizes"] == [64, 64]
+    assert hist[-1]["Episodes"] >= 2 * n          # 60 steps of <= 20-step episodes: at least two ended per env per epoch
+
+
+def test_episode_statistics_kernel(cuda_device):
+    import torch
+    from ml4ca_b200 import _lib
+    rng = np.random.default_rng(0)
+    n, T = 777, 50
+    rew = rng.normal(size=(2, T, n)).astype(np.float32)
+    done = (rng.random((2, T, n)) < 0.07).astype(np.uint8) * rng.integers(1, 4, (2, T, n)).astype(np.uint8)
+    run_ret, run_len = torch.zeros(n, device=cuda_device), torch.zeros(n, dtype=torch.int32, device=cuda_device)
+    s5 = torch.zeros(2, 5, dtype=torch.float64, device=cuda_device)
+    acc, ln = np.zeros(n), np.zeros(n, dtype=np.int64)
+    for e in range(2):                             # two consecutive buffers: episodes carry over the boundary
+        r_t, d_t = torch.as_tensor(rew[e], device=cuda_device), torch.as_tensor(done[e], device=cuda_device)
+        _lib.check(_lib.lib().ml4ca_episode_stats(n, T, _lib.ptr(r_t), _lib.ptr(d_t), _lib.ptr(run_ret), _lib.ptr(run_len),
+                                                  _lib.ptr(s5[0]), _lib.ptr(s5[1]), _lib.current_stream()))
+        rets, lens = [], []
+        for t in range(T):
+            acc += rew[e, t]; ln += 1
+            end = done[e, t] != 0
+            rets += list(acc[end]); lens += list(ln[end])
+            acc[end] = 0; ln[end] = 0
+        got = s5.cpu().numpy()
+        want_r = [np.sum(rets), np.sum(np.square(rets)), len(rets), np.min(rets), np.max(rets)]
+        want_l = [np.sum(lens), np.sum(np.square(lens)), len(lens), np.min(lens), np.max(lens)]
+        np.testing.assert_allclose(got[0], want_r, rtol=2e-5, atol=1e-4)
+        np.testing.assert_allclose(got[1], want_l, rtol=1e-12)
+    x = torch.as_tensor(rew[0], device=cuda_device)
+    _lib.check(_lib.lib().ml4ca_stats5(x.numel(), _lib.ptr(x), _lib.ptr(s5[0]), _lib.current_stream()))
+    np.testing.assert_allclose(s5[0].cpu().numpy(), [rew[0].astype(np.float64).sum(), (rew[0].astype(np.float64) ** 2).sum(), rew[0].size,
+                                                     rew[0].min(), rew[0].max()], rtol=1e-9)
