@@ -23,7 +23,8 @@ class TrajectoryBuffer(object):
         self.device = torch.device(device if device is not None else "cuda")
         T, n = int(size), int(num_envs)
         f = dict(dtype=torch.float32, device=self.device)
-        self.obs_buf = torch.zeros(T, obs_dim, n, **f)
+        self._obs_rows = torch.zeros(T + 1, obs_dim, n, **f)   # row t = observation the policy acts on at step t; row T =
+        self.obs_buf = self._obs_rows[:T]                      # the observation after the last step (no per-step copy)
         self.act_buf = torch.zeros(T, act_dim, n, **f)
         self.adv_buf = torch.zeros(T, n, **f)
         self.rew_buf = torch.zeros(T, n, **f)
@@ -78,18 +79,16 @@ def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, fused=False
                                             _lib.ptr(buf.rew_buf[t]), _lib.ptr(buf.val_buf[t]), _lib.ptr(buf.logp_buf[t]),
                                             _lib.ptr(buf.done_buf[t]), stream), "ml4ca_rollout_step")
         return None
-    obs = env._obs          # observation returned by the last reset()/step()
-    nxt = torch.empty_like(obs)
-    for t in range(T):
-        buf.obs_buf[t].copy_(obs)
-        _lib.check(L.ml4ca_policy_forward(ac._handle, n, _lib.ptr(obs), seed & 0xFFFFFFFFFFFFFFFF, start_step + t,
+    rows = buf._obs_rows
+    rows[0].copy_(env._obs)  # observation returned by the last reset()/step(); from here on the env kernel writes row t + 1
+    for t in range(T):       # directly, so the record costs no extra copy
+        _lib.check(L.ml4ca_policy_forward(ac._handle, n, _lib.ptr(rows[t]), seed & 0xFFFFFFFFFFFFFFFF, start_step + t,
                                           int(bool(deterministic)), env._cfg.env_id_offset, _lib.ptr(buf.act_buf[t]),
                                           _lib.ptr(buf.val_buf[t]), _lib.ptr(buf.logp_buf[t]), None, stream),
                    "ml4ca_policy_forward")
-        env.step_into(buf.act_buf[t], nxt, buf.rew_buf[t], buf.done_buf[t])
-        obs, nxt = nxt, obs
-    env._obs = obs
-    return obs
+        env.step_into(buf.act_buf[t], rows[t + 1], buf.rew_buf[t], buf.done_buf[t])
+    env._obs = rows[T].clone()
+    return env._obs
 
 
 class PPOUpdater(object):
