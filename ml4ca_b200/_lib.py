@@ -94,6 +94,14 @@ def lib():
     """The loaded library (loads on first use; raises if it has not been built)."""
     global _lib
     if _lib is None:
+        if "ML4CA_LIB" not in os.environ:
+            # building is not a fallback: the same sm_100a sources, compiled when the library is absent or older than
+            # them (nvcc cross-compiles without a GPU; a no-op when the stamp matches)
+            try:
+                from . import build as _build
+                _build.build()
+            except Exception:  # noqa: BLE001 -- no nvcc here: use the library that travelled with the tree, if any
+                pass
         if not os.path.exists(LIB_PATH):
             raise Ml4caError(
                 "libml4ca_b200.so is missing (%s). Build it with `python -m ml4ca_b200.build`; "
