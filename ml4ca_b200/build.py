@@ -35,7 +35,7 @@ def _nvcc():
 
 def _digest():
     h = hashlib.sha256()
-    files = sorted(os.listdir(CSRC)) + ["../../include/ml4ca_b200.h"]
+    files = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + ["../../include/ml4ca_b200.h"]
     for f in files:
         path = os.path.join(CSRC, f)
         if os.path.isfile(path):
