@@ -193,14 +193,19 @@ __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : (VEC ==
     int sat[T::NCMD];
 #pragma unroll
     for (int c = 0; c < T::ACT; ++c) act[c] = a[c][j];
-    transform_action<KIND, CONT>(act, cmd, sat);                       // customEnv.py:104-110
+    float sp = 0.f, cp = 1.f, ss = 0.f, cs = 1.f;
+    if constexpr (KIND == ML4CA_ENV_FINAL && CONT) {
+      transform_action_final_cont(act, cmd, sat, sp, cp, ss, cs);      // customEnv.py:104-110, (sin, cos) from the pairs
+    } else {
+      transform_action<KIND, CONT>(act, cmd, sat);
+    }
     const float pa_bow = ang[0][j], pa_port = ang[1][j], pa_star = ang[2][j];  // prev_angles, :102
     apply_angle_commands<KIND, CONT>(cmd, ang[0][j], ang[1][j], ang[2][j]);    // :117-122
     dang[0][j] = ang[0][j] - pa_bow, dang[1][j] = ang[1][j] - pa_port, dang[2][j] = ang[2][j] - pa_star;
     thr[0][j] = cmd[0], thr[1][j] = cmd[1], thr[2][j] = cmd[2];        // prev_thrust <- action[0:3], :126
     wx[j] = wy[j] = wn[j] = 0.f;
     if (p.n_sub > 0) {
-      float sb, cb, sp, cp, ss, cs;
+      float sb, cb;
       if constexpr (T::NANG == 3) {
         sincosf(ang[0][j], &sb, &cb);
       } else if constexpr (KIND == ML4CA_ENV_SIMPLE) {
@@ -208,10 +213,7 @@ __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : (VEC ==
       } else {
         sb = 1.f, cb = 0.f;                                            // bow azimuth fixed at 90 deg (:394-399)
       }
-      if constexpr (KIND == ML4CA_ENV_FINAL && CONT) {
-        unit_from_pair(act[3], act[4], sp, cp);                        // (sin, cos) straight from the network pair
-        unit_from_pair(act[5], act[6], ss, cs);
-      } else {
+      if constexpr (!(KIND == ML4CA_ENV_FINAL && CONT)) {
         sincosf(ang[1][j], &sp, &cp);
         sincosf(ang[2][j], &ss, &cs);
       }

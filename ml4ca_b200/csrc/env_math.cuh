@@ -183,6 +183,41 @@ __device__ __forceinline__ void unit_from_pair(float y, float x, float& s, float
   if (!ok && h2 != 0.f) sincosf(atan2f(y, x), &s, &c);  // denormal / overflow corner: exact route
 }
 
+// atan2(s, c) of a UNIT vector, branch-free: a = min(|s|, |c|) / max(|s|, |c|) in [0, 1] (the max is >= 0.707, so the
+// MUFU reciprocal is safe), odd minimax polynomial of degree 15 (max error 1.2e-7 rad in fp32, the size of one ulp of
+// pi), octant / quadrant / sign fix-ups by selects.  ~20 instructions against ~45 with branches for atan2f.
+__device__ __forceinline__ float atan2_unit(float s, float c) {
+  const float as = fabsf(s), ac = fabsf(c);
+  const float mx = fmaxf(as, ac), mn = fminf(as, ac);
+  const float a = mn * __frcp_rn(mx);
+  const float z = a * a;
+  float p = -0.004054387100040913f;
+  p = fmaf(p, z, 0.021862266585230827f);
+  p = fmaf(p, z, -0.05591126158833504f);
+  p = fmaf(p, z, 0.09642113000154495f);
+  p = fmaf(p, z, -0.13908593356609344f);
+  p = fmaf(p, z, 0.1994655728340149f);
+  p = fmaf(p, z, -0.33329859375953674f);
+  p = fmaf(p, z, 0.9999993443489075f);
+  float r = p * a;
+  r = as > ac ? 1.5707963267948966f - r : r;
+  r = c < 0.f ? 3.14159265358979323846f - r : r;
+  return copysignf(r, s);
+}
+
+// RevoltFinal with continuous angles on the step path: thrust commands as in transform_action, azimuth commands and
+// their (sin, cos) from the network's pairs without atan2f / sincosf.
+__device__ __forceinline__ void transform_action_final_cont(const float (&a)[7], float (&cmd)[5], int (&sat)[5], float& sp,
+                                                            float& cp, float& ss, float& cs) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) cmd[i] = scale_clip(a[i], (float)ML4CA_THRUST_BOUND, sat[i]);
+  unit_from_pair(a[3], a[4], sp, cp);
+  unit_from_pair(a[5], a[6], ss, cs);
+  cmd[3] = fminf(fmaxf(atan2_unit(sp, cp), -kPi), kPi);     // handle_continuous_angles + scale_and_clip, :227-235,215-225
+  cmd[4] = fminf(fmaxf(atan2_unit(ss, cs), -kPi), kPi);
+  sat[3] = sat[4] = 0;
+}
+
 // Per-launch constants of the integrator, folded on the host (hull_consts()).
 struct HullConsts {
   float h;                    // sub-step, s
@@ -218,8 +253,10 @@ inline HullConsts hull_consts(float h) {
 //  * nu+ = (1 - h d(nu)/m) nu + h (tau + coriolis)/m      -- 3 products + 3 x 3 FMA
 //  * the pose increments are summed un-scaled (sum R nu, sum r) and multiplied by h once, apart from the pose
 //    itself, so 20 small additions do not each round at the magnitude of N, E
-//  * R(psi) advances by the angle-sum recurrence with a 3rd-order small-angle kernel written in r
-//    (|h r| <= 1e-2: truncation ~1e-13 per sub-step); (s, c) only feed the position increment.
+//  * R(psi) advances by the angle-sum recurrence with the small-angle kernel (cos, sin)(h r) ~ (1 - (h r)^2 / 2, h r):
+//    |h r| <= 5.2e-3, so the heading used for the position increments drifts by (h r)^3 / 6 <= 2.3e-8 rad per
+//    sub-step (<= 7e-8 m per env step at top speed, below the fp32 resolution of N, E); (s, c) are re-derived from
+//    psi at every env step and psi itself is the exact sum of h r.
 __device__ __forceinline__ void integrate_hull(float& N, float& E, float& psi, float& u, float& v, float& r,
                                                float tx, float ty, float tn, int n_sub, const HullConsts& k) {
   const float ax = k.hm1 * tx, ay = k.hm2 * ty, an = k.hm3 * tn;
@@ -240,7 +277,7 @@ __device__ __forceinline__ void integrate_hull(float& N, float& E, float& psi, f
     sr += r;
     const float r2 = r * r;
     const float cd = fmaf(k.rot_c2, r2, 1.0f);
-    const float sd = r * fmaf(k.rot_s3, r2, k.rot_s1);
+    const float sd = r * k.rot_s1;
     const float cn = fmaf(-s, sd, c * cd);
     s = fmaf(c, sd, s * cd);
     c = cn;
@@ -264,7 +301,7 @@ __device__ __forceinline__ void integrate_hull2(float2& N, float2& E, float2& ps
   sincos_heading(psi.y, s.y, c.y);
   float2 sN = splat2(0.f), sE = splat2(0.f), sr = splat2(0.f);
   const float2 kvr = splat2(k.k_vr), nkur = splat2(-k.k_ur), nkuv = splat2(-k.k_uv);
-  const float2 c2 = splat2(k.rot_c2), s1 = splat2(k.rot_s1), s3 = splat2(k.rot_s3), one = splat2(1.0f);
+  const float2 c2 = splat2(k.rot_c2), s1 = splat2(k.rot_s1), one = splat2(1.0f);
 #pragma unroll 5
   for (int i = 0; i < n_sub; ++i) {
     const float2 vr = __fmul2_rn(v, r), ur = __fmul2_rn(u, r), uv = __fmul2_rn(u, v);
@@ -279,7 +316,7 @@ __device__ __forceinline__ void integrate_hull2(float2& N, float2& E, float2& ps
     sr = __fadd2_rn(sr, r);
     const float2 r2 = __fmul2_rn(r, r);
     const float2 cd = __ffma2_rn(c2, r2, one);
-    const float2 sd = __fmul2_rn(r, __ffma2_rn(s3, r2, s1));
+    const float2 sd = __fmul2_rn(r, s1);
     const float2 cn = __ffma2_rn(neg2(s), sd, __fmul2_rn(c, cd));
     s = __ffma2_rn(c, sd, __fmul2_rn(s, cd));
     c = cn;

@@ -434,15 +434,14 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
           int sat[5];
 #pragma unroll
           for (int a = 0; a < 7; ++a) a7[a] = pi[a];
-          transform_action<ML4CA_ENV_FINAL, true>(a7, cmd, sat);
+          float sp, cp, ss, cs;
+          transform_action_final_cont(a7, cmd, sat, sp, cp, ss, cs);
           float a_port = ep.angles[ep.n + env], a_star = ep.angles[2 * ep.n + env];
           const float pa_port = a_port, pa_star = a_star;
           a_port = cmd[3], a_star = cmd[4];
           int32_t epl = ep.ep_len[env];
           if (ep.n_sub > 0) {
-            float sp, cp, ss, cs, tx, ty, tn;
-            unit_from_pair(a7[3], a7[4], sp, cp);
-            unit_from_pair(a7[5], a7[6], ss, cs);
+            float tx, ty, tn;
             thruster_wrench_sc(cmd[0], cmd[1], cmd[2], 1.f, 0.f, sp, cp, ss, cs, tx, ty, tn);
             integrate_hull(eN, eE, ePsi, eu, ev, er, tx, ty, tn, ep.n_sub, ep.hull);
           }
