@@ -35,7 +35,7 @@ if not os.environ.get("ML4CA_KEEP_NCCL_DEBUG"):
     os.environ["NCCL_DEBUG"] = "WARN"
 
 ENV_STEP_BYTES = 177      # read 60 state + 28 action, write 48 state + 36 obs + 4 rew + 1 done
-ENV_STEP_TRAFFIC = 3.0087e9  # measured DRAM bytes of one 16 Mi-env launch (profiles/env_step_r1.md); algorithmic: 2.9696e9
+ENV_STEP_TRAFFIC = 2.9137e9  # measured DRAM bytes of one 16 Mi-env launch (profiles/env_step_r1.md, capture prof_env_r1h); algorithmic: 2.9696e9
 PINV_PID_BYTES = 80       # read eta, nu, ref, integ (48) + write integ, n, alpha (32)
 QP_BYTES = 68             # read tau 3 + prev 5 words, write x 8 + status 1
 POLICY_BYTES = 72         # read obs 36, write action 28 + value 4 + logp 4

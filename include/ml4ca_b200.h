@@ -53,7 +53,9 @@ typedef struct ml4ca_env_cfg {
   int32_t max_ep_len;     /* 400 at 5 Hz (customEnv.py:83) */
   int32_t auto_reset;     /* 0: reference semantics (caller resets).  1: an env whose done != 0 is re-sampled inside
                              step and the returned obs is the first obs of its next episode */
-  int32_t reserved0, reserved1;
+  int32_t reset_acts;     /* Revolt(reset_acts=True), customEnv.py:179-188: every reset draws the previous thrust
+                             as scale_and_clip(N(0, 0.1)^3) instead of [0, 0, 0] (:190); default 0 */
+  int32_t reserved1;
   float ss_bounds[6];     /* termination bounds real_ss_bounds (customEnv.py:26,337,361,386) */
   float sim_dt;           /* 0.01 s */
   float step_dt;          /* dt used by the action-derivative penalty = 0.01 * 20 (customEnv.py:81,311,317) */

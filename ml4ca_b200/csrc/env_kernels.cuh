@@ -43,7 +43,7 @@ struct EnvParams {
   float inv_step_dt, pad1;
   HullConsts hull;
   int32_t n_sub, max_ep_len;
-  int32_t auto_reset, pad0;
+  int32_t auto_reset, reset_acts;  // reset_acts: customEnv.py:179-188
   uint64_t seed;
   int64_t env_off;
   // one launch may cover a slice [first, first + count) of the batch (host-buffer pipeline, env_step.cu): the state
@@ -271,12 +271,14 @@ __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : (VEC ==
       if (flags[j] == 0u) continue;
       sample_reset(p.seed, p.env_off + i0 + j, ep[j], p.reset_scale, eta[0][j], eta[1][j], eta[2][j], nu[0][j],
                    nu[1][j], nu[2][j]);
-      ep[j] = next_episode_word(ep[j]);
       ang[0][j] = T::DEF_BOW, ang[1][j] = T::DEF_PORT, ang[2][j] = T::DEF_STAR;
-      pth[0][j] = pth[1][j] = pth[2][j] = 0.f;
+      float t0[3] = {0.f, 0.f, 0.f};                                   // customEnv.py:190
+      if (p.reset_acts) sample_reset_thrust(p.seed, p.env_off + i0 + j, ep[j], t0);   // :179-188 (old episode word)
+      ep[j] = next_episode_word(ep[j]);
+      pth[0][j] = t0[0], pth[1][j] = t0[1], pth[2][j] = t0[2];
       error_frame(eta[0][j], eta[1][j], eta[2][j], ref[0][j], ref[1][j], ref[2][j], o[0][j], o[1][j], o[2][j]);
       o[3][j] = nu[0][j], o[4][j] = nu[1][j], o[5][j] = nu[2][j];
-      if constexpr (EXT) o[6][j] = o[7][j] = o[8][j] = 0.f;
+      if constexpr (EXT) o[6][j] = div100(t0[0]), o[7][j] = div100(t0[1]), o[8][j] = div100(t0[2]);
     }
   }
 
@@ -318,16 +320,18 @@ __global__ void __launch_bounds__(256) env_reset_kernel(const EnvParams p, const
   }
   p.eta[i] = N, p.eta[n + i] = E, p.eta[2 * n + i] = psi;
   p.nu[i] = u, p.nu[n + i] = v, p.nu[2 * n + i] = r;
-  p.prev_thrust[i] = 0.f, p.prev_thrust[n + i] = 0.f, p.prev_thrust[2 * n + i] = 0.f;  // customEnv.py:190
+  float t0[3] = {0.f, 0.f, 0.f};                                                       // customEnv.py:190
+  if (p.reset_acts) sample_reset_thrust(p.seed, p.env_off + i, epi, t0);               // :179-188
+  p.prev_thrust[i] = t0[0], p.prev_thrust[n + i] = t0[1], p.prev_thrust[2 * n + i] = t0[2];
   p.angles[i] = T::DEF_BOW, p.angles[n + i] = T::DEF_PORT, p.angles[2 * n + i] = T::DEF_STAR;  // :173-177,192
-  p.obs_tail[i] = 0.f, p.obs_tail[n + i] = 0.f, p.obs_tail[2 * n + i] = 0.f;
+  p.obs_tail[i] = div100(t0[0]), p.obs_tail[n + i] = div100(t0[1]), p.obs_tail[2 * n + i] = div100(t0[2]);
   p.ep_len[i] = next_episode_word(epi);
   if (obs != nullptr) {
     float xb, yb, pb;
     error_frame(N, E, psi, p.ref[i], p.ref[n + i], p.ref[2 * n + i], xb, yb, pb);
     obs[i] = xb, obs[n + i] = yb, obs[2 * n + i] = pb;
     obs[3 * n + i] = u, obs[4 * n + i] = v, obs[5 * n + i] = r;
-    if constexpr (EXT) obs[6 * n + i] = 0.f, obs[7 * n + i] = 0.f, obs[8 * n + i] = 0.f;
+    if constexpr (EXT) obs[6 * n + i] = div100(t0[0]), obs[7 * n + i] = div100(t0[1]), obs[8 * n + i] = div100(t0[2]);
   }
 }
 

@@ -408,4 +408,22 @@ __device__ __forceinline__ void sample_reset(uint64_t seed, int64_t env_id, int3
   r = __fmul_rn(scale[5], symmetric_unit21(((q.z >> 21) | (q.w >> 21 << 11)) & 0x1FFFFFu));
 }
 
+// customEnv.py:179-188 (reset_acts=True): prev_thrust <- scale_and_clip([N(0, 0.1)]^3) = clip(100 * (0.1 z), +-100);
+// the thrust commands themselves only reach the simulator after the settle steps and are overwritten by the next
+// step's action, so the previous-thrust state (observation tail + first derivative penalty) is the whole effect.
+// Second Philox block of the restart (counter word 3 = 1), Box-Muller on (x, y) and (z, w).  Rare path: kept out
+// of line so that logf / sincospif do not enter the step kernel's register budget.
+static __device__ __noinline__ void sample_reset_thrust(uint64_t seed, int64_t env_id, int32_t episode, float* __restrict__ t) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ 0x5EED5EEDu;
+  const uint32_t lo = (uint32_t)((uint64_t)env_id), hi = (uint32_t)((uint64_t)env_id >> 32);
+  const Philox4 q = philox4x32_10(lo, hi, (uint32_t)episode, 1u, k0, k1);
+  const float r0 = sqrtf(-2.0f * logf(unit_open(q.x))), r1 = sqrtf(-2.0f * logf(unit_open(q.z)));
+  float s0, c0, s1, c1;
+  sincospif((float)(q.y >> 8) * 1.1920928955078125e-07f, &s0, &c0);   // angle = 2 pi * (y >> 8) * 2^-24
+  sincospif((float)(q.w >> 8) * 1.1920928955078125e-07f, &s1, &c1);
+  const float z[3] = {r0 * c0, r0 * s0, r1 * c1};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) t[c] = fminf(fmaxf(__fmul_rn(__fmul_rn(0.1f, z[c]), 100.0f), -100.0f), 100.0f);
+}
+
 }  // namespace ml4ca

@@ -217,7 +217,7 @@ int ml4ca_env_create(const ml4ca_env_cfg* cfg, int64_t n_env, int32_t device, ml
   p.n_sub = cfg->n_substeps;
   p.max_ep_len = cfg->max_ep_len;
   p.auto_reset = cfg->auto_reset;
-  p.pad0 = 0;
+  p.reset_acts = cfg->reset_acts ? 1 : 0;
   p.seed = cfg->seed;
   p.env_off = cfg->env_id_offset;
   p.count = n_env;

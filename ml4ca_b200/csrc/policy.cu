@@ -457,9 +457,10 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
           float npt[3] = {thrust[0], thrust[1], thrust[2]};
           if (ep.auto_reset && flags != 0u) {
             sample_reset(ep.seed, ep.env_off + env, epl, ep.reset_scale, eN, eE, ePsi, eu, ev, er);
+            npt[0] = npt[1] = npt[2] = 0.f;
+            if (ep.reset_acts) sample_reset_thrust(ep.seed, ep.env_off + env, epl, npt);   // customEnv.py:179-188
             epl = next_episode_word(epl);
             a_port = T::DEF_PORT, a_star = T::DEF_STAR;
-            npt[0] = npt[1] = npt[2] = 0.f;
           }
           ep.eta[env] = eN, ep.eta[ep.n + env] = eE, ep.eta[2 * ep.n + env] = ePsi;
           ep.nu[env] = eu, ep.nu[ep.n + env] = ev, ep.nu[2 * ep.n + env] = er;
@@ -467,7 +468,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
           for (int c = 0; c < 3; ++c) {
             ep.prev_thrust[(int64_t)c * ep.n + env] = npt[c];
             // tail of the observation this step returns: previous thrust / 100 (0 after a re-sample, :190)
-            ep.obs_tail[(int64_t)c * ep.n + env] = (ep.auto_reset && flags != 0u) ? 0.f : div100(pth[c]);
+            ep.obs_tail[(int64_t)c * ep.n + env] = div100((ep.auto_reset && flags != 0u) ? npt[c] : pth[c]);
           }
           ep.angles[ep.n + env] = a_port, ep.angles[2 * ep.n + env] = a_star;
           ep.ep_len[env] = epl;

@@ -137,7 +137,6 @@ class Revolt(object):
                  cont_ang=False,
                  num_envs=1, device=None, seed=0, auto_reset=False, env_id_offset=0, reset_fraction=0.8):
         assert digitwin is not None, 'No digitwin was passed to Revolt environment'
-        assert not reset_acts, 'reset_acts (customEnv.py:179-188, default off) is not part of the hot path'
         self.dTwin = digitwin
         if not hasattr(self, 'name'):
             self.name = 'full'
@@ -171,6 +170,7 @@ class Revolt(object):
         cfg.n_substeps = 0 if digitwin.frozen else n_sub
         cfg.max_ep_len = self.max_ep_len
         cfg.auto_reset = int(bool(auto_reset))
+        cfg.reset_acts = int(bool(reset_acts))            # customEnv.py:179-188
         for i in range(6):
             cfg.ss_bounds[i] = float(np.float32(self.real_ss_bounds[i]))
         cfg.step_dt = float(np.float32(self.dt))

@@ -216,18 +216,34 @@ def sample_reset(spec, seed, env_ids, episodes, fraction=0.8):
     return vals[:3], vals[3:]
 
 
-def reset(spec, state, mask=None, seed=0, env_id_offset=0, fraction=0.8, eta=None, nu=None, dt=np.float64):
-    """customEnv.py:135-194 (training mode, reset_acts off).  Either explicit eta/nu (the
-    reference's ``**init``) or Philox sampling.  Increments the per-env episode counter."""
+def reset_thrust(z, dt=np.float64):
+    """customEnv.py:179-188: action[0:3] = N(0, 0.1) -> scale_and_clip -> prev_thrust.  ``z`` = standard normals [3, n]."""
+    z = np.asarray(z, dtype=dt)
+    return np.clip((dt(0.1) * z) * dt(100.0), -100.0, 100.0).astype(dt)
+
+
+def reset(spec, state, mask=None, seed=0, env_id_offset=0, fraction=0.8, eta=None, nu=None, dt=np.float64,
+          reset_acts=False, thrust_noise=None):
+    """customEnv.py:135-194 (training mode).  Either explicit eta/nu (the reference's ``**init``) or Philox
+    sampling.  ``reset_acts`` (:179-188): the previous thrust becomes scale_and_clip(N(0, 0.1)^3) instead of
+    [0, 0, 0] (:190); the thrust commands themselves are overwritten by the next step before the simulator
+    advances, so nothing else changes.  ``thrust_noise`` = explicit standard normals [3, n] (pinning against the
+    reference's np.random.normal draws); default = the Philox normals of the restart.
+    Increments the per-env episode counter."""
     n = state['ep_len'].shape[0]
     m = np.ones(n, dtype=bool) if mask is None else np.asarray(mask, dtype=bool)
+    ids = np.arange(n, dtype=np.int64) + int(env_id_offset)
+    word = episode_word(state)
     if eta is None:
-        ids = np.arange(n, dtype=np.int64) + int(env_id_offset)
-        e32, v32 = sample_reset(spec, seed, ids, episode_word(state), fraction)
+        e32, v32 = sample_reset(spec, seed, ids, word, fraction)
         eta, nu = e32.astype(dt), v32.astype(dt)
     state['eta'][:, m] = np.asarray(eta, dtype=dt)[:, m]
     state['nu'][:, m] = np.asarray(nu, dtype=dt)[:, m]
-    state['prev_thrust'][:, m] = 0
+    if reset_acts:
+        z = philox.reset_thrust_normals(seed, ids, word) if thrust_noise is None else np.asarray(thrust_noise)
+        state['prev_thrust'][:, m] = reset_thrust(z, dt)[:, m]
+    else:
+        state['prev_thrust'][:, m] = 0
     state['angles'][:, m] = np.asarray(spec.default_angles, dtype=dt)[:, None]
     state['ep_len'][m] = 0
     state['episode'][m] += 1

@@ -74,3 +74,23 @@ def reset_draws(seed, env_id, episode):
     v6 = (q[2] >> s(21)) | ((q[3] >> s(21)) << s(11))
     return np.stack([symmetric_unit21(q[0]), symmetric_unit21(q[1]), symmetric_unit21(q[2]),
                      symmetric_unit21(q[3]), symmetric_unit21(v5), symmetric_unit21(v6)])
+
+
+def reset_thrust_normals(seed, env_id, episode):
+    """The three standard normals of a ``reset_acts`` restart (customEnv.py:181): SECOND Philox block of the
+    (env, episode word), counter (env_lo, env_hi, word, 1); Box-Muller on (out0, out1) -> z0 = r cos, z1 = r sin and
+    on (out2, out3) -> z2 = r cos, with r = sqrt(-2 ln unit_open(a)), angle = 2 pi (b >> 8) 2^-24.
+    Same uniforms as csrc/env_math.cuh::sample_reset_thrust; evaluated in float64 here (the kernel's logf / sincospif
+    are fp32, so agreement is ~1e-6 relative, not bit-level).  Returns float64 [3, n]."""
+    env_id = np.asarray(env_id, dtype=np.uint64)
+    episode = np.asarray(episode, dtype=np.uint64)
+    k0 = int(seed) & 0xFFFFFFFF
+    k1 = ((int(seed) >> 32) & 0xFFFFFFFF) ^ 0x5EED5EED
+    lo = env_id & _MASK
+    hi = env_id >> np.uint64(32)
+    q = philox4x32(lo, hi, episode & _MASK, np.ones_like(lo), k0, k1)
+    r0 = np.sqrt(-2.0 * np.log(unit_open(q[0]).astype(np.float64)))
+    r1 = np.sqrt(-2.0 * np.log(unit_open(q[2]).astype(np.float64)))
+    a0 = 2.0 * np.pi * (q[1] >> np.uint32(8)).astype(np.float64) * 2.0 ** -24
+    a1 = 2.0 * np.pi * (q[3] >> np.uint32(8)).astype(np.float64) * 2.0 ** -24
+    return np.stack([r0 * np.cos(a0), r0 * np.sin(a0), r1 * np.cos(a1)])

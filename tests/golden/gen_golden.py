@@ -15,6 +15,8 @@ qp_config1.npz        : reference QPTA.solve_QP + tau_controller_callback_func p
 policy_*.npz          : the shipped TF1 checkpoints' actor/critic weights, read by ml4ca_b200/tf_checkpoint.py
 ros_adapter.npz       : the deployment node RLTA (src/rl/ROS/rl_allocator/src/rl_allocator.py) driven message by message
                         with a stub actor: state vector, ROS-order action, published message fields.
+resetacts_final.npz   : RevoltFinal(reset_acts=True): reset observation with the N(0, 0.1) previous thrust
+                        (customEnv.py:179-188) and the first steps after it.
 gae.npz               : reference core.discount_cumsum formulation (scipy.signal.lfilter) and the
                         TrajectoryBuffer.finish_path arithmetic (ppo.py:82-91).
 """
@@ -178,8 +180,50 @@ def gen_ros_adapter(K=96, seed=21):
     return out
 
 
+def gen_reset_acts(B=64, T=3, seed=31):
+    """RevoltFinal(reset_acts=True) itself (customEnv.py:179-188): the np.random.normal draws of each reset are
+    reproduced beforehand from the same global seed (with explicit **init the reset draws nothing else), then the
+    reference is reset and stepped.  Records the standard normals, the reset observation and T steps."""
+    mod = ref_loader.load_env_module()
+    rng = np.random.default_rng(seed)
+    rec = {k: [] for k in ('eta0', 'nu0', 'z', 'obs0', 'actions', 'obs', 'rew')}
+    for b in range(B):
+        twin = vessel.VesselTwin(frozen=False)
+        env = mod.RevoltFinal(twin, extended_state=True, cont_ang=True, reset_acts=True)
+        eta0 = rng.uniform(-1, 1, 3) * np.array([6.0, 6.0, 0.6])
+        nu0 = rng.uniform(-1, 1, 3) * np.array([0.3, 0.07, 0.12])
+        init = {'Hull.PosNED': [eta0[0], eta0[1]], 'Hull.PosAttitude': [0, 0, eta0[2]],
+                'Hull.VelocityNu': [nu0[0], nu0[1], 0, 0, 0, nu0[2]]}
+        np.random.seed(1000 + b)
+        draws = np.random.normal(loc=0.0, scale=0.1, size=3)
+        np.random.seed(1000 + b)
+        real_normal = np.random.normal
+        if b % 16 == 5:                          # a few draws beyond the clip (|100 * draw| > 100): inflate x120
+            np.random.normal = lambda loc=0.0, scale=1.0, size=None: real_normal(loc=loc, scale=scale, size=size) * 120.0
+            draws = draws * 120.0
+        try:
+            o0 = env.reset(**init)
+        finally:
+            np.random.normal = real_normal
+        acts, obs, rew = [], [], []
+        for t in range(T):
+            a = rng.uniform(-1.1, 1.1, env.num_actions)
+            o, r, d, _ = env.step(a)
+            acts.append(a); obs.append(np.array(o, dtype=np.float64)); rew.append(float(np.asarray(r).ravel()[0]))
+        rec['eta0'].append(eta0); rec['nu0'].append(nu0); rec['z'].append(draws / 0.1)
+        rec['obs0'].append(np.array(o0, dtype=np.float64)); rec['actions'].append(acts); rec['obs'].append(obs)
+        rec['rew'].append(rew)
+    return {'eta0': np.array(rec['eta0']).T, 'nu0': np.array(rec['nu0']).T, 'z': np.array(rec['z']).T,
+            'obs0': np.array(rec['obs0']).T, 'actions': np.transpose(np.array(rec['actions']), (1, 2, 0)),
+            'obs': np.transpose(np.array(rec['obs']), (1, 2, 0)), 'rew': np.array(rec['rew']).T}
+
+
 def main():
     assert ref_loader.available(), "reference checkout not found"
+    if "--only-reset-acts" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, 'resetacts_final.npz'), **gen_reset_acts())
+        print('wrote resetacts_final.npz')
+        return
     if "--only-ros" in sys.argv:
         np.savez_compressed(os.path.join(HERE, 'ros_adapter.npz'), **gen_ros_adapter())
         print('wrote ros_adapter.npz')
@@ -204,6 +248,8 @@ def main():
     out = gen_qp(256, seed=0)
     np.savez_compressed(os.path.join(HERE, 'qp_config1.npz'), **out)
     print('wrote qp_config1.npz  success rate %.3f' % out['success'].mean())
+    np.savez_compressed(os.path.join(HERE, 'resetacts_final.npz'), **gen_reset_acts())
+    print('wrote resetacts_final.npz')
     np.savez_compressed(os.path.join(HERE, 'gae.npz'), **gen_gae(7))
     print('wrote gae.npz')
     gen_policy()

@@ -181,6 +181,53 @@ def test_auto_reset_and_episode_cut(cuda_device):
     assert episodes.min() >= 3      # every env was cut at least twice in 45 steps of 20-step episodes
 
 
+def test_reset_acts(cuda_device):
+    """Revolt(reset_acts=True), customEnv.py:179-188: previous thrust of every reset = clip(100 * N(0, 0.1), +-100),
+    drawn from the restart's second Philox block; explicit reset, in-kernel restart and the step after it."""
+    from oracle import philox
+    n, seed = 1 << 15, 77
+    spec = EO.EnvSpec('final', True, True, max_ep_len=12)      # 12 * 10 / 20 = 6-step episodes
+    env = make_env('final', True, True, n, seed=seed, auto_reset=True, max_ep_len=12, reset_acts=True)
+    obs = env.reset(fraction=0.8).cpu().numpy()
+    ids = np.arange(n)
+    t_ref = EO.reset_thrust(philox.reset_thrust_normals(seed, ids, np.zeros(n, dtype=np.int64)))
+    st = env.get_state()
+    np.testing.assert_allclose(st['prev_thrust'].cpu().numpy(), t_ref, rtol=0, atol=2e-4)
+    np.testing.assert_allclose(obs[6:9], t_ref / 100.0, rtol=0, atol=2e-6)
+    assert abs(float(t_ref.std()) - 10.0) < 0.1 and abs(float(t_ref.mean())) < 0.1
+    # the step after the reset against the float64 oracle started from the kernel's state
+    so = EO.new_state(spec, n)
+    so['eta'], so['nu'] = st['eta'].cpu().numpy().astype(np.float64), st['nu'].cpu().numpy().astype(np.float64)
+    so['prev_thrust'] = st['prev_thrust'].cpu().numpy().astype(np.float64)
+    so['angles'] = st['angles'].cpu().numpy().astype(np.float64)
+    rng = np.random.default_rng(5)
+    a = rng.uniform(-1, 1, (7, n)).astype(np.float32)
+    o, r, d, info = env.step(torch.as_tensor(a, device=cuda_device))
+    o64, r64, d64, _ = EO.step(spec, so, a.astype(np.float64))
+    alive = info['flags'].cpu().numpy() == 0
+    np.testing.assert_allclose(o.cpu().numpy()[:, alive], o64[:, alive], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(r.cpu().numpy().reshape(n)[alive], r64[alive], rtol=0, atol=1e-4)
+    # in-kernel restarts: run to the episode cut; restarted envs carry the normals of (env, episode word at the cut)
+    episodes = np.ones(n, dtype=np.int64)
+    prev_len = env.get_state()['ep_len'].cpu().numpy().astype(np.int64)
+    ended0 = ~alive
+    episodes[ended0] += 1
+    seen = 0
+    for t in range(8):
+        o, r, d, info = env.step(torch.as_tensor(rng.uniform(-1, 1, (7, n)).astype(np.float32), device=cuda_device))
+        ended = info['flags'].cpu().numpy() != 0
+        stt = env.get_state()
+        if ended.any():
+            word = (episodes << 16) | (prev_len + 1)
+            tr = EO.reset_thrust(philox.reset_thrust_normals(seed, ids, word))
+            np.testing.assert_allclose(stt['prev_thrust'].cpu().numpy()[:, ended], tr[:, ended], rtol=0, atol=2e-4)
+            np.testing.assert_allclose(o.cpu().numpy()[6:9, ended], tr[:, ended] / 100.0, rtol=0, atol=2e-6)
+            episodes[ended] += 1
+            seen += int(ended.sum())
+        prev_len = stt['ep_len'].cpu().numpy().astype(np.int64)
+    assert seen >= n
+
+
 def test_full_size_properties(cuda_device):
     """BASELINE config 3 scale (16 Mi envs, one step): size-independent invariants of the path."""
     n = 1 << 24

@@ -81,6 +81,33 @@ def test_reset_sampling_distribution():
     np.testing.assert_array_equal(e2, eta[:, 1000:2000])
 
 
+def test_reset_acts_oracle_matches_reference():
+    """RevoltFinal(reset_acts=True), customEnv.py:179-188: the reference's reset observation and the first steps
+    after it, given the reference's own normal draws (a few inflated beyond the clip)."""
+    g = golden("resetacts_final.npz")
+    spec = EO.EnvSpec('final', True, True)
+    B = g['eta0'].shape[1]
+    st = EO.new_state(spec, B)
+    obs0 = EO.reset(spec, st, eta=g['eta0'], nu=g['nu0'], reset_acts=True, thrust_noise=g['z'])
+    np.testing.assert_allclose(obs0, g['obs0'], rtol=0, atol=1e-12)
+    assert (np.abs(obs0[6:9]) == 1.0).any() and (np.abs(obs0[6:9]) <= 1.0).all()      # clipped draws are present
+    for t in range(g['actions'].shape[0]):
+        o, r, d, _ = EO.step(spec, st, g['actions'][t])
+        np.testing.assert_allclose(o, g['obs'][t], rtol=0, atol=1e-11)
+        np.testing.assert_allclose(r, g['rew'][t], rtol=0, atol=1e-11)
+
+
+def test_reset_thrust_normals_distribution():
+    """Box-Muller on the second Philox block of a restart: standard normal, independent components."""
+    z = philox.reset_thrust_normals(3, np.arange(200000), np.zeros(200000, dtype=np.int64))
+    assert np.all(np.abs(z.mean(axis=1)) < 0.01) and np.all(np.abs(z.std(axis=1) - 1.0) < 0.01)
+    assert np.all(np.abs(np.corrcoef(z) - np.eye(3)) < 0.01)
+    assert abs((np.abs(z) > 1.959964).mean() - 0.05) < 0.002
+    # different block from the pose draws of the same restart
+    u = philox.reset_draws(3, np.arange(200000), np.zeros(200000, dtype=np.int64))
+    assert np.all(np.abs(np.corrcoef(np.vstack([z, u]))[:3, 3:]) < 0.01)
+
+
 def test_qp_oracle_reproduces_reference_solver():
     g = golden("qp_config1.npz")
     import scipy

@@ -101,8 +101,8 @@ def test_unsupported_shapes_fail_loudly(cuda_device):
         M.ActorCritic(9, 7, (64, 80), device=cuda_device)
 
 
-@pytest.mark.parametrize("fused", [False, True])
-def test_rollout_matches_stepwise_reference_semantics(cuda_device, fused):
+@pytest.mark.parametrize("fused,reset_acts", [(False, False), (True, False), (True, True)])
+def test_rollout_matches_stepwise_reference_semantics(cuda_device, fused, reset_acts):
     """T steps of rollout() == the reference loop `a = pi(o); o, r, d = env.step(a)` (ppo.py:290-302) driven
     step by step through the separate policy / env kernels, including the stale-thrust tail of the observation
     the agent acts on and in-kernel restarts of finished episodes."""
@@ -112,7 +112,7 @@ def test_rollout_matches_stepwise_reference_semantics(cuda_device, fused):
     ac = M.ActorCritic(9, 7, (64, 64), "leaky_relu", params=MO.glorot_params(dims, seed=3), device=cuda_device, seed=21)
     n, T = 20000, 12
     mk = lambda: RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=n, device=cuda_device, seed=9,
-                             auto_reset=True, max_ep_len=16)          # 16 * 10 / 20 = 8-step episodes
+                             auto_reset=True, max_ep_len=16, reset_acts=reset_acts)   # 16 * 10 / 20 = 8-step episodes
     envA, envB = mk(), mk()
     o = envA.reset()
     envB.reset()
