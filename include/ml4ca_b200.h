@@ -235,6 +235,18 @@ ML4CA_API int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T,
  * the largest component).  enable = 1 selects the fp32 CUDA-core kernel (1e-5), 0 the tensor-core one, -1 only
  * queries; returns the previous setting.  Initial value: environment variable ML4CA_PPO_FP32. */
 ML4CA_API int ml4ca_ppo_use_fp32(int enable);
+/* ---- TRPO / NPG pieces (spinup/algos/tf1/trpo/trpo.py:236-247,264-303; trpo/core.py:52-60,88-100) -----------------------------
+ * The surrogate pi_loss = -mean(ratio adv) and its flat gradient (trpo.py:237,244) are ml4ca_ppo_grad with net 0 and a
+ * clip_ratio large enough never to bind (1e30).  The two passes below always run the fp32 CUDA-core kernel.
+ * ml4ca_trpo_policy_mu: the distribution "info" the reference's GAEBuffer stores per step (trpo.py:300): mu [T, act_dim, n]
+ * of obs [T, obs_dim, n] at the current parameters (log_std is state-independent: the caller copies it from the parameters). */
+ML4CA_API int ml4ca_trpo_policy_mu(ml4ca_policy* p, int64_t n, int32_t T, const float* obs, float* mu, void* stream);
+/* d_kl = mean KL(pi_theta || pi_old) (core.diagonal_gaussian_kl as mlp_gaussian_policy calls it, trpo/core.py:52-60,98) over
+ * the buffer, and its flat gradient w.r.t. the pi variables and log_std: grad (SUM convention, like ml4ca_ppo_grad; v block
+ * zero), stats[2] = sum of per-sample KL, stats[5] = sample count.  mu_old [T, act_dim, n], log_std_old [act_dim] (device).
+ * The Hessian-vector product of trpo/core.py:68-72 is a central difference of this gradient (host side, ml4ca_b200/trpo.py). */
+ML4CA_API int ml4ca_trpo_kl_grad(ml4ca_policy* p, int64_t n, int32_t T, const float* obs, const float* mu_old,
+                                 const float* log_std_old, float* grad, double* stats, void* stream);
 /* tf.train.AdamOptimizer step (beta1 0.9, beta2 0.999, eps 1e-8 in the reference) on m parameters:
  * g = grad * grad_scale; m1, m2 moment buffers; t = 1-based step count of this optimizer. */
 ML4CA_API int ml4ca_adam_step(int64_t m, float* params, const float* grad, float* m1, float* m2, float lr, float beta1,

@@ -82,6 +82,9 @@ _SIGNATURES = {
     "ml4ca_ppo_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_f32p,
                                       c_f32p, c_f32p, ctypes.c_float, c_f32p, ctypes.c_void_p, c_stream]),
     "ml4ca_ppo_use_fp32": (ctypes.c_int, [ctypes.c_int]),
+    "ml4ca_trpo_policy_mu": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_stream]),
+    "ml4ca_trpo_kl_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_f32p, c_f32p,
+                                          ctypes.c_void_p, c_stream]),
     "ml4ca_adam_step": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_float, ctypes.c_float, ctypes.c_int32, ctypes.c_float, c_stream]),
     "ml4ca_last_error": (ctypes.c_char_p, []),

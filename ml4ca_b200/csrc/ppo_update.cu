@@ -49,6 +49,12 @@ struct Args {
   const float* logp_old;   // [T, n]         (pi)
   const float* ret;        // [T, n]         (v)
   float clip;
+  // TRPO (spinup/algos/tf1/trpo): loss_mode 1 = d_kl = mean KL(pi_theta || pi_old) (trpo/core.py:52-60,98) in place of the PPO
+  // surrogate: act_buf then carries mu_old [T, act, n] and kl_ls_old the old log_std [act]; adv / logp_old unused.
+  // mu_out [T, act, n] (nullable): forward only, the means of every sample are stored and no gradient is computed.
+  int loss_mode;
+  const float* kl_ls_old;
+  float* mu_out;
   float* grad;             // flat, same layout as params; this net's block is accumulated into (caller zeroes)
   double* stats;           // [8]: 0 sum pi objective, 1 sum (ret - v)^2, 2 sum 0.5 (logp_old - logp)^2, 3 sum -logp,
                            //      4 clipped count, 5 sample count
@@ -62,6 +68,7 @@ struct Smem {
   float wotp[OP][H];    // wotp[o][4 tx + b] = Wo[tx + 16 b][o]
   float b1[H], b2[H], bo[OP];
   float sd[OP], inv[OP], ls[OP];   // exp(log_std), 1 / (exp(log_std) + 1e-8), log_std
+  float kiv[OP], kls[OP];          // KL mode: 1 / (exp(2 log_std_old) + 1e-8), log_std_old
   float x0[XR][RS];
   float h1[H][RS];
   float h2[H][RS];
@@ -133,6 +140,8 @@ __global__ void __launch_bounds__(256, 1) ppo_grad_kernel(const Args A) {
     const float ls = (NET == 0 && tid < nout) ? A.params[A.off_ls + tid] : 0.f;
     const float sd = expf(ls);
     S.ls[tid] = ls, S.sd[tid] = sd, S.inv[tid] = 1.0f / (sd + 1e-8f);
+    const float lo = (NET == 0 && A.loss_mode == 1 && tid < nout) ? A.kl_ls_old[tid] : 0.f;
+    S.kls[tid] = lo, S.kiv[tid] = 1.0f / (expf(2.0f * lo) + 1e-8f);               // trpo/core.py:57-58
   }
   // zero the padding rows / columns once
   for (int e = tid; e < XR * RS; e += 256) (&S.x0[0][0])[e] = 0.f;
@@ -167,13 +176,14 @@ __global__ void __launch_bounds__(256, 1) ppo_grad_kernel(const Args A) {
       const int idx = tid + 256 * m, row = idx >> 7, col = idx & 127;
       float v = 0.f;
       if (row < rows_in && i0 + col < n) {
-        const float* src;
-        if (row < obs) src = A.obs_buf + ((int64_t)t * obs + row) * n;
-        else if (NET == 1) src = A.ret + (int64_t)t * n;
-        else if (row < obs + A.act) src = A.act_buf + ((int64_t)t * A.act + (row - obs)) * n;
-        else if (row == obs + A.act) src = A.adv + (int64_t)t * n;
-        else src = A.logp_old + (int64_t)t * n;
-        v = __ldg(src + i0 + col);
+        const float* base;     // rows a mode does not use have a NULL base and read as zero
+        int64_t off;
+        if (row < obs) base = A.obs_buf, off = ((int64_t)t * obs + row) * n;
+        else if (NET == 1) base = A.ret, off = (int64_t)t * n;
+        else if (row < obs + A.act) base = A.act_buf, off = ((int64_t)t * A.act + (row - obs)) * n;
+        else if (row == obs + A.act) base = A.adv, off = (int64_t)t * n;
+        else base = A.logp_old, off = (int64_t)t * n;
+        if (base != nullptr) v = __ldg(base + off + i0 + col);
       }
       pre[m] = v;
     }
@@ -245,11 +255,35 @@ __global__ void __launch_bounds__(256, 1) ppo_grad_kernel(const Args A) {
       for (int q = 0; q < 4; ++q) S.out[4 * half + q][s] = o4[q];
     }
     __syncthreads();
+    if (A.mu_out != nullptr) {   // forward only (uniform branch): store the means, next tile
+      if (tid < TS && tid < valid) {
+        const int64_t t = tile / tiles_per_t;
+        for (int a = 0; a < nout; ++a) A.mu_out[((int64_t)t * nout + a) * n + i0 + tid] = S.out[a][tid];
+      }
+      __syncthreads();           // the next tile overwrites x0 / out
+      continue;
+    }
     // ---- 4. loss and dOUT (sum convention), one thread per sample -------------------------------------------------------
     if (tid < TS) {
       const int s = tid;
       const bool live = s < valid;
-      if constexpr (NET == 0) {
+      if (NET == 0 && A.loss_mode == 1) {
+        // d_kl = mean_s sum_a 0.5 (((mu_old - mu)^2 + var) / (var_old + EPS) - 1) + log_std_old - log_std   (trpo/core.py:52-60
+        // with mu0 = the current policy, mu1 = the old one, as mlp_gaussian_policy calls it, :98)
+        double kl = 0.0;
+#pragma unroll
+        for (int a = 0; a < OP; ++a) {
+          if (a < nout) {
+            const float d = S.out[a][s] - S.actb[a][s], var = S.sd[a] * S.sd[a];
+            kl += (double)(0.5f * ((d * d + var) * S.kiv[a] - 1.0f) + (S.kls[a] - S.ls[a]));
+            S.out[a][s] = live ? d * S.kiv[a] : 0.f;                               // d kl / d mu
+            dls_a[a] += live ? (var * S.kiv[a] - 1.0f) : 0.f;                      // d kl / d log_std
+          } else {
+            S.out[a][s] = 0.f;
+          }
+        }
+        if (live) st[2] += kl;
+      } else if constexpr (NET == 0) {
         float logp = 0.f, z[OP], dmu[OP];
 #pragma unroll
         for (int a = 0; a < OP; ++a) {
@@ -397,6 +431,7 @@ __global__ void __launch_bounds__(256, 1) ppo_grad_kernel(const Args A) {
     __syncthreads();   // the next tile overwrites x0 / actb / aux
   }
 
+  if (A.mu_out != nullptr) return;   // forward-only pass (uniform)
   // ---- flush: one atomicAdd per accumulator and CTA ------------------------------------------------------------------------------
   float* g = A.grad;
 #pragma unroll
@@ -478,21 +513,19 @@ extern "C" int ml4ca_policy_describe(const ml4ca_policy* p, ml4ca_policy_cfg* cf
 
 extern "C" {
 
-int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const float* obs, const float* act, const float* adv,
-                   const float* ret, const float* logp_old, float clip_ratio, float* grad, double* stats, void* stream) {
-  ML4CA_REQUIRE(p != nullptr && grad != nullptr && stats != nullptr && obs != nullptr, "policy, obs, grad and stats are required");
-  ML4CA_REQUIRE(net == 0 || net == 1, "net: 0 = pi, 1 = v");
+// Offsets of one network's variables in the flat parameter vector + the checks shared by every pass of this file.
+static int ppo_args(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const char* who, ppo::Args* out, ml4ca_policy_cfg* cfg_out,
+                    int32_t* device_out) {
+  ML4CA_REQUIRE(p != nullptr, "policy is NULL");
   ML4CA_REQUIRE(n >= 0 && T >= 0, "bad sizes");
   ml4ca_policy_cfg cfg;
   int32_t device = 0;
   int rc = ml4ca_policy_describe(p, &cfg, &device);
   if (rc != ML4CA_OK) return rc;
   if (!(cfg.hidden == 64 && cfg.n_hidden == 2 && cfg.obs_dim <= ppo::XR)) {
-    set_error("ml4ca_ppo_grad: the training kernel is built for the 64 x 64 networks of the BASELINE config");
+    set_error("%s: the training kernels are built for the 64 x 64 networks of the BASELINE config", who);
     return ML4CA_ERR_UNSUPPORTED;
   }
-  if (net == 0) ML4CA_REQUIRE(act && adv && logp_old, "pi pass needs act, adv and logp_old");
-  else ML4CA_REQUIRE(ret != nullptr, "v pass needs ret");
   const int H = ppo::H, O = cfg.obs_dim, Ad = cfg.act_dim;
   const int pi_size = O * H + H + H * H + H + H * Ad + Ad;
   ppo::Args a = {};
@@ -503,6 +536,41 @@ int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const flo
   a.off_bo = a.off_wo + H * a.nout;
   a.off_ls = pi_size;
   a.n = n, a.T = T;
+  *out = a, *cfg_out = cfg, *device_out = device;
+  return ML4CA_OK;
+}
+
+static int ppo_launch_fp32(const ppo::Args& a, int activation, int net, cudaStream_t st) {
+  const int64_t tiles = ((a.n + ppo::TS - 1) / ppo::TS) * a.T;
+  if (tiles == 0) return ML4CA_OK;
+  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  const size_t smem = sizeof(ppo::Smem);
+#define ML4CA_PPO_LAUNCH(ACTV, NETV)                                                                             \
+  do {                                                                                                           \
+    auto k = ppo::ppo_grad_kernel<ACTV, NETV>;                                                                   \
+    ML4CA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+    k<<<grid, 256, smem, st>>>(a);                                                                               \
+  } while (0)
+  if (activation == 1) {
+    if (net == 0) ML4CA_PPO_LAUNCH(1, 0); else ML4CA_PPO_LAUNCH(1, 1);
+  } else {
+    if (net == 0) ML4CA_PPO_LAUNCH(0, 0); else ML4CA_PPO_LAUNCH(0, 1);
+  }
+#undef ML4CA_PPO_LAUNCH
+  return check_launch("ppo_grad_kernel");
+}
+
+int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const float* obs, const float* act, const float* adv,
+                   const float* ret, const float* logp_old, float clip_ratio, float* grad, double* stats, void* stream) {
+  ML4CA_REQUIRE(p != nullptr && grad != nullptr && stats != nullptr && obs != nullptr, "policy, obs, grad and stats are required");
+  ML4CA_REQUIRE(net == 0 || net == 1, "net: 0 = pi, 1 = v");
+  if (net == 0) ML4CA_REQUIRE(act && adv && logp_old, "pi pass needs act, adv and logp_old");
+  else ML4CA_REQUIRE(ret != nullptr, "v pass needs ret");
+  ppo::Args a;
+  ml4ca_policy_cfg cfg;
+  int32_t device = 0;
+  int rc = ppo_args(p, net, n, T, "ml4ca_ppo_grad", &a, &cfg, &device);
+  if (rc != ML4CA_OK) return rc;
   a.obs_buf = obs, a.act_buf = act, a.adv = adv, a.logp_old = logp_old, a.ret = ret;
   a.clip = clip_ratio;
   a.grad = grad, a.stats = stats;
@@ -512,7 +580,7 @@ int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const flo
   const int64_t tiles = ((n + ppo::TS - 1) / ppo::TS) * T;
   if (tiles == 0) return ML4CA_OK;
   // Default: the tcgen05 kernel (fp16 operands, fp32 TMEM accumulation).  ML4CA_PPO_FP32=1 selects the fp32
-  // CUDA-core kernel below (gradients to 1e-5 instead of 1e-3).
+  // CUDA-core kernel (gradients to 1e-5 instead of 1e-3).
   if (!g_use_fp32) {
     static __half* blob[64] = {};       // per-device scratch for the packed operands (kept for the life of the process)
     ML4CA_REQUIRE(device >= 0 && device < 64, "device index out of range");
@@ -526,21 +594,34 @@ int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const flo
     t.clip = clip_ratio, t.grad = grad, t.stats = stats;
     return ml4ca_ppo_grad_tc_launch(t, cfg.activation, net, blob[device], st);
   }
-  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  const size_t smem = sizeof(ppo::Smem);
-#define ML4CA_PPO_LAUNCH(ACTV, NETV)                                                                             \
-  do {                                                                                                           \
-    auto k = ppo::ppo_grad_kernel<ACTV, NETV>;                                                                   \
-    ML4CA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-    k<<<grid, 256, smem, st>>>(a);                                                                               \
-  } while (0)
-  if (cfg.activation == 1) {
-    if (net == 0) ML4CA_PPO_LAUNCH(1, 0); else ML4CA_PPO_LAUNCH(1, 1);
-  } else {
-    if (net == 0) ML4CA_PPO_LAUNCH(0, 0); else ML4CA_PPO_LAUNCH(0, 1);
-  }
-#undef ML4CA_PPO_LAUNCH
-  return check_launch("ppo_grad_kernel");
+  return ppo_launch_fp32(a, cfg.activation, net, st);
+}
+
+int ml4ca_trpo_policy_mu(ml4ca_policy* p, int64_t n, int32_t T, const float* obs, float* mu, void* stream) {
+  ML4CA_REQUIRE(obs != nullptr && mu != nullptr, "obs and mu are required");
+  ppo::Args a;
+  ml4ca_policy_cfg cfg;
+  int32_t device = 0;
+  int rc = ppo_args(p, 0, n, T, "ml4ca_trpo_policy_mu", &a, &cfg, &device);
+  if (rc != ML4CA_OK) return rc;
+  a.obs_buf = obs, a.mu_out = mu;
+  return ppo_launch_fp32(a, cfg.activation, 0, static_cast<cudaStream_t>(stream));
+}
+
+int ml4ca_trpo_kl_grad(ml4ca_policy* p, int64_t n, int32_t T, const float* obs, const float* mu_old, const float* log_std_old,
+                       float* grad, double* stats, void* stream) {
+  ML4CA_REQUIRE(obs && mu_old && log_std_old && grad && stats, "obs, mu_old, log_std_old, grad and stats are required");
+  ppo::Args a;
+  ml4ca_policy_cfg cfg;
+  int32_t device = 0;
+  int rc = ppo_args(p, 0, n, T, "ml4ca_trpo_kl_grad", &a, &cfg, &device);
+  if (rc != ML4CA_OK) return rc;
+  a.obs_buf = obs, a.act_buf = mu_old, a.kl_ls_old = log_std_old, a.loss_mode = 1;
+  a.grad = grad, a.stats = stats;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ML4CA_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)ml4ca_policy_num_params(&cfg), st));
+  ML4CA_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 8, st));
+  return ppo_launch_fp32(a, cfg.activation, 0, st);
 }
 
 int ml4ca_adam_step(int64_t m, float* params, const float* grad, float* m1, float* m2, float lr, float beta1, float beta2,

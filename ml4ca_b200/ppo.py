@@ -147,6 +147,14 @@ class PPOUpdater(object):
         out["LossV"] = s[1] / c
         return out
 
+    def _update_v(self, data, T, n, info):
+        """ppo.py:272-273 / trpo.py:323-325: train_v_iters Adam steps on v_loss."""
+        for i in range(self.train_v_iters):
+            s, c = self._grad(1, data, T, n)
+            if i == 0:
+                info["LossV"] = s[1] / c
+            self._adam(1, c)
+
     def update(self, buf):
         """ppo.py:260-280.  ``buf`` = a TrajectoryBuffer after finish_path(); returns the logger's dictionary."""
         data = buf.get()
@@ -161,15 +169,14 @@ class PPOUpdater(object):
             if s[2] / c > 1.5 * self.target_kl:       # kl = mpi_avg(kl), :268-271 (the step of this iteration is applied)
                 break
         info["StopIter"] = stop
-        for i in range(self.train_v_iters):
-            s, c = self._grad(1, data, T, n)
-            if i == 0:
-                info["LossV"] = s[1] / c
-            self._adam(1, c)
+        self._update_v(data, T, n, info)
         new = self.losses(data, T, n)
         info.update(KL=new["KL"], ClipFrac=new["ClipFrac"], DeltaLossPi=new["LossPi"] - info.get("LossPi", new["LossPi"]),
                     DeltaLossV=new["LossV"] - info.get("LossV", new["LossV"]))
         return info
+
+
+PPO_COLUMNS = ('LossPi', 'LossV', 'DeltaLossPi', 'DeltaLossV', 'Entropy', 'KL', 'ClipFrac', 'StopIter')   # ppo.py:339-346
 
 
 def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2, pi_lr=3e-4, vf_lr=1e-3,
@@ -191,12 +198,24 @@ def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2,
     ac.refresh()
     buf = TrajectoryBuffer(env.num_states, env.num_actions, steps_per_epoch, n, gamma, lam, device=dev)
     upd = PPOUpdater(ac, clip_ratio, pi_lr, vf_lr, train_pi_iters, train_v_iters, target_kl)
+    config = dict(steps_per_epoch=steps_per_epoch, epochs=epochs, gamma=gamma, clip_ratio=clip_ratio, pi_lr=pi_lr,
+                  vf_lr=vf_lr, train_pi_iters=train_pi_iters, train_v_iters=train_v_iters, lam=lam,
+                  target_kl=target_kl, seed=seed)
+    return run_epochs(env, ac, buf, upd, steps_per_epoch, epochs, seed, fused, logger, logger_kwargs, config, PPO_COLUMNS,
+                      log_std_column=True)
+
+
+def run_epochs(env, ac, buf, upd, steps_per_epoch, epochs, seed, fused, logger, logger_kwargs, config, columns,
+               log_std_column=False):
+    """The epoch loop shared by ppo() (ppo.py:283-346) and trpo() (trpo.py:327-384): rollout of every environment,
+    bootstrap + GAE-lambda, episode / value statistics, ``upd.update(buf)``, the reference's progress.txt columns."""
+    import time as _time
+    from . import logx, mpi_tools
+    n, dev = env.num_envs, env.device
     flog = None
     if logger_kwargs is not None:
         flog = logx.Logger(rank=mpi_tools.proc_id(), **logger_kwargs)
-        flog.save_config(dict(steps_per_epoch=steps_per_epoch, epochs=epochs, gamma=gamma, clip_ratio=clip_ratio, pi_lr=pi_lr,
-                              vf_lr=vf_lr, train_pi_iters=train_pi_iters, train_v_iters=train_v_iters, lam=lam,
-                              target_kl=target_kl, seed=seed, max_ep_len=env.max_ep_len, num_envs=n,
+        flog.save_config(dict(config, max_ep_len=env.max_ep_len, num_envs=n,
                               num_procs=mpi_tools.num_procs(), actor_critic="mlp_actor_critic",
                               ac_kwargs=dict(hidden_sizes=list(ac.hidden_sizes), activation=ac.activation)))
     run_ret = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -238,11 +257,12 @@ def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2,
             flog.log_stats('EpLen', red[1], average_only=True)
             flog.log_stats('VVals', red[2], with_min_and_max=True)
             flog.log_tabular('TotalEnvInteracts', info['TotalEnvInteracts'])
-            for k in ('LossPi', 'LossV', 'DeltaLossPi', 'DeltaLossV', 'Entropy', 'KL', 'ClipFrac', 'StopIter'):
+            for k in columns:
                 flog.log_tabular(k, info[k])
             flog.log_tabular('Time', _time.time() - start_time)
-            off = ac.var_counts[0] - ac.act_dim
-            flog.log_tabular('MeanLogStd', float(ac.parameters()[off:off + ac.act_dim].mean().item()))
+            if log_std_column:
+                off = ac.var_counts[0] - ac.act_dim
+                flog.log_tabular('MeanLogStd', float(ac.parameters()[off:off + ac.act_dim].mean().item()))
             flog.dump_tabular()
         if logger is not None:
             logger(info)
