@@ -192,7 +192,9 @@ struct RolloutOut {   // trajectory slice of one time step (any pointer may be N
 // FUSE = true : one fused rollout step of RevoltFinal(extended_state, cont_ang): observation from the env state in
 //               HBM -> policy -> sampled action -> env step (env_math.cuh) -> new state, reward, done; the observation
 //               and the action never round-trip through HBM except as trajectory records.
-template <int H, int NL, int ACTIVATION, bool FUSE>
+//               S97 = the 9 -> 7 network of RevoltFinal(extended_state, cont_ang) with both dims known at compile time (no
+//               predicated row loads / stores); other shapes take the generic instantiation.
+template <int H, int NL, int ACTIVATION, bool FUSE, bool S97>
 __global__ void __launch_bounds__(PolicyGroups<H>::THREADS, 1)
 policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, uint64_t seed, uint32_t step,
               int deterministic, int64_t env_off, float* __restrict__ act_out, float* __restrict__ val_out,
@@ -201,6 +203,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
   constexpr int G = PolicyGroups<H>::G;
   extern __shared__ __align__(128) uint8_t smem[];
   const PolicyDims d = pp.d;
+  const int OBS = S97 ? 9 : d.obs, ACT = S97 ? 7 : d.act;
   constexpr int KP = H + 16;
   const PolicySmem L(d, G);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -222,7 +225,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
     }
     if (threadIdx.x < 8) {
       const int a = threadIdx.x;
-      const float ls = (a < d.act) ? pp.params[pp.log_std_off + a] : 0.f;
+      const float ls = (a < ACT) ? pp.params[pp.log_std_off + a] : 0.f;
       const float sd = expf(ls);
       consts[a] = sd;
       consts[8 + a] = sd / (sd + 1e-8f);                       // (pi - mu) / (exp(log_std) + EPS) per unit eps
@@ -336,12 +339,12 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) o[c] = (c < d.obs && live) ? __ldg(obs + (int64_t)c * n + env) : 0.f;
+        for (int c = 0; c < 16; ++c) o[c] = (c < OBS && live) ? __ldg(obs + (int64_t)c * n + env) : 0.f;
       }
       {
 #pragma unroll
         for (int c = 0; c < 16; ++c)
-          if (c == d.obs) o[c] = 1.0f;                 // constant-1 column: carries the layer-1 biases
+          if (c == OBS) o[c] = 1.0f;                   // constant-1 column: carries the layer-1 biases
         uint32_t w[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) w[c] = pack_f16x2(o[2 * c], o[2 * c + 1]);
@@ -408,7 +411,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
 #pragma unroll
         for (int a = 0; a < kMaxAct; ++a) {
           pi[a] = 0.f;
-          if (a < d.act) {
+          if (a < ACT) {
             pi[a] = fmaf(eps[a], consts[a], out[a]);                             // mu + eps * exp(log_std), core.py:85
             const float zn = eps[a] * consts[8 + a];                             // (pi - mu) / (std + 1e-8), core.py:45
             logp += -0.5f * fmaf(zn, zn, consts[16 + a]);
@@ -417,11 +420,11 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
         float vv = out[0];   // the value head is column act_dim of the output chain
 #pragma unroll
         for (int a = 1; a < 16; ++a)
-          if (a == d.act) vv = out[a];
+          if (a == ACT) vv = out[a];
         if constexpr (!FUSE) {
 #pragma unroll
           for (int a = 0; a < kMaxAct; ++a)
-            if (a < d.act) {
+            if (a < ACT) {
               act_out[(int64_t)a * n + env] = pi[a];
               if (mu_out != nullptr) mu_out[(int64_t)a * n + env] = out[a];
             }
@@ -515,15 +518,21 @@ static int launch_policy(const ml4ca_policy* p, const PolicyParams& pp, int64_t 
   const int64_t tiles = (n + 127) / 128;
   const int64_t want = (tiles + G - 1) / G;
   const int grid = (int)(want < p->num_sms ? want : p->num_sms);
-  if (p->d.activation == 1) {
-    auto k = policy_kernel<H, NL, 1, FUSE>;
-    ML4CA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    k<<<grid, PolicyGroups<H>::THREADS, L.total, st>>>(pp, n, obs, seed, step, det, env_off, act, val, logp, mu, ep, ro);
+  const bool s97 = p->d.obs == 9 && p->d.act == 7;
+#define ML4CA_POLICY_LAUNCH(ACTV, S97V)                                                                                   \
+  do {                                                                                                                    \
+    auto k = policy_kernel<H, NL, ACTV, FUSE, S97V>;                                                                      \
+    ML4CA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));                            \
+    k<<<grid, PolicyGroups<H>::THREADS, L.total, st>>>(pp, n, obs, seed, step, det, env_off, act, val, logp, mu, ep, ro); \
+  } while (0)
+  if constexpr (FUSE) {            // the fused rollout only exists for the 9 -> 7 network (checked by the caller)
+    if (p->d.activation == 1) ML4CA_POLICY_LAUNCH(1, true); else ML4CA_POLICY_LAUNCH(0, true);
+  } else if (s97) {
+    if (p->d.activation == 1) ML4CA_POLICY_LAUNCH(1, true); else ML4CA_POLICY_LAUNCH(0, true);
   } else {
-    auto k = policy_kernel<H, NL, 0, FUSE>;
-    ML4CA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    k<<<grid, PolicyGroups<H>::THREADS, L.total, st>>>(pp, n, obs, seed, step, det, env_off, act, val, logp, mu, ep, ro);
+    if (p->d.activation == 1) ML4CA_POLICY_LAUNCH(1, false); else ML4CA_POLICY_LAUNCH(0, false);
   }
+#undef ML4CA_POLICY_LAUNCH
   return check_launch("policy_kernel");
 }
 
