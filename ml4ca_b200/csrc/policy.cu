@@ -33,6 +33,16 @@
 
 namespace ml4ca {
 
+#ifdef ML4CA_POLICY_TRACE   // tuning builds only: per-group stage timestamps of CTA 0 (tools/policy_trace.py)
+__device__ long long g_policy_trace[4 * 64 * 8];
+#define ML4CA_TRACE(slot)                                                                              \
+  do {                                                                                                 \
+    if (blockIdx.x == 0 && row == 0 && r < 64) g_policy_trace[(g * 64 + (int)r) * 8 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define ML4CA_TRACE(slot) do { } while (0)
+#endif
+
 constexpr int kMaxAct = 8;
 
 struct PolicyDims {
@@ -206,7 +216,10 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
   const int OBS = S97 ? 9 : d.obs, ACT = S97 ? 7 : d.act;
   constexpr int KP = H + 16;
   const PolicySmem L(d, G);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it (group,
+  // operand addresses, MMA descriptors) in uniform registers -- tcgen05.mma takes its operands from there without a
+  // per-thread waterfall loop
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);  // [g] a_ready, [4 + g] d_ready
   float* consts = reinterpret_cast<float*>(smem + L.consts);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
@@ -271,13 +284,16 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
     const uint32_t b1 = sb + L.blob;
     const uint32_t bh0 = b1 + d.b1_elems() * 2;
     const uint32_t bo = bh0 + (NL - 1) * 2 * d.bh_elems() * 2;
+    const uint32_t grp_stride = (G > 1) ? (uint32_t)(L.a0[1] - L.a0[0]) : 0u;   // operand buffers of the groups are equally spaced
+    auto a0_off = [&](int g) { return (uint32_t)L.a0[0] + (uint32_t)g * grp_stride; };
+    auto act_off = [&](int g) { return (uint32_t)L.act[0] + (uint32_t)g * grp_stride; };
     auto issue_chain = [&](int g, int s) {   // one elected thread
       const uint32_t dt = tmem_base + g * PolicyGroups<H>::TMEM_STRIDE;
       if (s == 0) {
-        mma_f16(dt, smem_desc(sb + L.a0[g], 128, 16 * 16), smem_desc(b1, 128, 16 * 16), idesc_l1, false);
+        mma_f16(dt, smem_desc(sb + a0_off(g), 128, 16 * 16), smem_desc(b1, 128, 16 * 16), idesc_l1, false);
       } else if (s < NL) {
         for (int net = 0; net < 2; ++net) {
-          const uint32_t a = sb + L.act[g] + net * (KP / 8) * 128;
+          const uint32_t a = sb + act_off(g) + net * (KP / 8) * 128;
           const uint32_t b = bh0 + ((s - 1) * 2 + net) * d.bh_elems() * 2;
 #pragma unroll
           for (int ks = 0; ks < KP / 16; ++ks)
@@ -285,7 +301,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
                     idesc_h, ks > 0);
         }
       } else {
-        const uint32_t a = sb + L.act[g];
+        const uint32_t a = sb + act_off(g);
 #pragma unroll
         for (int ks = 0; ks < 2 * KP / 16; ++ks)
           mma_f16(dt, smem_desc(a + ks * 256, 128, 2 * KP * 16), smem_desc(bo + ks * 256, 128, 2 * KP * 16), idesc_o,
@@ -297,18 +313,22 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
     auto hand_over = [&](int g, int row, int s) {
       fence_async_smem();
       asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-      if (row == 0) {
-        fence_after_sync();
-        issue_chain(g, s);
+      if ((warp & 3) == 0) {             // warp-uniform branch: first warp of the group ...
+        if (elect_one()) {               // ... one elected lane issues
+          fence_after_sync();
+          issue_chain(g, s);
+        }
+        __syncwarp();
       }
     };
     const int g = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + g * PolicyGroups<H>::TMEM_STRIDE;
-    __half* a0 = reinterpret_cast<__half*>(smem + L.a0[g]);
-    uint8_t* actb = smem + L.act[g];
+    __half* a0 = reinterpret_cast<__half*>(smem + a0_off(g));
+    uint8_t* actb = smem + act_off(g);
     uint32_t dphase = 0;
     for (int64_t r = 0; r < rounds; ++r) {
+      ML4CA_TRACE(0);
       const int64_t tile = r * tiles_per_round + (int64_t)blockIdx.x * G + g;
       const int64_t env = tile * 128 + row;
       const bool live = env < n;
@@ -351,10 +371,12 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
         *reinterpret_cast<uint4*>(a0 + canon_off(row, 0, 16)) = make_uint4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<uint4*>(a0 + canon_off(row, 8, 16)) = make_uint4(w[4], w[5], w[6], w[7]);
       }
+      ML4CA_TRACE(1);
       hand_over(g, row, 0);
       // ---- hidden layers: TMEM -> activation -> fp16 operand rows (TMEM loads prefetched one chunk ahead) -------
       for (int s = 0; s < NL; ++s) {
         mbar_wait(&bars[4 + g], dphase);
+        ML4CA_TRACE(2 + 2 * s);
         dphase ^= 1;
         fence_after_sync();
         uint32_t bufA[16], bufB[16];
@@ -383,10 +405,12 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
           if (c0 + 32 < 2 * H) wait_ld();
         }
         fence_before_sync();
+        ML4CA_TRACE(3 + 2 * s);
         hand_over(g, row, s + 1);
       }
       // ---- output layer: mu, v -> sample, log-likelihood (-> env step) ---------------------------------------------
       mbar_wait(&bars[4 + g], dphase);
+      ML4CA_TRACE(6);
       dphase ^= 1;
       fence_after_sync();
       float out[16];
@@ -485,6 +509,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
           if (ro.done != nullptr) ro.done[env] = (uint8_t)flags;
         }
       }
+      ML4CA_TRACE(7);
     }
   }
   __syncthreads();
@@ -616,6 +641,12 @@ int ml4ca_policy_describe(const ml4ca_policy* p, ml4ca_policy_cfg* cfg, int32_t*
   if (device) *device = p->device;
   return ML4CA_OK;
 }
+
+#ifdef ML4CA_POLICY_TRACE
+__attribute__((visibility("default"))) int ml4ca_debug_policy_trace(long long* host) {
+  return cudaMemcpyFromSymbol(host, ml4ca::g_policy_trace, sizeof(long long) * 4 * 64 * 8) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int ml4ca_policy_refresh(ml4ca_policy* p, void* stream) {
   ML4CA_REQUIRE(p != nullptr, "policy is NULL");

@@ -147,6 +147,18 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// One lane of a converged warp (elect.sync): the elected lane's code sees warp-uniform operands.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // All previously issued MMAs of this thread arrive on the mbarrier when they have completed.
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
