@@ -327,6 +327,10 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
     __half* a0 = reinterpret_cast<__half*>(smem + a0_off(g));
     uint8_t* actb = smem + act_off(g);
     uint32_t dphase = 0;
+    constexpr int kPre = FUSE ? 1 : (S97 ? 9 : 12);   // observation rows fetched one tile ahead (wider inputs load the rest in place)
+    float onext[kPre];
+#pragma unroll
+    for (int c = 0; c < kPre; ++c) onext[c] = 0.f;
     for (int64_t r = 0; r < rounds; ++r) {
       ML4CA_TRACE(0);
       const int64_t tile = r * tiles_per_round + (int64_t)blockIdx.x * G + g;
@@ -358,8 +362,13 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
           }
         }
       } else {
+        // rows of this tile were requested during the previous tile (below, after its first hand-over), so their HBM
+        // latency is off the chain; only the first round loads in place
 #pragma unroll
-        for (int c = 0; c < 16; ++c) o[c] = (c < OBS && live) ? __ldg(obs + (int64_t)c * n + env) : 0.f;
+        for (int c = 0; c < 16; ++c) {
+          if (c < kPre) o[c] = (r == 0) ? ((c < OBS && live) ? __ldg(obs + (int64_t)c * n + env) : 0.f) : onext[c];
+          else o[c] = (c < OBS && live) ? __ldg(obs + (int64_t)c * n + env) : 0.f;
+        }
       }
       {
 #pragma unroll
@@ -373,6 +382,13 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
       }
       ML4CA_TRACE(1);
       hand_over(g, row, 0);
+      if constexpr (!FUSE) {
+        // next tile's observation rows: issued AFTER the hand-over (its MEMBAR would otherwise wait for these loads)
+        const int64_t env2 = env + tiles_per_round * 128;
+        const bool live2 = (r + 1 < rounds) && env2 < n;
+#pragma unroll
+        for (int c = 0; c < kPre; ++c) onext[c] = (c < OBS && live2) ? __ldg(obs + (int64_t)c * n + env2) : 0.f;
+      }
       // ---- hidden layers: TMEM -> activation -> fp16 operand rows (TMEM loads prefetched one chunk ahead) -------
       for (int s = 0; s < NL; ++s) {
         mbar_wait(&bars[4 + g], dphase);
