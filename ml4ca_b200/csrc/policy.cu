@@ -34,10 +34,10 @@
 namespace ml4ca {
 
 #ifdef ML4CA_POLICY_TRACE   // tuning builds only: per-group stage timestamps of CTA 0 (tools/policy_trace.py)
-__device__ long long g_policy_trace[4 * 64 * 8];
+__device__ long long g_policy_trace[4 * 64 * 16];
 #define ML4CA_TRACE(slot)                                                                              \
   do {                                                                                                 \
-    if (blockIdx.x == 0 && row == 0 && r < 64) g_policy_trace[(g * 64 + (int)r) * 8 + (slot)] = clock64(); \
+    if (blockIdx.x == 0 && row == 0 && r < 64) g_policy_trace[(g * 64 + (int)r) * 16 + (slot)] = clock64(); \
   } while (0)
 #else
 #define ML4CA_TRACE(slot) do { } while (0)
@@ -256,7 +256,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
   if (threadIdx.x == 0) {
     for (int g = 0; g < G; ++g) {
       mbar_init(&bars[g], 128);
-      mbar_init(&bars[4 + g], 1);
+      mbar_init(&bars[4 + g], 2);   // the two issuing warps of a group commit their halves of a chain
     }
     fence_barrier_init();
   }
@@ -287,36 +287,58 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
     const uint32_t grp_stride = (G > 1) ? (uint32_t)(L.a0[1] - L.a0[0]) : 0u;   // operand buffers of the groups are equally spaced
     auto a0_off = [&](int g) { return (uint32_t)L.a0[0] + (uint32_t)g * grp_stride; };
     auto act_off = [&](int g) { return (uint32_t)L.act[0] + (uint32_t)g * grp_stride; };
-    auto issue_chain = [&](int g, int s) {   // one elected thread
+    int64_t trace_r = 0; (void)trace_r;
+    auto issue_chain = [&](int g, int s, int part) {   // one elected lane of warp `part` (0, 1) of the group
       const uint32_t dt = tmem_base + g * PolicyGroups<H>::TMEM_STRIDE;
       if (s == 0) {
-        mma_f16(dt, smem_desc(sb + a0_off(g), 128, 16 * 16), smem_desc(b1, 128, 16 * 16), idesc_l1, false);
+        if (part == 0) mma_f16(dt, smem_desc(sb + a0_off(g), 128, 16 * 16), smem_desc(b1, 128, 16 * 16), idesc_l1, false);
       } else if (s < NL) {
-        for (int net = 0; net < 2; ++net) {
-          const uint32_t a = sb + act_off(g) + net * (KP / 8) * 128;
-          const uint32_t b = bh0 + ((s - 1) * 2 + net) * d.bh_elems() * 2;
+        // the two nets are independent accumulation chains: each is issued by its own warp (MMAs of one issuing thread run
+        // strictly one after the other, ~120 cycles each for these small operands; two issuers overlap)
+        const int net = part;
+        const uint32_t a = sb + act_off(g) + net * (KP / 8) * 128;
+        const uint32_t b = bh0 + ((s - 1) * 2 + net) * d.bh_elems() * 2;
 #pragma unroll
-          for (int ks = 0; ks < KP / 16; ++ks)
-            mma_f16(dt + net * H, smem_desc(a + ks * 256, 128, 2 * KP * 16), smem_desc(b + ks * 256, 128, KP * 16),
-                    idesc_h, ks > 0);
-        }
+        for (int ks = 0; ks < KP / 16; ++ks)
+          mma_f16(dt + net * H, smem_desc(a + ks * 256, 128, 2 * KP * 16), smem_desc(b + ks * 256, 128, KP * 16), idesc_h,
+                  ks > 0);
       } else {
+        // output layer: mu only sees the pi activations (K steps 0 .. KP/16 - 1), v only the v activations (the rest):
+        // two independent chains into two accumulators (columns 0-15: mu, 16-31: v in column ACT), one per issuing warp
         const uint32_t a = sb + act_off(g);
 #pragma unroll
-        for (int ks = 0; ks < 2 * KP / 16; ++ks)
-          mma_f16(dt, smem_desc(a + ks * 256, 128, 2 * KP * 16), smem_desc(bo + ks * 256, 128, 2 * KP * 16), idesc_o,
-                  ks > 0);
+        for (int j = 0; j < KP / 16; ++j) {
+          const int ks = part * (KP / 16) + j;
+          mma_f16(dt + 16 * part, smem_desc(a + ks * 256, 128, 2 * KP * 16), smem_desc(bo + ks * 256, 128, 2 * KP * 16),
+                  idesc_o, j > 0);
+        }
       }
+#ifdef ML4CA_POLICY_TRACE
+      if (s == NL && blockIdx.x == 0 && part == 0 && trace_r < 64) g_policy_trace[(g * 64 + (int)trace_r) * 16 + 14] = clock64();
+#endif
       mma_commit(&bars[4 + g]);
     };
     // operand rows of this group are complete and visible to the async proxy -> start MMA chain s
     auto hand_over = [&](int g, int row, int s) {
       fence_async_smem();
+#ifdef ML4CA_POLICY_TRACE
+      if (s == NL && blockIdx.x == 0 && row == 0 && trace_r < 64) g_policy_trace[(g * 64 + (int)trace_r) * 16 + 11] = clock64();
+#endif
       asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-      if ((warp & 3) == 0) {             // warp-uniform branch: first warp of the group ...
-        if (elect_one()) {               // ... one elected lane issues
+#ifdef ML4CA_POLICY_TRACE
+      if (s == NL && blockIdx.x == 0 && row == 0 && trace_r < 64) g_policy_trace[(g * 64 + (int)trace_r) * 16 + 12] = clock64();
+#endif
+      if ((warp & 3) < 2) {              // warp-uniform branch: the first two warps of the group ...
+        if (elect_one()) {               // ... one elected lane of each issues its half
+#ifdef ML4CA_POLICY_TRACE
+          const bool tr = s == NL && blockIdx.x == 0 && (warp & 3) == 0 && trace_r < 64;
+          if (tr) g_policy_trace[(g * 64 + (int)trace_r) * 16 + 13] = clock64();
+#endif
           fence_after_sync();
-          issue_chain(g, s);
+          issue_chain(g, s, warp & 3);
+#ifdef ML4CA_POLICY_TRACE
+          if (tr) g_policy_trace[(g * 64 + (int)trace_r) * 16 + 15] = clock64();
+#endif
         }
         __syncwarp();
       }
@@ -332,6 +354,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
 #pragma unroll
     for (int c = 0; c < kPre; ++c) onext[c] = 0.f;
     for (int64_t r = 0; r < rounds; ++r) {
+      trace_r = r;
       ML4CA_TRACE(0);
       const int64_t tile = r * tiles_per_round + (int64_t)blockIdx.x * G + g;
       const int64_t env = tile * 128 + row;
@@ -423,44 +446,59 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
         fence_before_sync();
         ML4CA_TRACE(3 + 2 * s);
         hand_over(g, row, s + 1);
+        ML4CA_TRACE(8 + s);
       }
       // ---- output layer: mu, v -> sample, log-likelihood (-> env step) ---------------------------------------------
+      // The noise and the log-likelihood depend on neither network (logp_pi is a function of eps and log_std only): they
+      // are drawn while the output chain runs on the tensor core, before the wait.
+      float eps[kMaxAct];
+      float logp = 0.f;
+#pragma unroll
+      for (int a = 0; a < kMaxAct; ++a) eps[a] = 0.f;
+      if (live && !deterministic) {
+        const uint64_t gid = (uint64_t)(env + env_off);
+        const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ 0xAC710Au;
+        const Philox4 pa = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), step, 0u, k0, k1);
+        const Philox4 pb = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), step, 1u, k0, k1);
+        normal_pair(pa.x, pa.y, eps[0], eps[1]);
+        normal_pair(pa.z, pa.w, eps[2], eps[3]);
+        normal_pair(pb.x, pb.y, eps[4], eps[5]);
+        normal_pair(pb.z, pb.w, eps[6], eps[7]);
+      }
+#pragma unroll
+      for (int a = 0; a < kMaxAct; ++a) {
+        if (a < ACT) {
+          const float zn = eps[a] * consts[8 + a];                               // (pi - mu) / (std + 1e-8), core.py:45
+          logp += -0.5f * fmaf(zn, zn, consts[16 + a]);
+        }
+        asm volatile("" : "+f"(eps[a]));                                         // keep the draw in front of the wait
+      }
+      asm volatile("" : "+f"(logp));
+      ML4CA_TRACE(10);
       mbar_wait(&bars[4 + g], dphase);
       ML4CA_TRACE(6);
       dphase ^= 1;
       fence_after_sync();
-      float out[16];
-      tmem_ld16(t_lane, out);
+      float out[16], vv = 0.f;
+      {
+        uint32_t r0[16], r1[16];
+        tmem_ld16_async(t_lane, r0);
+        tmem_ld16_async(t_lane + 16, r1);
+        wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          out[i] = __uint_as_float(r0[i]);
+          if (i == ACT) vv = __uint_as_float(r1[i]);     // the value head is output row act_dim, fed by the v chain
+        }
+      }
       fence_before_sync();
       if (live) {
-        float eps[kMaxAct];
-#pragma unroll
-        for (int a = 0; a < kMaxAct; ++a) eps[a] = 0.f;
-        if (!deterministic) {
-          const uint64_t gid = (uint64_t)(env + env_off);
-          const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ 0xAC710Au;
-          const Philox4 pa = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), step, 0u, k0, k1);
-          const Philox4 pb = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), step, 1u, k0, k1);
-          normal_pair(pa.x, pa.y, eps[0], eps[1]);
-          normal_pair(pa.z, pa.w, eps[2], eps[3]);
-          normal_pair(pb.x, pb.y, eps[4], eps[5]);
-          normal_pair(pb.z, pb.w, eps[6], eps[7]);
-        }
-        float logp = 0.f;
         float pi[kMaxAct];
 #pragma unroll
         for (int a = 0; a < kMaxAct; ++a) {
           pi[a] = 0.f;
-          if (a < ACT) {
-            pi[a] = fmaf(eps[a], consts[a], out[a]);                             // mu + eps * exp(log_std), core.py:85
-            const float zn = eps[a] * consts[8 + a];                             // (pi - mu) / (std + 1e-8), core.py:45
-            logp += -0.5f * fmaf(zn, zn, consts[16 + a]);
-          }
+          if (a < ACT) pi[a] = fmaf(eps[a], consts[a], out[a]);                  // mu + eps * exp(log_std), core.py:85
         }
-        float vv = out[0];   // the value head is column act_dim of the output chain
-#pragma unroll
-        for (int a = 1; a < 16; ++a)
-          if (a == ACT) vv = out[a];
         if constexpr (!FUSE) {
 #pragma unroll
           for (int a = 0; a < kMaxAct; ++a)
@@ -660,7 +698,7 @@ int ml4ca_policy_describe(const ml4ca_policy* p, ml4ca_policy_cfg* cfg, int32_t*
 
 #ifdef ML4CA_POLICY_TRACE
 __attribute__((visibility("default"))) int ml4ca_debug_policy_trace(long long* host) {
-  return cudaMemcpyFromSymbol(host, ml4ca::g_policy_trace, sizeof(long long) * 4 * 64 * 8) == cudaSuccess ? 0 : -2;
+  return cudaMemcpyFromSymbol(host, ml4ca::g_policy_trace, sizeof(long long) * 4 * 64 * 16) == cudaSuccess ? 0 : -2;
 }
 #endif
 

@@ -16,9 +16,9 @@ for i in range(3):
     ac.step(obs, out=out, step=i)
 torch.cuda.synchronize()
 L = ctypes.CDLL(os.environ["ML4CA_LIB"])
-buf = (ctypes.c_longlong * (4 * 64 * 8))()
+buf = (ctypes.c_longlong * (4 * 64 * 16))()
 assert L.ml4ca_debug_policy_trace(buf) == 0
-t = np.array(buf[:], dtype=np.int64).reshape(4, 64, 8)
+t = np.array(buf[:], dtype=np.int64).reshape(4, 64, 16)
 t0 = t[:, 0, 0].min()
 for r in list(range(0, 4)) + list(range(40, 46)):
     for g in range(4):
@@ -26,6 +26,11 @@ for r in list(range(0, 4)) + list(range(40, 46)):
         print("round %2d group %d  start %7d | stage %5d | L1 wait %5d | epi1 %5d | L2 wait %5d | epi2 %5d | out wait %5d | epi3 %5d | total %5d"
               % (r, g, rel[0], rel[1] - rel[0], rel[2] - rel[1], rel[3] - rel[2], rel[4] - rel[3], rel[5] - rel[4], rel[6] - rel[5],
                  rel[7] - rel[6], rel[7] - rel[0]))
-d = np.diff(t, axis=2)[:, 8:60]
+d = np.diff(t[:, :, :8], axis=2)[:, 8:60]
 print("mean per stage (rounds 8..59):", np.round(d.mean(axis=(0, 1))).astype(int), "tile total", int((t[:, 8:60, 7] - t[:, 8:60, 0]).mean()))
+m = lambda a, b: int((t[:, 8:60, a] - t[:, 8:60, b]).mean())
+print("hand-over 1 (fence + barrier + issue): %d, then wait %d | hand-over 2: %d, noise+logp %d, then wait %d"
+      % (m(8, 3), m(4, 8), m(9, 5), m(10, 9), m(6, 10)))
+print("hand-over 2 split: proxy fence %d | group barrier %d | elect + issue %d" % (m(11, 5), m(12, 11), m(9, 12)))
+print("  inside: barrier -> elected %d | fence + MMAs %d | commit %d | elected -> reconverged %d" % (m(13, 12), m(14, 13), m(15, 14), m(9, 15)))
 print("period per group (start to next start):", np.round(np.diff(t[:, 8:60, 0], axis=1).mean(axis=1)).astype(int))
