@@ -24,7 +24,8 @@
 //
 // Bias gradients fall out of the constant-1 columns (row H of dWo / dW2, column obs of dW1T).  Weight-gradient
 // accumulators stay in TMEM for all tiles of the CTA (persistent grid) and are flushed once.  Three tile groups of
-// 128 threads (thread = sample = TMEM lane) run out of phase; thread 0 of a group issues its MMAs.
+// 128 threads (thread = sample = TMEM lane) run out of phase; an elected lane of the first two warps of a group issues its
+// MMA chains (independent chains of a stage go to different issuers: one thread's MMAs run strictly one after the other).
 //
 // Numerics: fp16 operands (activations, weights, back-propagated signals x 64), fp32 accumulation: gradients agree
 // with the float64 oracle to ~1e-3 of the largest component (tests/test_ppo_update_gpu.py); the fp32 CUDA-core
@@ -129,7 +130,9 @@ __device__ __forceinline__ float2 act_grad2(uint32_t h2) {
 template <int ACTIVATION, int NET>
 __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: warp-uniform for the compiler, so the group index and every MMA descriptor derived from it
+  // live in uniform registers (tcgen05.mma then issues back to back, without a per-thread waterfall loop)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int g = warp >> 2, row = (warp & 3) * 32 + lane;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
   float* consts = reinterpret_cast<float*>(smem + OFF_CONST);
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
     a2[canon(row, H, KP)] = __float2half_rn(1.0f);
   }
   if (threadIdx.x == 0) {
-    for (int q = 0; q < G; ++q) mbar_init(&bars[q], 1);
+    for (int q = 0; q < G; ++q) mbar_init(&bars[q], 2);   // the two issuing warps of a group each commit their part of a stage
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -249,10 +252,15 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
       *reinterpret_cast<uint4*>(pA0 + canon(row, 8, 16)) = make_uint4(w[4], w[5], w[6], w[7]);
     }
     sync_group();
-    if (row == 0) {
-      fence_after_sync();
-      chain_k(tD, sA0, 16, sB1, 16, H, 1, false);                  // F1
-      mma_commit(&bars[g]);
+    if ((warp & 3) < 2) {                                          // warp-uniform: the two issuing warps of the group
+      if (elect_one()) {
+        fence_after_sync();
+        if ((warp & 3) == 0) {
+          chain_k(tD, sA0, 16, sB1, 16, H, 1, false);              // F1
+        }
+        mma_commit(&bars[g]);
+      }
+      __syncwarp();
     }
     // ---- hidden epilogues: D -> f -> operand rows -------------------------------------------------------------------------
     auto hidden = [&](uint8_t* dst) {
@@ -275,16 +283,26 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
       sync_group();
     };
     hidden(pA1);
-    if (row == 0) {
-      fence_after_sync();
-      chain_k(tD, sA1, KP, sB2, KP, H, KP / 16, false);            // F2
-      mma_commit(&bars[g]);
+    if ((warp & 3) < 2) {                                          // warp-uniform: the two issuing warps of the group
+      if (elect_one()) {
+        fence_after_sync();
+        if ((warp & 3) == 0) {
+          chain_k(tD, sA1, KP, sB2, KP, H, KP / 16, false);        // F2
+        }
+        mma_commit(&bars[g]);
+      }
+      __syncwarp();
     }
     hidden(pA2);
-    if (row == 0) {
-      fence_after_sync();
-      chain_k(tD, sA2, KP, sBo, KP, OP, KP / 16, false);           // F3
-      mma_commit(&bars[g]);
+    if ((warp & 3) < 2) {                                          // warp-uniform: the two issuing warps of the group
+      if (elect_one()) {
+        fence_after_sync();
+        if ((warp & 3) == 0) {
+          chain_k(tD, sA2, KP, sBo, KP, OP, KP / 16, false);       // F3
+        }
+        mma_commit(&bars[g]);
+      }
+      __syncwarp();
     }
     // ---- loss: per-sample dOUT (sum convention), scaled, -> G3 ---------------------------------------------------------------
     wait_mma();
@@ -334,11 +352,17 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
       *reinterpret_cast<uint4*>(pG3 + canon(row, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
     }
     sync_group();
-    if (row == 0) {
-      fence_after_sync();
-      chain_mn(tWo, sA2, KP, sG3, 16, OP, acc);                    // dWo += A2^T G3
-      chain_k(tD, sG3, 16, sWoT, 16, H, 1, false);                 // D = G3 WoT^T
-      mma_commit(&bars[g]);
+    if ((warp & 3) < 2) {                                          // warp-uniform: the two issuing warps of the group
+      if (elect_one()) {
+        fence_after_sync();
+        if ((warp & 3) == 0) {
+          chain_mn(tWo, sA2, KP, sG3, 16, OP, acc);                // dWo += A2^T G3
+        } else {
+          chain_k(tD, sG3, 16, sWoT, 16, H, 1, false);             // D = G3 WoT^T
+        }
+        mma_commit(&bars[g]);
+      }
+      __syncwarp();
     }
     // ---- backward epilogues: G = D .* f'(h) ------------------------------------------------------------------------------------
     auto backward = [&](const uint8_t* hsrc, uint8_t* dst) {
@@ -364,17 +388,28 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
       sync_group();
     };
     backward(pA2, pG2);
-    if (row == 0) {
-      fence_after_sync();
-      chain_mn(tW2, sA1, KP, sG2, H, H, acc);                      // dW2 += A1^T G2
-      chain_k(tD, sG2, H, sW2n, H, H, H / 16, false);              // D = G2 W2n^T
-      mma_commit(&bars[g]);
+    if ((warp & 3) < 2) {                                          // warp-uniform: the two issuing warps of the group
+      if (elect_one()) {
+        fence_after_sync();
+        if ((warp & 3) == 0) {
+          chain_mn(tW2, sA1, KP, sG2, H, H, acc);                  // dW2 += A1^T G2
+        } else {
+          chain_k(tD, sG2, H, sW2n, H, H, H / 16, false);          // D = G2 W2n^T
+        }
+        mma_commit(&bars[g]);
+      }
+      __syncwarp();
     }
     backward(pA1, pG1);                                            // G1 takes over the G2 buffer (its readers have completed)
-    if (row == 0) {
-      fence_after_sync();
-      chain_mn(tW1, sG1, H, sA0, 16, OP, acc);                     // dW1T += G1^T A0
-      mma_commit(&bars[g]);
+    if ((warp & 3) < 2) {                                          // warp-uniform: the two issuing warps of the group
+      if (elect_one()) {
+        fence_after_sync();
+        if ((warp & 3) == 0) {
+          chain_mn(tW1, sG1, H, sA0, 16, OP, acc);                 // dW1T += G1^T A0
+        }
+        mma_commit(&bars[g]);
+      }
+      __syncwarp();
     }
     acc = true;
     pending = true;                                                // waited for before A0 / G2 are written again
