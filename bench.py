@@ -473,6 +473,26 @@ def run_b200(args, rank, local_rank, world):
             del env3, ac3
         except Exception as e:  # noqa: BLE001
             extra["ppo_train"] = {"error": repr(e)}
+        # the same epoch with the TRPO update (train.py --algo trpo): CG on the Fisher-vector product + line search + 80 v steps
+        try:
+            ne, Tp = 1 << 14, 400
+            env4 = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=ne, device=dev, seed=7,
+                               auto_reset=True, env_id_offset=rank * ne)
+            ac4 = M.ActorCritic(9, 7, (64, 64), "leaky_relu", device=dev, seed=7)
+            M.trpo(env4, ac4, steps_per_epoch=Tp, epochs=1, seed=7)
+            barrier()
+            t0 = time.perf_counter()
+            _, hist = M.trpo(env4, ac4, steps_per_epoch=Tp, epochs=2, seed=8)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0) / 2
+            extra["trpo_train"] = {"workload": "TRPO epoch = 400-step rollout of 16 Ki envs/GPU + GAE + update (trpo.py defaults: "
+                                               "10 CG iterations on the damped Fisher-vector product, <= 10 backtracking steps, "
+                                               "80 v iterations), all-reduce of every flat gradient",
+                                   "value": ne * world * Tp / dt, "unit": "env-steps/s incl. update", "s_per_epoch": dt,
+                                   "last_epoch": {k: hist[-1][k] for k in ("KL", "BacktrackIters", "DeltaLossPi", "LossV")}}
+            del env4, ac4
+        except Exception as e:  # noqa: BLE001
+            extra["trpo_train"] = {"error": repr(e)}
 
     sampler.stop_flag.set()
     sampler.join(timeout=1.0)

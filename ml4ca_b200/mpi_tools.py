@@ -45,7 +45,12 @@ def shard_bounds(n_global, rank=None, world=None):
 def allreduce_sum_(t):
     """In-place sum over ranks (mpi_tools.allreduce :47-52)."""
     if _on():
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if t.is_contiguous():
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        else:                       # a strided view (e.g. columns of a statistics table): reduce a packed copy, write it back
+            c = t.contiguous()
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            t.copy_(c)
     return t
 
 

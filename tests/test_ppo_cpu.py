@@ -47,7 +47,9 @@ def _worker(rank, world, port, out):
     params = torch.full((5,), float(rank))
     mpi_tools.sync_all_params(params)
     kl = mpi_tools.mpi_avg(0.01 * (rank + 1))
-    out[rank] = dict(mean=mean, std=std, lo=lo, hi=hi, grad=grad.tolist(), params=params.tolist(), kl=kl,
+    table = torch.arange(15, dtype=torch.float64).reshape(3, 5) * (rank + 1)     # the epoch-statistics table of run_epochs:
+    mpi_tools.allreduce_sum_(table[:, 0:3])                                      # only its sum columns are rank-summed (strided view)
+    out[rank] = dict(table=table.tolist(), mean=mean, std=std, lo=lo, hi=hi, grad=grad.tolist(), params=params.tolist(), kl=kl,
                      ids=(mpi_tools.proc_id(), mpi_tools.num_procs()), x=x.numpy())
     dist.destroy_process_group()
 
@@ -68,6 +70,9 @@ def test_collectives_world_size_2_gloo():
         assert o['grad'] == [1.5] * 7                 # mean of 1 and 2: Allreduce(SUM) / num_procs (mpi_tf.py:59-62)
         assert o['params'] == [0.0] * 5               # broadcast from rank 0 (mpi_tf.py:24-27)
         assert abs(o['kl'] - 0.015) < 1e-15           # mpi_avg (mpi_tools.py:67-69)
+        want = np.arange(15, dtype=np.float64).reshape(3, 5) * (r + 1)
+        want[:, 0:3] = np.arange(15, dtype=np.float64).reshape(3, 5)[:, 0:3] * 3
+        assert o['table'] == want.tolist()
 
 
 def test_gradient_oracle_matches_torch_autograd():
