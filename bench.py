@@ -29,10 +29,19 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: no NCCL version / debug banner (NCCL prints it to stdout when the box sets
-# NCCL_DEBUG=VERSION or INFO); set ML4CA_KEEP_NCCL_DEBUG=1 to keep the caller's setting
+# stdout carries exactly one JSON line.  NCCL writes its version / debug banner to file descriptor 1 from C (at WARN level
+# too), so descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a duplicate of the real stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+sys.stdout.flush()
+os.dup2(2, 1)
 if not os.environ.get("ML4CA_KEEP_NCCL_DEBUG"):
     os.environ["NCCL_DEBUG"] = "WARN"
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
 
 ENV_STEP_BYTES = 177      # read 60 state + 28 action, write 48 state + 36 obs + 4 rew + 1 done
 ENV_STEP_TRAFFIC = 2.9137e9  # measured DRAM bytes of one 16 Mi-env launch (profiles/env_step_r1.md, capture prof_env_r1h); algorithmic: 2.9696e9
@@ -253,7 +262,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -526,7 +535,7 @@ def run_b200(args, rank, local_rank, world):
                     "steps": e2e_steps, "note": "RevoltFinal.step_host: pinned host actions in, obs+reward+done out, every step, chunked H2D|kernel|D2H pipeline"},
             "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
