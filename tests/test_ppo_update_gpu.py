@@ -165,3 +165,21 @@ def test_episode_statistics_kernel(cuda_device):
     _lib.check(_lib.lib().ml4ca_stats5(x.numel(), _lib.ptr(x), _lib.ptr(s5[0]), _lib.current_stream()))
     np.testing.assert_allclose(s5[0].cpu().numpy(), [rew[0].astype(np.float64).sum(), (rew[0].astype(np.float64) ** 2).sum(), rew[0].size,
                                                      rew[0].min(), rew[0].max()], rtol=1e-9)
+
+
+def test_ppo_learns_station_keeping_at_the_reference_batch_size(cuda_device):
+    """End-to-end learning check at the reference's own batch size (4 envs x 400 steps = 1600 interactions per epoch,
+    config.json): the reference's shipped run (data/finalmodel/finconttothighbowder_s0/progress.txt) starts at
+    AverageEpRet -21 / AverageVVals -0.7 and passes AverageEpRet 787 / VVals 231 at 638 k interactions; the GPU pipeline
+    (rollout, GAE, tensor-core update) on the stand-in hull starts at the same level and is well past +1 reward per step
+    after 200 epochs = 320 k interactions (measured: 2.2-2.3 per step, EpRet ~800, VVals ~260).  Loose thresholds: fp32
+    atomics make the run non-reproducible at the last bit."""
+    import ml4ca_b200 as M
+    from ml4ca_b200.env import RevoltFinal, StandInHull
+    env = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=4, device=cuda_device, seed=0, auto_reset=True)
+    ac, hist = M.ppo(env, steps_per_epoch=400, epochs=200, seed=0)
+    first, last = hist[0], hist[-10:]
+    assert -0.6 < first["AverageStepReward"] < 0.1 and abs(first["AverageVVals"]) < 5
+    assert np.mean([h["AverageStepReward"] for h in last]) > 1.0
+    assert np.mean([h["AverageVVals"] for h in last]) > 100
+    assert np.mean([h["EpLen"] for h in last if h["Episodes"] > 0]) > 250
