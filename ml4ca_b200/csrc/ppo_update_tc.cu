@@ -127,7 +127,8 @@ __device__ __forceinline__ float2 act_grad2(uint32_t h2) {
   return make_float2(1.0f - h.x * h.x, 1.0f - h.y * h.y);
 }
 
-template <int ACTIVATION, int NET>
+// S97: the 9 -> 7 (pi) / 9 -> 1 (v) networks of RevoltFinal(extended_state, cont_ang) with the dims known at compile time.
+template <int ACTIVATION, int NET, bool S97>
 __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
   extern __shared__ __align__(128) uint8_t smem[];
   // warp index through a shuffle: warp-uniform for the compiler, so the group index and every MMA descriptor derived from it
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
   float* consts = reinterpret_cast<float*>(smem + OFF_CONST);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
-  const int obs = A.obs, nout = A.nout;
+  const int obs = S97 ? 9 : A.obs, nout = S97 ? (NET == 0 ? 7 : 1) : A.nout, act_dim = S97 ? 7 : A.act;
 
   // ---- setup: operand images -> smem, zero the activation buffers, constant-1 columns, barriers, TMEM ------------------
   {
@@ -219,27 +220,44 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
   double st[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   bool acc = false, pending = false;   // acc: the dW accumulators hold a tile already; pending: the dW1T chain is in flight
 
-  for (int64_t tile = (int64_t)blockIdx.x * G + g; tile < num_tiles; tile += (int64_t)gridDim.x * G) {
-    const int64_t t = tile / tiles_per_t, i = (tile % tiles_per_t) * TS + row;
-    const bool live = i < n;
-    // ---- inputs: thread = sample ----------------------------------------------------------------------------------------
-    float o[16];
+  constexpr int kPreObs = S97 ? 9 : 12;        // observation rows fetched one tile ahead (wider inputs load the rest in place)
+  float pf_o[kPreObs], pf_a[8], pf_adv = 0.f, pf_lpo = 0.f, pf_ret = 0.f;
+  auto fetch = [&](int64_t tl) {
+    const int64_t t = tl / tiles_per_t, i = (tl % tiles_per_t) * TS + row;
+    const bool live = tl < num_tiles && i < n;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) o[c] = (c < obs && live) ? __ldg(A.obs_buf + ((int64_t)t * obs + c) * n + i) : 0.f;
+    for (int c = 0; c < kPreObs; ++c) pf_o[c] = (c < obs && live) ? __ldg(A.obs_buf + ((int64_t)t * obs + c) * n + i) : 0.f;
 #pragma unroll
-    for (int c = 0; c < 16; ++c)
-      if (c == obs) o[c] = 1.0f;
-    float av[8], adv = 0.f, lpo = 0.f, ret = 0.f;
-#pragma unroll
-    for (int a = 0; a < 8; ++a) av[a] = 0.f;
+    for (int a = 0; a < 8; ++a) pf_a[a] = 0.f;
+    pf_adv = pf_lpo = pf_ret = 0.f;
     if constexpr (NET == 0) {
 #pragma unroll
       for (int a = 0; a < 8; ++a)
-        if (a < nout && live) av[a] = __ldg(A.act_buf + ((int64_t)t * A.act + a) * n + i);
-      if (live) adv = __ldg(A.adv + (int64_t)t * n + i), lpo = __ldg(A.logp_old + (int64_t)t * n + i);
+        if (a < nout && live) pf_a[a] = __ldg(A.act_buf + ((int64_t)t * act_dim + a) * n + i);
+      if (live) pf_adv = __ldg(A.adv + (int64_t)t * n + i), pf_lpo = __ldg(A.logp_old + (int64_t)t * n + i);
     } else {
-      if (live) ret = __ldg(A.ret + (int64_t)t * n + i);
+      if (live) pf_ret = __ldg(A.ret + (int64_t)t * n + i);
     }
+  };
+  bool first_tile = true;
+  for (int64_t tile = (int64_t)blockIdx.x * G + g; tile < num_tiles; tile += (int64_t)gridDim.x * G) {
+    const int64_t t = tile / tiles_per_t, i = (tile % tiles_per_t) * TS + row;
+    const bool live = i < n;
+    // ---- inputs: thread = sample.  Requested one tile ahead (below, after the first hand-over), so their HBM latency is
+    // off the serial chain of the group; only the first tile loads in place.
+    if (first_tile) {
+      fetch(tile);
+      first_tile = false;
+    }
+    float o[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = (c < kPreObs) ? pf_o[c] : ((c < obs && live) ? __ldg(A.obs_buf + ((int64_t)t * obs + c) * n + i) : 0.f);
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c == obs) o[c] = 1.0f;
+    float av[8], adv = pf_adv, lpo = pf_lpo, ret = pf_ret;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) av[a] = pf_a[a];
     if (pending) {                             // the previous tile's dW1T chain still reads A0 / G1
       wait_mma();
       pending = false;
@@ -262,6 +280,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
       }
       __syncwarp();
     }
+    fetch(tile + (int64_t)gridDim.x * G);          // next tile's rows: AFTER the hand-over (its MEMBAR would wait for them)
     // ---- hidden epilogues: D -> f -> operand rows -------------------------------------------------------------------------
     auto hidden = [&](uint8_t* dst) {
       wait_mma();
@@ -485,9 +504,10 @@ int ml4ca_ppo_grad_tc_launch(const ppotc::Args& args, int activation, int net, v
   const int64_t tiles = ((a.n + ppotc::TS - 1) / ppotc::TS) * a.T;
   const int64_t want = (tiles + ppotc::G - 1) / ppotc::G;
   const int grid = (int)(want < kNumSMs ? want : kNumSMs);
+  const bool s97 = a.obs == 9 && a.act == 7;
 #define ML4CA_TC_LAUNCH(ACTV, NETV)                                                                                      \
   do {                                                                                                                   \
-    auto k = ppotc::ppo_grad_tc_kernel<ACTV, NETV>;                                                                      \
+    auto k = s97 ? ppotc::ppo_grad_tc_kernel<ACTV, NETV, true> : ppotc::ppo_grad_tc_kernel<ACTV, NETV, false>;           \
     ML4CA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, ppotc::SMEM_BYTES));                 \
     k<<<grid, ppotc::THREADS, ppotc::SMEM_BYTES, st>>>(a);                                                               \
   } while (0)
