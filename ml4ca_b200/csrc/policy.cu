@@ -8,20 +8,25 @@
 //   v-net  : obs -> H -> ... -> 1                                v
 //   pi = mu + eps * exp(log_std),  logp_pi = sum -0.5 (((pi - mu) / (exp(log_std) + 1e-8))^2 + 2 log_std + log 2 pi)
 //
-// Tensor-core mapping.  A tile is 128 observations = the M = 128 rows of a cta_group::1 UMMA.  The two networks
-// share every MMA chain:
-//   layer 1 : A0 [128 x 16]  (obs, 1.0, zero pad)           x  B1   [2H x 16]        -> D[:, 0:2H]
+// Tensor-core mapping.  A tile is 128 observations = the M = 128 rows of a cta_group::1 UMMA:
+//   layer 1 : A0 [128 x 16]  (obs, 1.0, zero pad)           x  B1   [2H x 16]        -> D[:, 0:2H]     (both nets, one MMA)
 //   hidden l: A  [128 x KP]  per net (H activations, 1.0, pad; KP = H + 16) x Bl [H x KP] -> D[:, net*H : net*H+H]
-//   output  : A  [128 x 2KP] (both nets side by side)        x  Bout [16 x 2KP]       -> D[:, 0:16] = mu(7), v, pad
+//   output  : A  [128 x KP]  per net                          x  its KP columns of Bout [16 x 2KP]
+//                                                              -> D[:, 0:16] = mu (pi chain), D[:, 16:32] = v in column act_dim (v chain)
 // The constant-1 column folds every bias into the MMA (the epilogue is activation + convert only).
 // Operands are fp16 in shared memory in the canonical no-swizzle K-major core-matrix layout (tc05.cuh), written by
 // the epilogue threads themselves; accumulators are fp32 in tensor memory.  Weights (<= 72 KB) are packed once per
 // parameter update into that layout and stay resident in shared memory for the life of the persistent CTA.
 //
 // Thread roles (1 CTA per SM, grid = #SMs): 4 tile groups of 128 threads for H = 64 (2 for H = 80), thread = one
-// observation = one TMEM lane; thread 0 of a group issues that group's MMA chains after a group-local named
-// barrier (operand rows complete), tcgen05.commit signals the group's mbarrier.  The groups drift out of phase:
-// while some run their epilogue on the CUDA cores the tensor core runs the chains of the others.
+// observation = one TMEM lane.  A stage hand-over = proxy fence + group-local named barrier (operand rows complete); then
+// one ELECTED lane of each of the group's first two warps issues its half of the stage (one net / one output accumulator)
+// from a warp-uniform branch and commits to the group's mbarrier (count 2).  Uniformity matters: with the warp index taken
+// through __shfl_sync the compiler keeps the group index and every descriptor in uniform registers and the UTCHMMAs go out
+// back to back; issued from `if (row == 0)` each MMA cost a 14-instruction waterfall loop.  One thread's MMAs execute
+// strictly one after the other, hence two issuers for independent chains.  The groups run out of phase: while some run
+// their epilogue on the CUDA cores the tensor core runs the chains of the others.  Measured bounds and dead ends:
+// profiles/policy_qp_r1.md.
 //
 // Numerics: fp16 operands (10-bit mantissa), fp32 accumulation: mu and v carry ~1e-3 relative error against the float64 oracle
 // (stated in tests/test_policy_gpu.py); logp_pi depends only on eps and log_std and is fp32-exact.
