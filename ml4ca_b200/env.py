@@ -15,7 +15,6 @@ The proprietary Cybersea simulator behind ``digitwin`` is absent from the refere
 passes a ``DigiTwin``.
 """
 import ctypes
-import math
 
 import numpy as np
 import torch

@@ -5,7 +5,6 @@
 
 Everything heavy runs behind the C ABI (csrc/policy.cu, csrc/env_step*.cu, csrc/gae.cu); this module is plumbing.
 """
-import ctypes
 
 import torch
 

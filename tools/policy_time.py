@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import ml4ca_b200 as M
-from ml4ca_b200 import synth
+
 
 n = int(os.environ.get("N", 1 << 23))
 dev = torch.device("cuda", 0)

@@ -5,7 +5,7 @@ import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import ml4ca_b200 as M
-from ml4ca_b200 import _lib
+
 
 n = 1 << 23
 dev = torch.device("cuda", 0)
