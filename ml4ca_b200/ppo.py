@@ -186,8 +186,7 @@ def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2,
     Hyper-parameter defaults are the reference's config.json.  ``logger_kwargs=dict(output_dir=..., exp_name=...)``
     writes progress.txt / config.json in the reference's format (ppo.py:332-346, logx.py).  ``logger`` may be a callable
     receiving each epoch's dictionary.  Returns (ac, list of per-epoch dictionaries)."""
-    import time as _time
-    from . import logx, mpi_tools
+    from . import mpi_tools
     from .core import ActorCritic
     n, dev = env.num_envs, env.device
     if ac is None:
