@@ -166,6 +166,11 @@ ML4CA_API int ml4ca_policy_forward(ml4ca_policy* p, int64_t n, const float* obs,
                                    int32_t deterministic, int64_t env_id_offset, float* act, float* val, float* logp,
                                    float* mu, void* stream);
 
+/* CUDA-graph support for launch-bound rollouts (no reference counterpart: the reference steps one env per sess.run).  With a
+ * device-resident counter set, every later ml4ca_policy_forward / ml4ca_rollout_step uses step + *step_dev as the Philox
+ * step: a captured graph of T rollout steps (step arguments 0 .. T-1) is replayed epoch after epoch with fresh noise by
+ * writing the epoch's first step number into the counter.  NULL restores the plain step argument. */
+ML4CA_API int ml4ca_policy_set_step_counter(ml4ca_policy* p, const uint32_t* step_dev);
 /* One fused rollout step = ppo.py:291-293 (`sess.run(get_action_ops)` then `env.step(a)`) for every environment of
  * `env` (RevoltFinal, extended state, continuous angles; 9 -> 7 policy): observation from the state in HBM -> tcgen05
  * MLP -> sampled action -> env step, in ONE kernel.  Trajectory records of this time step (each nullable):

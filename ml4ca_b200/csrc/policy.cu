@@ -131,6 +131,7 @@ struct PolicyParams {
   const float* params;  // fp32 master copy (log_std lives here)
   int log_std_off;
   PolicyDims d;
+  const uint32_t* step_dev;   // nullable: device-resident base added to the step argument (ml4ca_policy_set_step_counter)
 };
 
 // Activation on a packed pair, evaluated in fp16 AFTER the rounding to the operand format (the result is an fp16
@@ -463,8 +464,9 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
       if (live && !deterministic) {
         const uint64_t gid = (uint64_t)(env + env_off);
         const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ 0xAC710Au;
-        const Philox4 pa = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), step, 0u, k0, k1);
-        const Philox4 pb = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), step, 1u, k0, k1);
+        const uint32_t step_eff = step + (pp.step_dev != nullptr ? __ldg(pp.step_dev) : 0u);
+        const Philox4 pa = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), step_eff, 0u, k0, k1);
+        const Philox4 pb = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), step_eff, 1u, k0, k1);
         normal_pair(pa.x, pa.y, eps[0], eps[1]);
         normal_pair(pa.z, pa.w, eps[2], eps[3]);
         normal_pair(pb.x, pb.y, eps[4], eps[5]);
@@ -583,6 +585,7 @@ struct ml4ca_policy {
   float* params;             // fp32 master parameters (device)
   __half* blob;       // packed fp16 operands (device)
   int num_sms;
+  const uint32_t* step_dev = nullptr;   // ml4ca_policy_set_step_counter
 };
 
 namespace ml4ca {
@@ -629,6 +632,7 @@ static int dispatch_policy(const ml4ca_policy* p, int64_t n, const float* obs, u
   pp.params = p->params;
   pp.log_std_off = p->d.n_params_net(p->d.act);
   pp.d = p->d;
+  pp.step_dev = p->step_dev;
   if (p->d.H == 64 && p->d.NL == 2) return launch_policy<64, 2, FUSE>(p, pp, n, obs, seed, step, det, env_off, act, val, logp, mu, ep, ro, st);
   if (p->d.H == 64 && p->d.NL == 3) return launch_policy<64, 3, FUSE>(p, pp, n, obs, seed, step, det, env_off, act, val, logp, mu, ep, ro, st);
   return launch_policy<80, 3, FUSE>(p, pp, n, obs, seed, step, det, env_off, act, val, logp, mu, ep, ro, st);
@@ -706,6 +710,12 @@ __attribute__((visibility("default"))) int ml4ca_debug_policy_trace(long long* h
   return cudaMemcpyFromSymbol(host, ml4ca::g_policy_trace, sizeof(long long) * 4 * 64 * 16) == cudaSuccess ? 0 : -2;
 }
 #endif
+
+int ml4ca_policy_set_step_counter(ml4ca_policy* p, const uint32_t* step_dev) {
+  ML4CA_REQUIRE(p != nullptr, "policy is NULL");
+  p->step_dev = step_dev;
+  return ML4CA_OK;
+}
 
 int ml4ca_policy_refresh(ml4ca_policy* p, void* stream) {
   ML4CA_REQUIRE(p != nullptr, "policy is NULL");

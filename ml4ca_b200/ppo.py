@@ -60,14 +60,8 @@ class TrajectoryBuffer(object):
         return [self.obs_buf, self.act_buf, self.adv_buf, self.ret_buf, self.logp_buf]
 
 
-def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, fused=False):
-    """Fill ``buf`` with T = buf.max_size steps of every environment (ppo.py:290-302 batched).
-
-    fused=False: policy kernel then env-step kernel per time step (the faster arrangement on B200: both kernels
-    are issue-bound); fused=True: the single fused kernel (ml4ca_rollout_step), which keeps
-    observation and action out of HBM.  The env must have auto_reset=True (finished episodes restart in-kernel).
-    Returns the observation after the last step (for the bootstrap value).
-    """
+def _rollout_launches(env, ac, buf, seed, start_step, deterministic, fused):
+    """The 2T (or T) kernel launches of one rollout on the current stream; nothing else (capturable)."""
     L = _lib.lib()
     T, n = buf.max_size, env.num_envs
     stream = _lib.current_stream()
@@ -77,16 +71,58 @@ def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, fused=False
                                             int(bool(deterministic)), _lib.ptr(buf.obs_buf[t]), _lib.ptr(buf.act_buf[t]),
                                             _lib.ptr(buf.rew_buf[t]), _lib.ptr(buf.val_buf[t]), _lib.ptr(buf.logp_buf[t]),
                                             _lib.ptr(buf.done_buf[t]), stream), "ml4ca_rollout_step")
-        return None
-    rows = buf._obs_rows
-    rows[0].copy_(env._obs)  # observation returned by the last reset()/step(); from here on the env kernel writes row t + 1
-    for t in range(T):       # directly, so the record costs no extra copy
+        return
+    rows = buf._obs_rows     # row t = observation acted on at step t; the env kernel writes row t + 1 directly (no per-step copy)
+    for t in range(T):
         _lib.check(L.ml4ca_policy_forward(ac._handle, n, _lib.ptr(rows[t]), seed & 0xFFFFFFFFFFFFFFFF, start_step + t,
                                           int(bool(deterministic)), env._cfg.env_id_offset, _lib.ptr(buf.act_buf[t]),
                                           _lib.ptr(buf.val_buf[t]), _lib.ptr(buf.logp_buf[t]), None, stream),
                    "ml4ca_policy_forward")
         env.step_into(buf.act_buf[t], rows[t + 1], buf.rew_buf[t], buf.done_buf[t])
-    env._obs = rows[T].clone()
+
+
+def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, fused=False, graph=False):
+    """Fill ``buf`` with T = buf.max_size steps of every environment (ppo.py:290-302 batched).
+
+    fused=False: policy kernel then env-step kernel per time step (the faster arrangement on B200, see DESIGN.md);
+    fused=True: the single fused kernel (ml4ca_rollout_step), which keeps observation and action out of HBM.
+    graph=True: the T steps are captured once into a CUDA graph (per env / policy / buffer) and replayed on later calls --
+    for small and medium batches the rollout is launch-bound (2T launches through ctypes); the Philox step number then comes
+    from a device counter (ml4ca_policy_set_step_counter) that is set to ``start_step`` before every replay, so a graph
+    rollout draws exactly the noise of the eager one.  The first call runs eagerly (it also initialises the kernels).
+    The env must have auto_reset=True (finished episodes restart in-kernel).
+    Returns the observation after the last step (for the bootstrap value); None on the fused path.
+    """
+    T = buf.max_size
+    if not fused:
+        buf._obs_rows[0].copy_(env._obs)   # observation returned by the last reset() / step()
+    if not graph:
+        _rollout_launches(env, ac, buf, seed, start_step, deterministic, fused)
+    else:
+        cache = buf.__dict__.setdefault("_rollout_graphs", {})
+        key = (id(env), id(ac), int(seed), bool(deterministic), bool(fused))
+        entry = cache.get(key)
+        if entry is None:                  # first call: eager, and remember that the next one may capture
+            cache[key] = {"graph": None, "counter": torch.zeros(1, dtype=torch.int32, device=buf.device)}
+            _rollout_launches(env, ac, buf, seed, start_step, deterministic, fused)
+        else:
+            L = _lib.lib()
+            if entry["graph"] is None:
+                _lib.check(L.ml4ca_policy_set_step_counter(ac._handle, _lib.ptr(entry["counter"])))
+                try:
+                    torch.cuda.synchronize(buf.device)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode="relaxed"):
+                        _rollout_launches(env, ac, buf, seed, 0, deterministic, fused)     # step = counter + t
+                finally:
+                    _lib.check(L.ml4ca_policy_set_step_counter(ac._handle, None))
+                entry["graph"] = g
+            v = int(start_step) & 0xFFFFFFFF                       # the kernel adds it as uint32
+            entry["counter"].fill_(v - (1 << 32) if v >= (1 << 31) else v)
+            entry["graph"].replay()
+    if fused:
+        return None
+    env._obs = buf._obs_rows[T].clone()
     return env._obs
 
 
@@ -180,7 +216,7 @@ PPO_COLUMNS = ('LossPi', 'LossV', 'DeltaLossPi', 'DeltaLossV', 'Entropy', 'KL', 
 
 def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2, pi_lr=3e-4, vf_lr=1e-3,
         train_pi_iters=80, train_v_iters=80, lam=0.97, target_kl=0.01, seed=0, hidden_sizes=(64, 64),
-        activation="leaky_relu", fused=False, logger=None, logger_kwargs=None):
+        activation="leaky_relu", fused=False, logger=None, logger_kwargs=None, graph=False):
     """ppo.py:107-346 for a batched env: every epoch = ``steps_per_epoch`` steps of EVERY environment of ``env``
     (rollout), GAE-lambda (finish_path), advantage normalisation over all ranks, then the PPO update.
     Hyper-parameter defaults are the reference's config.json.  ``logger_kwargs=dict(output_dir=..., exp_name=...)``
@@ -200,11 +236,11 @@ def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2,
                   vf_lr=vf_lr, train_pi_iters=train_pi_iters, train_v_iters=train_v_iters, lam=lam,
                   target_kl=target_kl, seed=seed)
     return run_epochs(env, ac, buf, upd, steps_per_epoch, epochs, seed, fused, logger, logger_kwargs, config, PPO_COLUMNS,
-                      log_std_column=True)
+                      log_std_column=True, graph=graph)
 
 
 def run_epochs(env, ac, buf, upd, steps_per_epoch, epochs, seed, fused, logger, logger_kwargs, config, columns,
-               log_std_column=False):
+               log_std_column=False, graph=False):
     """The epoch loop shared by ppo() (ppo.py:283-346) and trpo() (trpo.py:327-384): rollout of every environment,
     bootstrap + GAE-lambda, episode / value statistics, ``upd.update(buf)``, the reference's progress.txt columns."""
     import time as _time
@@ -223,7 +259,7 @@ def run_epochs(env, ac, buf, upd, steps_per_epoch, epochs, seed, fused, logger, 
     env.reset(fraction=0.8)
     history, step, start_time = [], 0, _time.time()
     for epoch in range(epochs):
-        o_last = rollout(env, ac, buf, seed=seed, start_step=step, fused=fused)
+        o_last = rollout(env, ac, buf, seed=seed, start_step=step, fused=fused, graph=graph)
         step += steps_per_epoch
         if o_last is None:                        # fused path: the observation is rebuilt from the env state
             o_last = env.observe()

@@ -132,3 +132,34 @@ def test_rollout_matches_stepwise_reference_semantics(cuda_device, fused, reset_
     for k in ('eta', 'nu', 'prev_thrust', 'angles'):
         np.testing.assert_allclose(sB[k].cpu().numpy(), sA[k].cpu().numpy(), rtol=0, atol=2e-6)
     assert torch.equal(sA['ep_len'], sB['ep_len'])
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_graph_rollout_equals_eager_rollout(cuda_device, fused):
+    """rollout(graph=True): the T steps captured into a CUDA graph and replayed with the Philox step number taken from a
+    device counter reproduce the eager launches bit for bit, epoch after epoch (first call eager, second captures)."""
+    import ml4ca_b200 as M
+    from ml4ca_b200.env import RevoltFinal, StandInHull
+    dims = dict(obs_dim=9, act_dim=7, hidden=64, n_hidden=2)
+    ac = M.ActorCritic(9, 7, (64, 64), "leaky_relu", params=MO.glorot_params(dims, seed=3), device=cuda_device, seed=21)
+    n, T = 3000, 10
+    mk = lambda: RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=n, device=cuda_device, seed=9,
+                             auto_reset=True, max_ep_len=16)
+    envA, envB = mk(), mk()
+    envA.reset(); envB.reset()
+    bufA = M.TrajectoryBuffer(9, 7, T, n, device=cuda_device)
+    bufB = M.TrajectoryBuffer(9, 7, T, n, device=cuda_device)
+    for epoch, start in enumerate([0, T, 2 * T, (1 << 32) - 4]):       # the last one wraps the 32-bit step number
+        M.rollout(envA, ac, bufA, seed=5, start_step=start, fused=fused)
+        M.rollout(envB, ac, bufB, seed=5, start_step=start, fused=fused, graph=True)
+        for name in ("obs_buf", "act_buf", "rew_buf", "logp_buf", "done_buf"):
+            assert torch.equal(getattr(bufA, name), getattr(bufB, name)), (epoch, name)
+        assert torch.equal(bufA.val_buf[:T], bufB.val_buf[:T])
+        sA, sB = envA.get_state(), envB.get_state()
+        for k in ("eta", "nu", "prev_thrust", "angles", "ep_len"):
+            assert torch.equal(sA[k], sB[k]), (epoch, k)
+    assert bufB._rollout_graphs and all(e["graph"] is not None for e in bufB._rollout_graphs.values())
+    # eager calls after a capture are unaffected by the counter
+    a1 = ac.step(bufA.obs_buf[0], step=7)[0]
+    a2 = ac.step(bufA.obs_buf[0], step=7)[0]
+    assert torch.equal(a1, a2)
