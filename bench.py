@@ -54,6 +54,17 @@ ACTION_POOL = 2           # flat U(-1,1) buffers; step i reads a [7, n] window a
 ACTION_SHIFT = 4 * 1031   # floats between consecutive windows (16-byte aligned, so the vectorised kernel path is kept)
 
 
+def load_tensor_peak():
+    """Sustained dense bf16/fp16 TFLOP/s (MEASURED_PEAKS.json), else the profiling guide's nominal figure."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        if "bf16_tflops_sustained" in p:
+            return float(p["bf16_tflops_sustained"]), "measured sustained (MEASURED_PEAKS.json)"
+    return 2250.0, "nominal dense bf16 (B200_PROFILING.md)"
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -430,7 +441,12 @@ def run_b200(args, rank, local_rank, world):
             extra["policy_forward"] = {"workload": "BASELINE configs[3] network: 9-64-64-7 + 9-64-64-1 leaky-ReLU actor/critic, "
                                                    "8 Mi observations, tcgen05 fp16 operands / fp32 TMEM accumulators",
                                        "value": m / t, "unit": "observations/s", "ms_per_launch": t * 1e3,
-                                       "achieved_GBs": POLICY_BYTES * m / t / 1e9, "achieved_TFLOPs": flop * m / t / 1e12}
+                                       "achieved_GBs": POLICY_BYTES * m / t / 1e9, "achieved_TFLOPs": flop * m / t / 1e12,
+                                       "roofline": {"bound": "tensor", "achieved": flop * m / t / 1e12, "peak": load_tensor_peak()[0],
+                                                    "unit": "TFLOP/s", "frac": flop * m / t / 1e12 / load_tensor_peak()[0],
+                                                    "peak_source": load_tensor_peak()[1],
+                                                    "note": "algorithmic flop (19 712 per observation); tensor pipe 64 % active under ncu "
+                                                            "(profiles/policy_qp_r1.md): the MMAs are operand-read bound"}}
             env2 = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=m, device=dev, seed=4,
                                auto_reset=True, env_id_offset=rank * m)
             env2.reset(fraction=0.8)
@@ -454,7 +470,8 @@ def run_b200(args, rank, local_rank, world):
             gbuf.rew_buf.normal_(generator=gen); gbuf.val_buf.normal_(generator=gen)
             t = timed(lambda: gbuf.finish_path(), 5)
             extra["gae"] = {"workload": "TrajectoryBuffer.finish_path, T=64 x 2 Mi envs", "value": Tg * mg / t,
-                            "unit": "steps/s", "ms_per_launch": t * 1e3, "achieved_GBs": GAE_BYTES * Tg * mg / t / 1e9}
+                            "unit": "steps/s", "ms_per_launch": t * 1e3, "achieved_GBs": GAE_BYTES * Tg * mg / t / 1e9,
+                            "hbm_frac": GAE_BYTES * Tg * mg / t / 1e9 / peak_gbs}
             del env2, buf, gbuf, ac
         except Exception as e:  # noqa: BLE001
             extra["policy_rollout"] = {"error": repr(e)}
