@@ -145,7 +145,8 @@ class PPOUpdater(object):
         self.t_pi = self.t_v = 0
 
     # -- one gradient pass: returns the rank-summed statistics as a list of 5 floats and the global sample count ------
-    def _grad(self, net, data, T, n):
+    def _grad(self, net, data, T, n, read=True):
+        """One gradient pass.  read=False leaves the statistics on the device (no host synchronisation): (None, count)."""
         obs, act, adv, ret, logp = data
         L, ac = _lib.lib(), self.ac
         with torch.cuda.device(ac.device):
@@ -157,7 +158,7 @@ class PPOUpdater(object):
         self.flat[P:P + 5].copy_(self.stats[:5])
         mpi_tools.allreduce_sum_(self.flat)
         count = float(T) * float(n) * mpi_tools.num_procs()   # equal shards (mpi_tools.shard_bounds differ by <= 1 env)
-        return self.flat[P:P + 5].tolist(), count
+        return (self.flat[P:P + 5].tolist() if read else None), count
 
     def _adam(self, net, count):
         ac, L = self.ac, _lib.lib()
@@ -172,7 +173,8 @@ class PPOUpdater(object):
             _lib.check(L.ml4ca_adam_step(hi - lo, _lib.ptr(params[lo:hi]), _lib.ptr(self.flat[lo:hi]), _lib.ptr(self.m1[lo:hi]),
                                          _lib.ptr(self.m2[lo:hi]), lr, 0.9, 0.999, 1e-8, t, 1.0 / count,
                                          _lib.current_stream()), "ml4ca_adam_step")
-        ac.refresh()
+        # the fp16 operand image of the forward kernel is NOT refreshed here: the gradient kernels read the fp32 master
+        # parameters, so update() refreshes it once, after the last step
 
     def losses(self, data, T, n):
         """pi_loss, v_loss, approx_kl, approx_ent, clipfrac at the current parameters (ppo.py:262,275)."""
@@ -184,8 +186,8 @@ class PPOUpdater(object):
 
     def _update_v(self, data, T, n, info):
         """ppo.py:272-273 / trpo.py:323-325: train_v_iters Adam steps on v_loss."""
-        for i in range(self.train_v_iters):
-            s, c = self._grad(1, data, T, n)
+        for i in range(self.train_v_iters):      # nothing to test between the steps: only the first pass is read back
+            s, c = self._grad(1, data, T, n, read=(i == 0))
             if i == 0:
                 info["LossV"] = s[1] / c
             self._adam(1, c)
@@ -205,6 +207,7 @@ class PPOUpdater(object):
                 break
         info["StopIter"] = stop
         self._update_v(data, T, n, info)
+        self.ac.refresh()
         new = self.losses(data, T, n)
         info.update(KL=new["KL"], ClipFrac=new["ClipFrac"], DeltaLossPi=new["LossPi"] - info.get("LossPi", new["LossPi"]),
                     DeltaLossV=new["LossV"] - info.get("LossV", new["LossV"]))

@@ -66,10 +66,12 @@ class TRPOUpdater(PPOUpdater):
     def _pi_params(self):
         return self.ac.parameters()[:self.n_pi]
 
-    def _set_pi(self, theta):
-        """set_pi_params (trpo.py:250-251): theta = float64 host vector."""
+    def _set_pi(self, theta, refresh=False):
+        """set_pi_params (trpo.py:250-251): theta = float64 host vector.  The passes of the update read the fp32 master
+        parameters; the forward kernel's fp16 operand image is refreshed once, at the end of update()."""
         self._pi_params().copy_(torch.as_tensor(np.asarray(theta, dtype=np.float32)))
-        self.ac.refresh()
+        if refresh:
+            self.ac.refresh()
 
     def _surrogate(self, data, T, n):
         """-> (flat gradient of pi_loss [n_pi] float64, pi_loss), both rank-averaged (trpo.py:287-288)."""
@@ -161,6 +163,7 @@ class TRPOUpdater(PPOUpdater):
         T, n = buf.max_size, buf.num_envs
         info = self.update_policy(data, T, n)
         self._update_v(data[:5], T, n, info)
+        self.ac.refresh()
         s, c = self._grad(1, data[:5], T, n)
         info['DeltaLossV'] = s[1] / c - info['LossV']
         return info
