@@ -112,19 +112,21 @@ class TRPOUpdater(PPOUpdater):
         return (gp - gm) / (2.0 * e) + self.damping_coeff * v
 
     def cg(self, Ax, b):
-        """trpo.py:264-281."""
+        """Conjugate gradients on A x = b from x = 0 for exactly ``cg_iters`` steps (no residual test), as trpo.py:264-281
+        runs it: the direction update uses the ratio of successive squared residual norms, the step length carries the
+        reference's +1e-8 in its denominator."""
         x = np.zeros_like(b)
-        r = b.copy()
-        p = r.copy()
-        r_dot_old = np.dot(r, r)
+        res = np.array(b, dtype=np.float64)          # residual b - A x at x = 0
+        direction = res.copy()
+        rr = float(res @ res)
         for _ in range(self.cg_iters):
-            z = Ax(p)
-            alpha = r_dot_old / (np.dot(p, z) + EPS)
-            x += alpha * p
-            r -= alpha * z
-            r_dot_new = np.dot(r, r)
-            p = r + (r_dot_new / r_dot_old) * p
-            r_dot_old = r_dot_new
+            Ad = Ax(direction)
+            step = rr / (float(direction @ Ad) + EPS)
+            x = x + step * direction
+            res = res - step * Ad
+            rr_next = float(res @ res)
+            direction = res + (rr_next / rr) * direction
+            rr = rr_next
         return x
 
     def update_policy(self, data, T, n):

@@ -105,19 +105,18 @@ class Problem(object):
 
 
 def cg(Ax, b, cg_iters=10):
-    """trpo.py:264-281, verbatim algorithm."""
+    """trpo.py:264-281: conjugate gradients from x = 0, a fixed number of steps, +1e-8 in the step-length denominator."""
     x = np.zeros_like(b)
-    r = b.copy()
-    p = r.copy()
-    r_dot_old = np.dot(r, r)
+    res, direction = b.copy(), b.copy()
+    rr = np.dot(res, res)
     for _ in range(cg_iters):
-        z = Ax(p)
-        alpha = r_dot_old / (np.dot(p, z) + EPS)
-        x += alpha * p
-        r -= alpha * z
-        r_dot_new = np.dot(r, r)
-        p = r + (r_dot_new / r_dot_old) * p
-        r_dot_old = r_dot_new
+        Ad = Ax(direction)
+        step = rr / (np.dot(direction, Ad) + EPS)
+        x += step * direction
+        res -= step * Ad
+        rr_next = np.dot(res, res)
+        direction = res + (rr_next / rr) * direction
+        rr = rr_next
     return x
 
 
