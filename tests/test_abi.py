@@ -77,3 +77,14 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_every_entry_point_is_placed_at_a_reference_seam():
+    """INTEGRATION.md names every exported function next to the reference call site it replaces."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "ml4ca_b200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    funcs = sorted(set(re.findall(r"\b(ml4ca_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(funcs) >= 40
+    missing = [f for f in funcs if f not in doc]
+    assert not missing, missing
