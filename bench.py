@@ -525,27 +525,30 @@ def run_b200(args, rank, local_rank, world):
             del env3, ac3
         except Exception as e:  # noqa: BLE001
             extra["ppo_train"] = {"error": repr(e)}
-        # the same epoch with the TRPO update (train.py --algo trpo): CG on the Fisher-vector product + line search + 80 v steps
-        try:
-            ne, Tp = 1 << 14, 400
-            env4 = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=ne, device=dev, seed=7,
-                               auto_reset=True, env_id_offset=rank * ne)
-            ac4 = M.ActorCritic(9, 7, (64, 64), "leaky_relu", device=dev, seed=7)
-            marks = []
+        # the same epoch with the TRPO update (train.py --algo trpo): CG on the Fisher-vector product + line search + 80 v steps;
+        # once with every policy pass on the fp32 kernel (parity mode, default) and once with the CG passes on tcgen05
+        for leg, kern in (("trpo_train", "fp32"), ("trpo_train_tc", "tensor_core")):
+            try:
+                ne, Tp = 1 << 14, 400
+                env4 = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=ne, device=dev, seed=7,
+                                   auto_reset=True, env_id_offset=rank * ne)
+                ac4 = M.ActorCritic(9, 7, (64, 64), "leaky_relu", device=dev, seed=7)
+                marks = []
 
-            def mark4(info):
-                torch.cuda.synchronize()
-                marks.append(time.perf_counter())
-            _, hist = M.trpo(env4, ac4, steps_per_epoch=Tp, epochs=4, seed=7, graph=True, logger=mark4)
-            dt = max_over_ranks(marks[3] - marks[1]) / 2
-            extra["trpo_train"] = {"workload": "TRPO epoch = 400-step rollout of 16 Ki envs/GPU + GAE + update (trpo.py defaults: "
-                                               "10 CG iterations on the damped Fisher-vector product, <= 10 backtracking steps, "
-                                               "80 v iterations), all-reduce of every flat gradient",
-                                   "value": ne * world * Tp / dt, "unit": "env-steps/s incl. update", "s_per_epoch": dt,
-                                   "last_epoch": {k: hist[-1][k] for k in ("KL", "BacktrackIters", "DeltaLossPi", "LossV")}}
-            del env4, ac4
-        except Exception as e:  # noqa: BLE001
-            extra["trpo_train"] = {"error": repr(e)}
+                def mark4(info):
+                    torch.cuda.synchronize()
+                    marks.append(time.perf_counter())
+                _, hist = M.trpo(env4, ac4, steps_per_epoch=Tp, epochs=4, seed=7, graph=True, logger=mark4, kernel=kern)
+                dt = max_over_ranks(marks[3] - marks[1]) / 2
+                extra[leg] = {"workload": "TRPO epoch = 400-step rollout of 16 Ki envs/GPU + GAE + update (trpo.py defaults: "
+                                          "10 CG iterations on the damped Fisher-vector product, <= 10 backtracking steps, "
+                                          "80 v iterations), all-reduce of every flat gradient; KL-gradient passes of the CG solve on the "
+                                          + ("fp32 CUDA-core kernel" if kern == "fp32" else "tcgen05 kernel"),
+                              "value": ne * world * Tp / dt, "unit": "env-steps/s incl. update", "s_per_epoch": dt,
+                              "last_epoch": {k: hist[-1][k] for k in ("KL", "BacktrackIters", "DeltaLossPi", "LossV")}}
+                del env4, ac4
+            except Exception as e:  # noqa: BLE001
+                extra[leg] = {"error": repr(e)}
 
     sampler.stop_flag.set()
     sampler.join(timeout=1.0)

@@ -242,9 +242,14 @@ ML4CA_API int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T,
 ML4CA_API int ml4ca_ppo_use_fp32(int enable);
 /* ---- TRPO / NPG pieces (spinup/algos/tf1/trpo/trpo.py:236-247,264-303; trpo/core.py:52-60,88-100) -----------------------------
  * The surrogate pi_loss = -mean(ratio adv) and its flat gradient (trpo.py:237,244) are ml4ca_ppo_grad with net 0 and a
- * clip_ratio large enough never to bind (1e30).  The two passes below always run the fp32 CUDA-core kernel.
+ * clip_ratio large enough never to bind (1e30).  The two passes below run the fp32 CUDA-core kernel unless
+ * ml4ca_trpo_use_tensor_cores(1) selects the tcgen05 one.
  * ml4ca_trpo_policy_mu: the distribution "info" the reference's GAEBuffer stores per step (trpo.py:300): mu [T, act_dim, n]
  * of obs [T, obs_dim, n] at the current parameters (log_std is state-independent: the caller copies it from the parameters). */
+/* enable = 1 runs the two TRPO passes on the tensor-core gradient kernel (fp16 operands: the Hessian-vector product then needs a
+ * wider central-difference bracket and is good to a few per cent, see ml4ca_b200/trpo.py); 0 = the fp32 kernel (default),
+ * -1 only queries; returns the previous setting. */
+ML4CA_API int ml4ca_trpo_use_tensor_cores(int enable);
 ML4CA_API int ml4ca_trpo_policy_mu(ml4ca_policy* p, int64_t n, int32_t T, const float* obs, float* mu, void* stream);
 /* d_kl = mean KL(pi_theta || pi_old) (core.diagonal_gaussian_kl as mlp_gaussian_policy calls it, trpo/core.py:52-60,98) over
  * the buffer, and its flat gradient w.r.t. the pi variables and log_std: grad (SUM convention, like ml4ca_ppo_grad; v block

@@ -83,6 +83,7 @@ _SIGNATURES = {
     "ml4ca_ppo_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_f32p,
                                       c_f32p, c_f32p, ctypes.c_float, c_f32p, ctypes.c_void_p, c_stream]),
     "ml4ca_ppo_use_fp32": (ctypes.c_int, [ctypes.c_int]),
+    "ml4ca_trpo_use_tensor_cores": (ctypes.c_int, [ctypes.c_int]),
     "ml4ca_trpo_policy_mu": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_stream]),
     "ml4ca_trpo_kl_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_f32p, c_f32p,
                                           ctypes.c_void_p, c_stream]),

@@ -17,6 +17,10 @@ struct Args {
   int T;
   const float *obs_buf, *act_buf, *adv, *logp_old, *ret;
   float clip;
+  // TRPO (see ppo_update.cu): loss_mode 1 = d_kl with act_buf = mu_old and kl_ls_old = old log_std; mu_out = forward only
+  int loss_mode;
+  const float* kl_ls_old;
+  float* mu_out;
   float* grad;
   double* stats;
 };

@@ -508,6 +508,35 @@ extern "C" int ml4ca_ppo_use_fp32(int enable) {
   return prev;
 }
 
+static bool g_trpo_tc = false;   // TRPO passes on the tensor-core kernel (ml4ca_trpo_use_tensor_cores)
+
+extern "C" int ml4ca_trpo_use_tensor_cores(int enable) {
+  const int prev = g_trpo_tc ? 1 : 0;
+  if (enable >= 0) g_trpo_tc = enable != 0;
+  return prev;
+}
+
+// per-device scratch for the packed fp16 operands of the tensor-core gradient kernel (kept for the life of the process)
+static int tc_blob(int32_t device, __half** out) {
+  static __half* blob[64] = {};
+  ML4CA_REQUIRE(device >= 0 && device < 64, "device index out of range");
+  if (blob[device] == nullptr) ML4CA_CUDA(cudaMalloc(&blob[device], sizeof(__half) * ppotc::kBlobHalves));
+  *out = blob[device];
+  return ML4CA_OK;
+}
+
+static ppotc::Args tc_args(const ppo::Args& a) {
+  ppotc::Args t = {};
+  t.params = a.params, t.obs = a.obs, t.act = a.act, t.nout = a.nout;
+  t.off_w1 = a.off_w1, t.off_b1 = a.off_b1, t.off_w2 = a.off_w2, t.off_b2 = a.off_b2, t.off_wo = a.off_wo;
+  t.off_bo = a.off_bo, t.off_ls = a.off_ls;
+  t.n = a.n, t.T = a.T;
+  t.obs_buf = a.obs_buf, t.act_buf = a.act_buf, t.adv = a.adv, t.logp_old = a.logp_old, t.ret = a.ret;
+  t.clip = a.clip, t.loss_mode = a.loss_mode, t.kl_ls_old = a.kl_ls_old, t.mu_out = a.mu_out;
+  t.grad = a.grad, t.stats = a.stats;
+  return t;
+}
+
 // policy.cu
 extern "C" int ml4ca_policy_describe(const ml4ca_policy* p, ml4ca_policy_cfg* cfg, int32_t* device);
 
@@ -582,17 +611,10 @@ int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const flo
   // Default: the tcgen05 kernel (fp16 operands, fp32 TMEM accumulation).  ML4CA_PPO_FP32=1 selects the fp32
   // CUDA-core kernel (gradients to 1e-5 instead of 1e-3).
   if (!g_use_fp32) {
-    static __half* blob[64] = {};       // per-device scratch for the packed operands (kept for the life of the process)
-    ML4CA_REQUIRE(device >= 0 && device < 64, "device index out of range");
-    if (blob[device] == nullptr) ML4CA_CUDA(cudaMalloc(&blob[device], sizeof(__half) * ppotc::kBlobHalves));
-    ppotc::Args t = {};
-    t.params = a.params, t.obs = a.obs, t.act = a.act, t.nout = a.nout;
-    t.off_w1 = a.off_w1, t.off_b1 = a.off_b1, t.off_w2 = a.off_w2, t.off_b2 = a.off_b2, t.off_wo = a.off_wo;
-    t.off_bo = a.off_bo, t.off_ls = a.off_ls;
-    t.n = n, t.T = T;
-    t.obs_buf = obs, t.act_buf = act, t.adv = adv, t.logp_old = logp_old, t.ret = ret;
-    t.clip = clip_ratio, t.grad = grad, t.stats = stats;
-    return ml4ca_ppo_grad_tc_launch(t, cfg.activation, net, blob[device], st);
+    __half* blob = nullptr;
+    rc = tc_blob(device, &blob);
+    if (rc != ML4CA_OK) return rc;
+    return ml4ca_ppo_grad_tc_launch(tc_args(a), cfg.activation, net, blob, st);
   }
   return ppo_launch_fp32(a, cfg.activation, net, st);
 }
@@ -605,6 +627,12 @@ int ml4ca_trpo_policy_mu(ml4ca_policy* p, int64_t n, int32_t T, const float* obs
   int rc = ppo_args(p, 0, n, T, "ml4ca_trpo_policy_mu", &a, &cfg, &device);
   if (rc != ML4CA_OK) return rc;
   a.obs_buf = obs, a.mu_out = mu;
+  if (g_trpo_tc && ((n + ppo::TS - 1) / ppo::TS) * T > 0) {
+    __half* blob = nullptr;
+    rc = tc_blob(device, &blob);
+    if (rc != ML4CA_OK) return rc;
+    return ml4ca_ppo_grad_tc_launch(tc_args(a), cfg.activation, 0, blob, static_cast<cudaStream_t>(stream));
+  }
   return ppo_launch_fp32(a, cfg.activation, 0, static_cast<cudaStream_t>(stream));
 }
 
@@ -621,6 +649,12 @@ int ml4ca_trpo_kl_grad(ml4ca_policy* p, int64_t n, int32_t T, const float* obs, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ML4CA_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)ml4ca_policy_num_params(&cfg), st));
   ML4CA_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 8, st));
+  if (g_trpo_tc && ((n + ppo::TS - 1) / ppo::TS) * T > 0) {
+    __half* blob = nullptr;
+    rc = tc_blob(device, &blob);
+    if (rc != ML4CA_OK) return rc;
+    return ml4ca_ppo_grad_tc_launch(tc_args(a), cfg.activation, 0, blob, st);
+  }
   return ppo_launch_fp32(a, cfg.activation, 0, st);
 }
 

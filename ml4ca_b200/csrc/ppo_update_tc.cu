@@ -57,8 +57,8 @@ constexpr int OFF_BLOB = 0;
 constexpr int OFF_GROUPS = (BLOB_E * 2 + 127) & ~127;
 constexpr int OFF_TAIL = OFF_GROUPS + G * GROUP_B;             // 2 KB of zeros: spill target of the last transposed view
 constexpr int OFF_BARS = OFF_TAIL + 2048;
-constexpr int OFF_CONST = OFF_BARS + 64;                       // sd[8], inv[8], ls[8]
-constexpr int OFF_TMEM = OFF_CONST + 96;
+constexpr int OFF_CONST = OFF_BARS + 64;                       // sd[8], inv[8], ls[8], kiv[8], kls[8]
+constexpr int OFF_TMEM = OFF_CONST + 160;
 constexpr int OFF_RED = OFF_TMEM + 16;                         // double [G * 4][8]
 constexpr int SMEM_BYTES = OFF_RED + G * 4 * 8 * 8;
 
@@ -152,6 +152,8 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
       const float ls = (NET == 0 && a < nout) ? A.params[A.off_ls + a] : 0.f;
       const float sd = expf(ls);
       consts[a] = sd, consts[8 + a] = 1.0f / (sd + 1e-8f), consts[16 + a] = ls;
+      const float lo = (NET == 0 && A.loss_mode == 1 && a < nout) ? A.kl_ls_old[a] : 0.f;        // trpo/core.py:57-58
+      consts[24 + a] = 1.0f / (expf(2.0f * lo) + 1e-8f), consts[32 + a] = lo;
     }
   }
   __syncthreads();
@@ -232,9 +234,10 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
     pf_adv = pf_lpo = pf_ret = 0.f;
     if constexpr (NET == 0) {
 #pragma unroll
-      for (int a = 0; a < 8; ++a)
-        if (a < nout && live) pf_a[a] = __ldg(A.act_buf + ((int64_t)t * act_dim + a) * n + i);
-      if (live) pf_adv = __ldg(A.adv + (int64_t)t * n + i), pf_lpo = __ldg(A.logp_old + (int64_t)t * n + i);
+      for (int a = 0; a < 8; ++a)       // rows a mode does not use are NULL and read as zero (KL mode: act_buf = mu_old only)
+        if (a < nout && live && A.act_buf != nullptr) pf_a[a] = __ldg(A.act_buf + ((int64_t)t * act_dim + a) * n + i);
+      if (live && A.adv != nullptr) pf_adv = __ldg(A.adv + (int64_t)t * n + i);
+      if (live && A.logp_old != nullptr) pf_lpo = __ldg(A.logp_old + (int64_t)t * n + i);
     } else {
       if (live) pf_ret = __ldg(A.ret + (int64_t)t * n + i);
     }
@@ -328,10 +331,30 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
     float out[16];
     tmem_ld16(tD + lane_off, out);
     fence_before_sync();
+    if (A.mu_out != nullptr) {                 // forward only (uniform): store the means of this tile, next tile
+      if (live) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+          if (a < nout) A.mu_out[((int64_t)t * nout + a) * n + i] = out[a];
+      }
+      continue;
+    }
     float dout[8];
 #pragma unroll
     for (int a = 0; a < 8; ++a) dout[a] = 0.f;
-    if constexpr (NET == 0) {
+    if (NET == 0 && A.loss_mode == 1) {
+      // d_kl = mean_s sum_a 0.5 (((mu_old - mu)^2 + var) / (var_old + EPS) - 1) + log_std_old - log_std  (trpo/core.py:52-60,98)
+      double kl = 0.0;
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+        if (a < nout) {
+          const float d = out[a] - av[a], var = consts[a] * consts[a];
+          kl += (double)(0.5f * ((d * d + var) * consts[24 + a] - 1.0f) + (consts[32 + a] - consts[16 + a]));
+          dout[a] = live ? d * consts[24 + a] : 0.f;
+          dls[a] += live ? (var * consts[24 + a] - 1.0f) : 0.f;
+        }
+      if (live) st[2] += kl;
+    } else if constexpr (NET == 0) {
       float logp = 0.f, z[8];
 #pragma unroll
       for (int a = 0; a < 8; ++a) {
@@ -480,7 +503,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
     for (int off = 16; off >= 1; off >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, off);
     if (lane == 0 && r != 0.0) atomicAdd(A.stats + q, r);
   }
-  if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(A.stats + 5, (double)A.n * (double)A.T);
+  if (threadIdx.x == 0 && blockIdx.x == 0 && A.mu_out == nullptr) atomicAdd(A.stats + 5, (double)A.n * (double)A.T);
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }

@@ -7,9 +7,9 @@
   trpo()       trpo.py:95-384   training loop (shared epoch loop of ppo.run_epochs) and the reference's log columns
 
 Device work runs behind the C ABI: ml4ca_ppo_grad (surrogate: clip ratio that never binds), ml4ca_trpo_policy_mu,
-ml4ca_trpo_kl_grad (csrc/ppo_update.cu, always the fp32 kernel).  The reference builds the Hessian-vector product by
+ml4ca_trpo_kl_grad (csrc/ppo_update.cu; the fp32 kernel by default, the tensor-core one for the CG passes with kernel='tensor_core').  The reference builds the Hessian-vector product by
 double back-propagation through the TF graph (trpo/core.py:68-72); here it is a central difference of the KL gradient,
-Hx(v) = (grad d_kl(theta + e v) - grad d_kl(theta - e v)) / 2e + damping v with |e v| = fd_radius: the gradient of
+Hx(v) = (grad d_kl(theta + e v) - grad d_kl(theta - e v)) / 2e + damping v with |e v| = fd_radius (2e-3): the gradient of
 d_kl vanishes at theta_old, the difference removes the second-order term, and the result matches the exact product of
 the float64 oracle to ~1e-3 (tests/test_trpo_gpu.py; what remains are leaky-ReLU units that change branch inside the
 bracket, an error that shrinks with the radius and with the number of samples, against fp32 rounding that grows).
@@ -55,12 +55,22 @@ class TRPOUpdater(PPOUpdater):
     """The update() closure of trpo.py:283-331 for a device-resident buffer."""
 
     def __init__(self, ac, vf_lr=1e-3, train_v_iters=80, target_kl=0.01, damping_coeff=0.1, cg_iters=10,
-                 backtrack_iters=10, backtrack_coeff=0.8, algo='trpo', fd_radius=2e-3):
-        assert algo in ('trpo', 'npg')
+                 backtrack_iters=10, backtrack_coeff=0.8, algo='trpo', fd_radius=None, kernel='fp32'):
+        """kernel='fp32' (default): every policy pass of the update on the fp32 CUDA-core kernel; the Hessian-vector product
+        matches the exact one to ~1e-3.  kernel='tensor_core': the KL-gradient passes of the conjugate-gradient solve (22 of
+        the ~26 passes) on the tcgen05 kernel, ~10x faster each; its fp16 operands put ~1e-3 of rounding on the means, so the
+        central difference uses a 25x wider bracket and the product is good to a few per cent -- enough for ten CG
+        iterations (the step direction stays within ~1 degree of the fp32 one), not for line-by-line parity.  The surrogate
+        gradient, the step length's x^T H x and the line search stay on the fp32 kernel in both modes."""
+        assert algo in ('trpo', 'npg') and kernel in ('fp32', 'tensor_core')
         super().__init__(ac, clip_ratio=NO_CLIP, vf_lr=vf_lr, train_v_iters=train_v_iters, target_kl=target_kl)
         self.damping_coeff, self.cg_iters = float(damping_coeff), int(cg_iters)
         self.backtrack_iters, self.backtrack_coeff = int(backtrack_iters), float(backtrack_coeff)
-        self.algo, self.fd_radius = algo, float(fd_radius)
+        self.algo, self.kernel = algo, kernel
+        self.fd_radius = {'fp32': 2e-3, 'tensor_core': 5e-2}      # |e v| of the central difference, per kernel
+        if fd_radius is not None:
+            self.fd_radius[kernel] = float(fd_radius)
+        self._mu_tc = None          # mu_old of the tensor-core forward (its own rounding, so that d_kl(theta_old) = 0 there too)
 
     # -- device passes -------------------------------------------------------------------------------------------------
     def _pi_params(self):
@@ -84,30 +94,50 @@ class TRPOUpdater(PPOUpdater):
         g = self.flat[:self.n_pi].double().cpu().numpy() / c
         return g, -s[0] / c
 
-    def _kl(self, data, T, n):
+    def _kl(self, data, T, n, tensor_core=False):
         """-> (flat gradient of d_kl [n_pi] float64, d_kl), rank-averaged."""
         obs, log_std_old, mu_old = data[0], data[5], data[6]
         ac, P = self.ac, self.ac.num_params
-        with torch.cuda.device(ac.device):
-            _lib.check(_lib.lib().ml4ca_trpo_kl_grad(ac._handle, int(n), int(T), _lib.ptr(obs), _lib.ptr(mu_old),
-                                                     _lib.ptr(log_std_old), _lib.ptr(self.flat), _lib.ptr(self.stats),
-                                                     _lib.current_stream()), "ml4ca_trpo_kl_grad")
+        L = _lib.lib()
+        prev = L.ml4ca_trpo_use_tensor_cores(1 if tensor_core else 0)
+        try:
+            with torch.cuda.device(ac.device):
+                if tensor_core:
+                    mu_old = self._mu_tc
+                _lib.check(L.ml4ca_trpo_kl_grad(ac._handle, int(n), int(T), _lib.ptr(obs), _lib.ptr(mu_old),
+                                                _lib.ptr(log_std_old), _lib.ptr(self.flat), _lib.ptr(self.stats),
+                                                _lib.current_stream()), "ml4ca_trpo_kl_grad")
+        finally:
+            L.ml4ca_trpo_use_tensor_cores(prev)
         self.flat[P:P + 5].copy_(self.stats[:5])
         mpi_tools.allreduce_sum_(self.flat)
         c = float(T) * float(n) * mpi_tools.num_procs()
         return self.flat[:self.n_pi].double().cpu().numpy() / c, float(self.flat[P + 2].item()) / c
 
-    def hvp(self, data, T, n, theta, v):
+    def _record_mu_tc(self, data, T, n):
+        """Means of the OLD policy as the tensor-core forward computes them (called at theta_old)."""
+        obs, ac, L = data[0], self.ac, _lib.lib()
+        if self._mu_tc is None or self._mu_tc.shape != data[6].shape:
+            self._mu_tc = torch.empty_like(data[6])
+        prev = L.ml4ca_trpo_use_tensor_cores(1)
+        try:
+            with torch.cuda.device(ac.device):
+                _lib.check(L.ml4ca_trpo_policy_mu(ac._handle, int(n), int(T), _lib.ptr(obs), _lib.ptr(self._mu_tc),
+                                                  _lib.current_stream()), "ml4ca_trpo_policy_mu")
+        finally:
+            L.ml4ca_trpo_use_tensor_cores(prev)
+
+    def hvp(self, data, T, n, theta, v, tensor_core=False):
         """Damped Hessian-vector product of d_kl at theta (trpo.py:245-247) by a central difference of its gradient."""
         v = np.asarray(v, dtype=np.float64)
         norm = float(np.linalg.norm(v))
         if norm == 0.0:
             return np.zeros_like(v)
-        e = self.fd_radius / norm
+        e = self.fd_radius['tensor_core' if tensor_core else 'fp32'] / norm
         self._set_pi(theta + e * v)
-        gp, _ = self._kl(data, T, n)
+        gp, _ = self._kl(data, T, n, tensor_core)
         self._set_pi(theta - e * v)
-        gm, _ = self._kl(data, T, n)
+        gm, _ = self._kl(data, T, n, tensor_core)
         self._set_pi(theta)
         return (gp - gm) / (2.0 * e) + self.damping_coeff * v
 
@@ -132,10 +162,12 @@ class TRPOUpdater(PPOUpdater):
     def update_policy(self, data, T, n):
         """trpo.py:285-321 -> dict(LossPi, KL, DeltaLossPi[, BacktrackIters]) + internals (x, alpha, g)."""
         theta_old = self._pi_params().double().cpu().numpy()
-        Hx = lambda v: self.hvp(data, T, n, theta_old, v)
+        fast = self.kernel == 'tensor_core'
+        if fast:
+            self._record_mu_tc(data, T, n)
         g, pi_l_old = self._surrogate(data, T, n)
-        x = self.cg(Hx, g)
-        alpha = float(np.sqrt(2 * self.target_kl / (np.dot(x, Hx(x)) + EPS)))
+        x = self.cg(lambda v: self.hvp(data, T, n, theta_old, v, tensor_core=fast), g)
+        alpha = float(np.sqrt(2 * self.target_kl / (np.dot(x, self.hvp(data, T, n, theta_old, x)) + EPS)))   # fp32 always
 
         def set_and_eval(step):
             self._set_pi(theta_old - alpha * x * step)
@@ -184,7 +216,8 @@ class _InfoRecordingUpdater(object):
 
 def trpo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, target_kl=0.01, vf_lr=1e-3, train_v_iters=80,
          damping_coeff=0.1, cg_iters=10, backtrack_iters=10, backtrack_coeff=0.8, lam=0.97, seed=0, algo='trpo',
-         hidden_sizes=(64, 64), activation="leaky_relu", fused=False, logger=None, logger_kwargs=None, graph=False):
+         hidden_sizes=(64, 64), activation="leaky_relu", fused=False, logger=None, logger_kwargs=None, graph=False,
+         kernel='fp32'):
     """trpo.py:95-384 for a batched env (hyper-parameter defaults: trpo.py:95-99, train.py:86-90).  Every epoch =
     ``steps_per_epoch`` steps of EVERY environment, GAE-lambda, the TRPO (or NPG) policy step, ``train_v_iters`` value
     steps.  Returns (ac, list of per-epoch dictionaries); ``logger_kwargs`` writes progress.txt with the reference's
@@ -196,7 +229,8 @@ def trpo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, target_kl=0.01
     mpi_tools.sync_all_params(ac.parameters())    # trpo.py:257
     ac.refresh()
     buf = GAEBuffer(env.num_states, env.num_actions, steps_per_epoch, n, gamma, lam, device=dev)
-    upd = TRPOUpdater(ac, vf_lr, train_v_iters, target_kl, damping_coeff, cg_iters, backtrack_iters, backtrack_coeff, algo)
+    upd = TRPOUpdater(ac, vf_lr, train_v_iters, target_kl, damping_coeff, cg_iters, backtrack_iters, backtrack_coeff, algo,
+                      kernel=kernel)
     config = dict(steps_per_epoch=steps_per_epoch, epochs=epochs, gamma=gamma, target_kl=target_kl, vf_lr=vf_lr,
                   train_v_iters=train_v_iters, damping_coeff=damping_coeff, cg_iters=cg_iters,
                   backtrack_iters=backtrack_iters, backtrack_coeff=backtrack_coeff, lam=lam, seed=seed, algo=algo)

@@ -1,5 +1,5 @@
 """Learning check: PPO (or TRPO) on the batched RevoltFinal env for a few dozen epochs; prints the per-epoch reward.
-Usage: python tools/train_demo.py [ppo|trpo] [epochs] [num_envs] [graph]"""
+Usage: python tools/train_demo.py [ppo|trpo] [epochs] [num_envs] [graph|eager] [fp32|tensor_core]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -9,11 +9,12 @@ algo = sys.argv[1] if len(sys.argv) > 1 else "ppo"
 epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
 graph = (sys.argv[4] == "graph") if len(sys.argv) > 4 else False
+kw = dict(kernel=sys.argv[5]) if len(sys.argv) > 5 and algo == "trpo" else {}
 dev = torch.device("cuda", 0)
 env = M.RevoltFinal(M.StandInHull(), extended_state=True, cont_ang=True, num_envs=n, device=dev, seed=0, auto_reset=True)
 t0 = time.time()
 fn = M.ppo if algo == "ppo" else M.trpo
-ac, hist = fn(env, steps_per_epoch=400, epochs=epochs, seed=0, graph=graph)
+ac, hist = fn(env, steps_per_epoch=400, epochs=epochs, seed=0, graph=graph, **kw)
 torch.cuda.synchronize()
 for h in hist:
     if h["Epoch"] % max(1, epochs // 20) == 0 or h["Epoch"] == epochs - 1:
