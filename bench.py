@@ -506,16 +506,16 @@ def run_b200(args, rank, local_rank, world):
             env3 = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=ne, device=dev, seed=5,
                                auto_reset=True, env_id_offset=rank * ne)
             ac3 = M.ActorCritic(9, 7, (64, 64), "leaky_relu", device=dev, seed=5)
-            # one run of 4 epochs: the first two warm up (parameter sync, eager rollout, graph capture), the last two are timed
+            # one run of 5 epochs: the first two warm up (parameter sync, eager rollout, graph capture), the median of the last three is reported
             marks = []
 
             def mark(info):
                 torch.cuda.synchronize()
                 marks.append(time.perf_counter())
-            _, hist = M.ppo(env3, ac3, steps_per_epoch=Tp, epochs=4, seed=5, graph=True, logger=mark)
-            dt = max_over_ranks(marks[3] - marks[1]) / 2
+            _, hist = M.ppo(env3, ac3, steps_per_epoch=Tp, epochs=5, seed=5, graph=True, logger=mark)
+            dt = max_over_ranks(sorted(b - a for a, b in zip(marks[1:-1], marks[2:]))[1])     # median of the last three epochs
             hist = hist[2:]
-            passes = sum(h["StopIter"] + 1 + 80 + 2 for h in hist) / 2.0
+            passes = sum(h["StopIter"] + 1 + 80 + 2 for h in hist) / float(len(hist))
             extra["ppo_train"] = {"workload": "BASELINE configs[4]: PPO epoch = 400-step rollout of 16 Ki envs/GPU + GAE + update "
                                               "(config.json hyper-parameters: <= 80 pi + 80 v full-batch Adam iterations, target_kl 0.01), "
                                               "NCCL all-reduce of the flat gradient per iteration; rollout replayed from a CUDA graph",
@@ -538,8 +538,8 @@ def run_b200(args, rank, local_rank, world):
                 def mark4(info):
                     torch.cuda.synchronize()
                     marks.append(time.perf_counter())
-                _, hist = M.trpo(env4, ac4, steps_per_epoch=Tp, epochs=4, seed=7, graph=True, logger=mark4, kernel=kern)
-                dt = max_over_ranks(marks[3] - marks[1]) / 2
+                _, hist = M.trpo(env4, ac4, steps_per_epoch=Tp, epochs=5, seed=7, graph=True, logger=mark4, kernel=kern)
+                dt = max_over_ranks(sorted(b - a for a, b in zip(marks[1:-1], marks[2:]))[1])
                 extra[leg] = {"workload": "TRPO epoch = 400-step rollout of 16 Ki envs/GPU + GAE + update (trpo.py defaults: "
                                           "10 CG iterations on the damped Fisher-vector product, <= 10 backtracking steps, "
                                           "80 v iterations), all-reduce of every flat gradient; KL-gradient passes of the CG solve on the "
