@@ -56,3 +56,20 @@ def test_update_respects_the_trust_region_and_improves_the_surrogate():
     assert np.linalg.norm(r) < 0.5 * np.linalg.norm(out["g"])
     npg = TO.update(prob, theta, algo="npg")
     np.testing.assert_allclose(npg["theta"], theta - npg["alpha"] * npg["x"])
+
+
+def test_product_cg_equals_oracle_cg_and_solves_spd_systems():
+    """ml4ca_b200.trpo.TRPOUpdater.cg (host logic, no GPU needed) against the restatement of trpo.py:264-281 and against
+    a direct solve: n iterations of conjugate gradients solve an n x n SPD system."""
+    import types
+    from ml4ca_b200.trpo import TRPOUpdater
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(12, 12))
+    A = A @ A.T + 0.5 * np.eye(12)
+    b = rng.normal(size=12)
+    for iters in (3, 12):
+        me = types.SimpleNamespace(cg_iters=iters)
+        x_prod = TRPOUpdater.cg(me, lambda v: A @ v, b.copy())
+        x_orac = TO.cg(lambda v: A @ v, b.copy(), iters)
+        np.testing.assert_allclose(x_prod, x_orac, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(x_prod, np.linalg.solve(A, b), rtol=1e-6, atol=1e-8)
