@@ -65,7 +65,7 @@ def test_product_cg_equals_oracle_cg_and_solves_spd_systems():
     from ml4ca_b200.trpo import TRPOUpdater
     rng = np.random.default_rng(0)
     A = rng.normal(size=(12, 12))
-    A = A @ A.T + 0.5 * np.eye(12)
+    A = np.eye(12) + 0.3 * (A @ A.T) / 12.0          # well conditioned: 12 steps reach the solution in floating point
     b = rng.normal(size=12)
     for iters in (3, 12):
         me = types.SimpleNamespace(cg_iters=iters)
