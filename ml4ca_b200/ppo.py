@@ -143,25 +143,46 @@ class PPOUpdater(object):
         self.m1 = torch.zeros(P, dtype=torch.float32, device=dev)
         self.m2 = torch.zeros(P, dtype=torch.float32, device=dev)
         self.t_pi = self.t_v = 0
+        # policy loop: two (gradient, statistics) slots so that the pass of iteration i + 1 can be queued while the host is still
+        # waiting for the KL of iteration i (update())
+        self._flat2 = torch.zeros(P + 8, dtype=torch.float32, device=dev)
+        self._stats2 = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._host = [torch.zeros(5, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._events = [torch.cuda.Event() for _ in range(2)]
 
     # -- one gradient pass: returns the rank-summed statistics as a list of 5 floats and the global sample count ------
-    def _grad(self, net, data, T, n, read=True):
-        """One gradient pass.  read=False leaves the statistics on the device (no host synchronisation): (None, count)."""
+    def _slot(self, slot):
+        return (self.flat, self.stats) if slot == 0 else (self._flat2, self._stats2)
+
+    def _grad(self, net, data, T, n, read=True, slot=0):
+        """One gradient pass.  read=False leaves the statistics on the device (no host synchronisation): (None, count).
+        read='async': the five statistics are copied to a pinned host slot behind the pass and an event is recorded;
+        ``_read(slot)`` later waits for that event only, not for work queued after it."""
         obs, act, adv, ret, logp = data
         L, ac = _lib.lib(), self.ac
+        flat, stats = self._slot(slot)
         with torch.cuda.device(ac.device):
             _lib.check(L.ml4ca_ppo_grad(ac._handle, int(net), int(n), int(T), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(adv),
-                                        _lib.ptr(ret), _lib.ptr(logp), self.clip_ratio, _lib.ptr(self.flat),
-                                        _lib.ptr(self.stats), _lib.current_stream()), "ml4ca_ppo_grad")
+                                        _lib.ptr(ret), _lib.ptr(logp), self.clip_ratio, _lib.ptr(flat),
+                                        _lib.ptr(stats), _lib.current_stream()), "ml4ca_ppo_grad")
         from . import mpi_tools
         P = ac.num_params
-        self.flat[P:P + 5].copy_(self.stats[:5])
-        mpi_tools.allreduce_sum_(self.flat)
+        flat[P:P + 5].copy_(stats[:5])
+        mpi_tools.allreduce_sum_(flat)
         count = float(T) * float(n) * mpi_tools.num_procs()   # equal shards (mpi_tools.shard_bounds differ by <= 1 env)
-        return (self.flat[P:P + 5].tolist() if read else None), count
+        if read == 'async':
+            self._host[slot].copy_(flat[P:P + 5], non_blocking=True)
+            self._events[slot].record()
+            return None, count
+        return (flat[P:P + 5].tolist() if read else None), count
 
-    def _adam(self, net, count):
+    def _read(self, slot):
+        self._events[slot].synchronize()
+        return self._host[slot].tolist()
+
+    def _adam(self, net, count, slot=0):
         ac, L = self.ac, _lib.lib()
+        flat = self._slot(slot)[0]
         lo, hi = (0, self.n_pi) if net == 0 else (self.n_pi, ac.num_params)
         if net == 0:
             self.t_pi += 1
@@ -170,7 +191,7 @@ class PPOUpdater(object):
         t, lr = (self.t_pi, self.pi_lr) if net == 0 else (self.t_v, self.vf_lr)
         params = ac.parameters()
         with torch.cuda.device(ac.device):
-            _lib.check(L.ml4ca_adam_step(hi - lo, _lib.ptr(params[lo:hi]), _lib.ptr(self.flat[lo:hi]), _lib.ptr(self.m1[lo:hi]),
+            _lib.check(L.ml4ca_adam_step(hi - lo, _lib.ptr(params[lo:hi]), _lib.ptr(flat[lo:hi]), _lib.ptr(self.m1[lo:hi]),
                                          _lib.ptr(self.m2[lo:hi]), lr, 0.9, 0.999, 1e-8, t, 1.0 / count,
                                          _lib.current_stream()), "ml4ca_adam_step")
         # the fp16 operand image of the forward kernel is NOT refreshed here: the gradient kernels read the fp32 master
@@ -197,13 +218,20 @@ class PPOUpdater(object):
         data = buf.get()
         T, n = buf.max_size, buf.num_envs
         info, stop = {}, 0
+        # The KL of iteration i (ppo.py:268-271) is only known after a device -> host round trip; instead of idling the GPU for
+        # it, the Adam step of iteration i (always applied) and the gradient pass of iteration i + 1 are queued first, into
+        # the other slot.  When the test stops the loop that pass was for nothing: it changes no parameter.
+        _, c = self._grad(0, data, T, n, read='async', slot=0)
         for i in range(self.train_pi_iters):
-            s, c = self._grad(0, data, T, n)          # loss statistics belong to the parameters BEFORE this step
+            cur = i & 1
+            self._adam(0, c, slot=cur)
+            if i + 1 < self.train_pi_iters:
+                self._grad(0, data, T, n, read='async', slot=cur ^ 1)
+            s = self._read(cur)                       # loss statistics belong to the parameters BEFORE this step
             if i == 0:
                 info.update(LossPi=-s[0] / c, Entropy=s[3] / c)
-            self._adam(0, c)
             stop = i
-            if s[2] / c > 1.5 * self.target_kl:       # kl = mpi_avg(kl), :268-271 (the step of this iteration is applied)
+            if s[2] / c > 1.5 * self.target_kl:       # kl = mpi_avg(kl): the step of this iteration has been applied
                 break
         info["StopIter"] = stop
         self._update_v(data, T, n, info)
