@@ -247,7 +247,7 @@ ML4CA_API int ml4ca_ppo_use_fp32(int enable);
  * ml4ca_trpo_policy_mu: the distribution "info" the reference's GAEBuffer stores per step (trpo.py:300): mu [T, act_dim, n]
  * of obs [T, obs_dim, n] at the current parameters (log_std is state-independent: the caller copies it from the parameters). */
 /* enable = 1 runs the two TRPO passes on the tensor-core gradient kernel (fp16 operands: the Hessian-vector product then needs a
- * wider central-difference bracket and is good to a few per cent, see ml4ca_b200/trpo.py); 0 = the fp32 kernel (default),
+ * wider central-difference bracket and matches the exact one to 0.2-0.3 % instead of 0.02 %, see ml4ca_b200/trpo.py); 0 = the fp32 kernel (default),
  * -1 only queries; returns the previous setting. */
 ML4CA_API int ml4ca_trpo_use_tensor_cores(int enable);
 ML4CA_API int ml4ca_trpo_policy_mu(ml4ca_policy* p, int64_t n, int32_t T, const float* obs, float* mu, void* stream);

@@ -151,8 +151,8 @@ def test_training_run_and_log_columns(cuda_device, tmp_path, algo):
 
 def test_tensor_core_kernel_option(cuda_device):
     """TRPOUpdater(kernel='tensor_core'): the KL-gradient passes of the CG solve on the tcgen05 kernel.  Stated accuracy: the
-    Hessian-vector product within 6 % of the exact one, the step direction within ~2.5 degrees (cosine > 0.999 would be the
-    fp32 path), the update still inside the KL budget and improving the surrogate."""
+    Hessian-vector product within 2 % of the exact one (measured 0.2-0.3 %, tools/trpo_margins.py), step direction cosine
+    > 0.998 (measured 0.9997-0.9999), step length within 2 %, the update inside the KL budget and improving the surrogate."""
     import ml4ca_b200 as M
     T, n = 4, 8192
     ac, data, prob, theta, mu64 = _setup(cuda_device, T, n, seed=2)
@@ -168,10 +168,10 @@ def test_tensor_core_kernel_option(cuda_device):
     g64, _ = prob.gradient(theta)
     h = upd.hvp(full, T, n, theta, g64, tensor_core=True)
     h64 = prob.hvp(theta, g64, damping=0.1)
-    assert np.linalg.norm(h - h64) < 6e-2 * np.linalg.norm(h64)
+    assert np.linalg.norm(h - h64) < 2e-2 * np.linalg.norm(h64)
     ref = TO.update(prob, theta)
     info = upd.update_policy(full, T, n)
     x, x64 = upd.last["x"], ref["x"]
-    assert np.dot(x, x64) / (np.linalg.norm(x) * np.linalg.norm(x64)) > 0.99
-    assert abs(upd.last["alpha"] / ref["alpha"] - 1) < 0.1
+    assert np.dot(x, x64) / (np.linalg.norm(x) * np.linalg.norm(x64)) > 0.998
+    assert abs(upd.last["alpha"] / ref["alpha"] - 1) < 0.02
     assert info["KL"] <= 0.01 and info["DeltaLossPi"] < 0
