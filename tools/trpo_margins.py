@@ -1,5 +1,8 @@
-import sys, numpy as np, torch
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+"""Measured distance of the TRPO update to the float64 oracle for both kernels (Hessian-vector product, CG direction, step
+length, KL, line-search index) on the batches of tests/test_trpo_gpu.py.  Tuning / evidence tool."""
+import os, sys, numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import test_trpo_gpu as TT
 from oracle import trpo_oracle as TO
 import ml4ca_b200 as M
