@@ -83,6 +83,14 @@ ML4CA_API int ml4ca_env_reset(ml4ca_env* env, const uint8_t* mask, float fractio
  * eta [3, n] = N, E, yaw; nu [3, n] = u, v, r. */
 ML4CA_API int ml4ca_env_reset_to(ml4ca_env* env, const uint8_t* mask, const float* eta, const float* nu, float* obs,
                        void* stream);
+/* Side buffer for the value bootstrap at the episode-length cut (ppo.py:303-311: `last_val = 0 if d else v(o)` on the
+ * observation o2 that env.step returned).  With auto_reset the in-kernel restart replaces that observation in the step's
+ * output; cut_obs [obs_dim, n] (caller-owned device memory, NULL = off) receives it instead, for the envs whose flag byte
+ * is exactly ML4CA_DONE_TRUNCATED; other columns are left untouched.  Used by ml4ca_env_step and ml4ca_rollout_step. */
+ML4CA_API int ml4ca_env_set_cut_obs(ml4ca_env* env, float* cut_obs);
+/* The `fraction` every later in-kernel restart samples with (curriculum learning, ppo.py:286,319-322: the reference passes
+ * it to each env.reset).  Launch parameter: CUDA graphs captured earlier keep the value they were captured with. */
+ML4CA_API int ml4ca_env_set_reset_fraction(ml4ca_env* env, float fraction);
 /* ErrorFrame.update(ref=new_ref) (errorFrame.py:34-38; customEnv.py:131,155-156): ref [3, n]. */
 ML4CA_API int ml4ca_env_set_ref(ml4ca_env* env, const float* ref, void* stream);
 /* Revolt.step(action) (customEnv.py:92-133): action [act_dim, n] -> obs [obs_dim, n], rew [n], done [n] flags. */
@@ -126,9 +134,23 @@ ML4CA_API int ml4ca_pinv_allocate(int64_t n, const float* tau, float* n_pct, flo
  * previous thruster state [f_port, f_star, f_bow, a_port, a_star] -> x [8, n] = [f(3), a(2), s(3)] after the
  * |x| < 0.01 clean-up (:232), status [n]: bit 0 = success (the reference's second return value; on failure the
  * caller holds the previous state, :267-269), bits 1..16 = active set at x (bits 1-5 z_i at its lower effective
- * bound, 6-10 upper, 11-13 s_i = -1, 14-16 s_i = +1), bits 24..31 = SQP iterations.  Never fails on infeasible
- * demands: it reports success = 0, like the reference. */
+ * bound, 6-10 upper, 11-13 s_i = -1, 14-16 s_i = +1), bits 17..20 = SLSQP exit mode (0 success, 4 incompatible
+ * constraints, 8 positive directional derivative, 9 iteration limit), bits 24..31 = major iterations.  The solver
+ * follows SLSQP's own path (csrc/qp_slsqp.cuh), in float64: same local minimum, same stopping iteration, same flag as the
+ * reference.  Never fails on infeasible demands: it reports success = 0, like the reference. */
 ML4CA_API int ml4ca_qp_solve(int64_t n, const float* tau, const float* prev, float* x, uint32_t* status, void* stream);
+/* The objective switches of solve_QP(tau_d, weight_matrix, reduce_fuel, reduce_flickering, reduce_angular) (:108,116-150).
+ * weights = diagonal of Q over obj = [s(3), fuel term (3), |a - a_prev| (2), |f - f_prev| (3)]; a term that is switched
+ * off (reduce_angular / reduce_flickering = False) has weight 0.  Reference default (:138-148): 1,1,1, 1,1,1, .25,.25,
+ * .25,.25,.25.  reduce_fuel = 0 replaces |f|^1.5 by f (:128-131).  raw = 1 skips the |x| < 0.01 clean-up (diagnostics). */
+typedef struct ml4ca_qp_options {
+  float weights[11];
+  int32_t reduce_fuel;
+  int32_t raw;
+} ml4ca_qp_options;
+ML4CA_API int ml4ca_qp_options_default(ml4ca_qp_options* opt);
+ML4CA_API int ml4ca_qp_solve_ex(int64_t n, const float* tau, const float* prev, const ml4ca_qp_options* opt /* NULL = default */,
+                                float* x, uint32_t* status, void* stream);
 /* QPTA.tau_controller_callback_func (:247-320): solve + post-processing + state update.  prev [5, n] is updated
  * in place to [F, mapToPi(alpha)] (held where the solve failed); out [7, n] = thrust percent n_port, n_star, n_bow
  * (n = sign(F/K) sqrt(|F/K|), :284-288), azimuths a_port, a_star, a_bow in rad mapped to [-pi, pi) (:276-277), bow
@@ -180,9 +202,12 @@ ML4CA_API int ml4ca_rollout_step(ml4ca_env* env, ml4ca_policy* p, uint64_t seed,
 
 /* TrajectoryBuffer.finish_path for every environment (ppo.py:65-91; core.discount_cumsum core.py:48-63):
  * rew [T, n], val [T + 1, n] (row T = bootstrap values at the buffer end, ppo.py:311), done [T, n] flag bytes
- * (nullable), boot [T, n] (nullable) = V(s_{t+1}) at episode-length cuts -> adv [T, n], ret [T, n]. */
+ * (nullable) -> adv [T, n], ret [T, n].  boot [ceil(T / boot_window), n] (nullable): `last_val = v(o)` of ppo.py:311 at
+ * an episode-length cut inside the buffer, i.e. V of the observation the env returned AT the cut (ml4ca_env_set_cut_obs);
+ * a cut at step t reads row t / boot_window.  Two cuts of one env are >= max_ep_len steps apart, so boot_window =
+ * max_ep_len keeps one row per window; boot_window = 1 is the plain [T, n] layout.  boot = NULL: V(s_t) stands in. */
 ML4CA_API int ml4ca_gae(int64_t n, int32_t T, const float* rew, const float* val, const uint8_t* done, const float* boot,
-                        float gamma, float lam, float* adv, float* ret, void* stream);
+                        int32_t boot_window, float gamma, float lam, float* adv, float* ret, void* stream);
 /* mpi_statistics_scalar (mpi_tools.py:71-93), local part: out3 (device, 3 doubles) = [sum, sum of squares, count]. */
 ML4CA_API int ml4ca_stats(int64_t m, const float* x, double* out3, void* stream);
 /* ... with_min_and_max=True: out5 (device, 5 doubles) = [sum, sum of squares, count, min, max] (min / max = +-1e300 if empty). */

@@ -33,6 +33,11 @@ class PolicyCfg(ctypes.Structure):
                 ("n_hidden", ctypes.c_int32), ("activation", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
+class QpOptions(ctypes.Structure):
+    """struct ml4ca_qp_options"""
+    _fields_ = [("weights", ctypes.c_float * 11), ("reduce_fuel", ctypes.c_int32), ("raw", ctypes.c_int32)]
+
+
 class Ml4caError(RuntimeError):
     pass
 
@@ -46,6 +51,8 @@ _SIGNATURES = {
     "ml4ca_env_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "ml4ca_env_reset": (ctypes.c_int, [ctypes.c_void_p, c_u8p, ctypes.c_float, c_f32p, c_stream]),
     "ml4ca_env_reset_to": (ctypes.c_int, [ctypes.c_void_p, c_u8p, c_f32p, c_f32p, c_f32p, c_stream]),
+    "ml4ca_env_set_cut_obs": (ctypes.c_int, [ctypes.c_void_p, c_f32p]),
+    "ml4ca_env_set_reset_fraction": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float]),
     "ml4ca_env_set_ref": (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_stream]),
     "ml4ca_env_step": (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_u8p, c_stream]),
     "ml4ca_env_observe": (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_stream]),
@@ -57,6 +64,8 @@ _SIGNATURES = {
     "ml4ca_pinv_pid": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_stream]),
     "ml4ca_pinv_allocate": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_stream]),
     "ml4ca_qp_solve": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, ctypes.c_void_p, c_stream]),
+    "ml4ca_qp_options_default": (ctypes.c_int, [ctypes.POINTER(QpOptions)]),
+    "ml4ca_qp_solve_ex": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, ctypes.POINTER(QpOptions), c_f32p, ctypes.c_void_p, c_stream]),
     "ml4ca_qp_allocate": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, ctypes.c_void_p, c_stream]),
     "ml4ca_policy_num_params": (ctypes.c_int64, [ctypes.POINTER(PolicyCfg)]),
     "ml4ca_policy_create": (ctypes.c_int, [ctypes.POINTER(PolicyCfg), ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
@@ -68,7 +77,7 @@ _SIGNATURES = {
     "ml4ca_policy_set_step_counter": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "ml4ca_rollout_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32,
                                           c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_stream]),
-    "ml4ca_gae": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_u8p, c_f32p, ctypes.c_float, ctypes.c_float,
+    "ml4ca_gae": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_u8p, c_f32p, ctypes.c_int32, ctypes.c_float, ctypes.c_float,
                                  c_f32p, c_f32p, c_stream]),
     "ml4ca_stats": (ctypes.c_int, [ctypes.c_int64, c_f32p, ctypes.c_void_p, c_stream]),
     "ml4ca_stats5": (ctypes.c_int, [ctypes.c_int64, c_f32p, ctypes.c_void_p, c_stream]),
@@ -102,11 +111,11 @@ def lib():
         if "ML4CA_LIB" not in os.environ:
             # building is not a fallback: the same sm_100a sources, compiled when the library is absent or older than
             # them (nvcc cross-compiles without a GPU; a no-op when the stamp matches)
+            from . import build as _build
             try:
-                from . import build as _build
                 _build.build()
-            except Exception:  # noqa: BLE001 -- no nvcc here: use the library that travelled with the tree, if any
-                pass
+            except FileNotFoundError:   # no nvcc on this box: use the library that travelled with the tree, if any
+                pass                    # (compile / link failures propagate: a stale .so must not load silently)
         if not os.path.exists(LIB_PATH):
             raise Ml4caError(
                 "libml4ca_b200.so is missing (%s). Build it with `python -m ml4ca_b200.build`; "

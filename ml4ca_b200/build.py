@@ -54,6 +54,18 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
         LIB = os.path.join(HERE, out)
         STAMP = LIB + ".stamp"
         force = True
+    # one builder at a time: under torchrun every rank may get here at once and would write the same .o / .so / stamp files
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose, extra_flags, out)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose, extra_flags, out):
+    global LIB, STAMP
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:

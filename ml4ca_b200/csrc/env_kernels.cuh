@@ -7,8 +7,10 @@
 //
 // Data layout in HBM: struct-of-arrays fp32, one row per state component, row length n_env:
 //   eta[3] nu[3] ref[3] prev_thrust[3] angles[3]  +  int32 ep_len, episode
-// One thread owns VEC consecutive environments (VEC = 4 -> every row access is one 128-bit, fully coalesced
-// LDG/STG; a warp touches 512 contiguous bytes per row).  There is no reuse between environments, so nothing is
+// One thread owns VEC consecutive environments.  The shipped default is VEC = 2: every row access is one 64-bit, fully
+// coalesced LDG/STG (a warp touches 256 contiguous bytes per row) and the pair of envs runs the hull sub-steps on the
+// packed FP32 pipe (FFMA2, integrate_hull2); VEC = 4 (128-bit rows) and VEC = 1 (unaligned batches) are also
+// instantiated (env_step_inst.cu picks).  There is no reuse between environments, so nothing is
 // staged through shared memory here; the kernel streams 177 algorithmic bytes per env-step (RevoltFinal,
 // extended state, continuous angles: read 60 state + 28 action, write 48 state + 36 obs + 4 rew + 1 done).
 // Grid: enough 256-thread CTAs to cover n_env, rounded so that the last wave is full where possible.
@@ -36,6 +38,8 @@ struct EnvParams {
   float* prev_thrust;  // [3, n]
   float* angles;       // [3, n] bow, port, star
   float* obs_tail;     // [3, n] tail (prev_thrust / 100) of the last returned observation; fused rollout only
+  float* cut_obs;      // [obs_dim, n] caller-owned, nullable (ml4ca_env_set_cut_obs): the observation an env returned at its
+                       // episode-length cut, saved before the in-kernel restart replaces it (ppo.py:311 evaluates V on it)
   int32_t* ep_len;     // [n] episode word: episode counter << 16 | steps in this episode (env_math.cuh)
   int64_t n;
   float bounds[6];
@@ -269,6 +273,10 @@ __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : (VEC ==
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       if (flags[j] == 0u) continue;
+      if (flags[j] == ML4CA_DONE_TRUNCATED && p.cut_obs != nullptr) {   // o2 of ppo.py:293 at the cut: the bootstrap input
+#pragma unroll
+        for (int c = 0; c < (EXT ? 9 : 6); ++c) p.cut_obs[(int64_t)c * n + i0 + j] = o[c][j];
+      }
       sample_reset(p.seed, p.env_off + i0 + j, ep[j], p.reset_scale, eta[0][j], eta[1][j], eta[2][j], nu[0][j],
                    nu[1][j], nu[2][j]);
       ang[0][j] = T::DEF_BOW, ang[1][j] = T::DEF_PORT, ang[2][j] = T::DEF_STAR;

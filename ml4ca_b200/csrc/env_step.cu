@@ -89,6 +89,7 @@ static int launch_step(const ml4ca_env* e, int64_t first, int64_t count, int64_t
   EnvParams p = e->p;
   p.eta += first, p.nu += first, p.ref += first, p.prev_thrust += first, p.angles += first, p.obs_tail += first;
   p.ep_len += first;
+  if (p.cut_obs != nullptr) p.cut_obs += first;
   p.env_off += first;
   p.count = count;
   p.io_stride = io_stride;
@@ -208,6 +209,7 @@ int ml4ca_env_create(const ml4ca_env_cfg* cfg, int64_t n_env, int32_t device, ml
   p.angles = f + 12 * n_env;
   p.obs_tail = f + 15 * n_env;
   p.ep_len = reinterpret_cast<int32_t*>(f + 18 * n_env);
+  p.cut_obs = nullptr;
   p.n = n_env;
   for (int i = 0; i < 6; ++i) p.bounds[i] = cfg->ss_bounds[i];
   make_reset_scale(*cfg, cfg->reset_fraction, p.reset_scale);
@@ -263,6 +265,20 @@ int ml4ca_env_reset_to(ml4ca_env* env, const uint8_t* mask, const float* eta, co
   return launch_reset(env, env->p, mask, eta, nu, obs, static_cast<cudaStream_t>(stream));
 }
 
+int ml4ca_env_set_cut_obs(ml4ca_env* env, float* cut_obs) {
+  ML4CA_REQUIRE(env != nullptr, "env is NULL");
+  env->p.cut_obs = cut_obs;
+  return ML4CA_OK;
+}
+
+int ml4ca_env_set_reset_fraction(ml4ca_env* env, float fraction) {
+  ML4CA_REQUIRE(env != nullptr, "env is NULL");
+  ML4CA_REQUIRE(fraction >= 0.f, "fraction must be non-negative");
+  env->cfg.reset_fraction = fraction;
+  make_reset_scale(env->cfg, fraction, env->p.reset_scale);
+  return ML4CA_OK;
+}
+
 int ml4ca_env_set_ref(ml4ca_env* env, const float* ref, void* stream) {
   ML4CA_REQUIRE(env != nullptr && ref != nullptr, "env and ref are required");
   DeviceGuard guard(env->device);
@@ -296,7 +312,9 @@ int ml4ca_env_step_host(ml4ca_env* env, const float* action_host, float* obs_hos
     ML4CA_REQUIRE(hp != nullptr, "out of host memory");
     static const int64_t chunk_pref = [] {   // tuning knob: envs per pipeline chunk
       const char* e = getenv("ML4CA_HOST_CHUNK");
-      return e ? (int64_t)atoll(e) : (int64_t)1 << 20;
+      int64_t c = e ? (int64_t)atoll(e) : (int64_t)1 << 20;
+      if (c < 4) c = (int64_t)1 << 20;          // 0 / negative / garbage: the loop below would never advance
+      return (c + 3) / 4 * 4;                   // rows of a chunk stay 16-byte aligned
     }();
     hp->chunk = n < chunk_pref ? ((n + 3) / 4) * 4 : chunk_pref;
     const size_t per_slot = (size_t)hp->chunk * ((size_t)(act_dim + obs_dim + 1) * sizeof(float) + 1) + 64;

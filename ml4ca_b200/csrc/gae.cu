@@ -7,8 +7,9 @@
 // Batched form: one thread per environment scans its column backwards; the per-step flag byte written by the env
 // kernels (bit 0 terminal, bit 1 episode-length cut) marks the path ends inside the buffer:
 //     terminal  -> last_val = 0
-//     cut       -> last_val = boot[t] if given, else V_t  (the reference evaluates V on the post-step observation;
-//                  with in-kernel restarts that observation is gone, so V of the last observed state stands in)
+//     cut       -> last_val = boot[t / boot_window] = V(o_{t+1}) of the observation the env returned at the cut
+//                  (ppo.py:311; the env kernels save that observation before an in-kernel restart replaces it,
+//                  ml4ca_env_set_cut_obs).  Only without a boot buffer does V_t stand in.
 //     buffer end-> last_val = val[T]  (row T of the value buffer: the epoch-end bootstrap)
 // HBM-bound: 17 algorithmic bytes per (step, env): read r, V, flag; write A, R.  Coalesced across environments.
 #include "common.h"
@@ -17,7 +18,7 @@ namespace ml4ca {
 
 __global__ void __launch_bounds__(256) gae_kernel(int64_t n, int T, const float* __restrict__ rew,
                                                   const float* __restrict__ val, const uint8_t* __restrict__ done,
-                                                  const float* __restrict__ boot, float gamma, float lam,
+                                                  const float* __restrict__ boot, int boot_window, float gamma, float lam,
                                                   float* __restrict__ adv, float* __restrict__ ret) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -32,7 +33,7 @@ __global__ void __launch_bounds__(256) gae_kernel(int64_t n, int T, const float*
     if (f & ML4CA_DONE_TERMINAL) {
       next_val = 0.f, next_adv = 0.f, next_ret = 0.f;
     } else if (f & ML4CA_DONE_TRUNCATED) {
-      next_val = boot != nullptr ? boot[k] : v;
+      next_val = boot != nullptr ? boot[(int64_t)(t / boot_window) * n + i] : v;
       next_adv = 0.f, next_ret = next_val;
     }
     const float delta = r + gamma * next_val - v;      // ppo.py:86
@@ -170,11 +171,12 @@ using namespace ml4ca;
 extern "C" {
 
 int ml4ca_gae(int64_t n, int32_t T, const float* rew, const float* val, const uint8_t* done, const float* boot,
-              float gamma, float lam, float* adv, float* ret, void* stream) {
+              int32_t boot_window, float gamma, float lam, float* adv, float* ret, void* stream) {
   ML4CA_REQUIRE(n >= 0 && T >= 0 && rew && val && adv && ret, "bad arguments");
+  ML4CA_REQUIRE(boot == nullptr || boot_window >= 1, "boot_window must be >= 1 when boot is given");
   if (n == 0 || T == 0) return ML4CA_OK;
-  gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, T, rew, val, done, boot, gamma,
-                                                                                       lam, adv, ret);
+  gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      n, T, rew, val, done, boot, boot_window < 1 ? 1 : boot_window, gamma, lam, adv, ret);
   return check_launch("gae_kernel");
 }
 

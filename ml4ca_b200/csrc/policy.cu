@@ -544,6 +544,11 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
           const uint32_t flags = (term ? ML4CA_DONE_TERMINAL : 0u) | (trunc ? ML4CA_DONE_TRUNCATED : 0u);
           float npt[3] = {thrust[0], thrust[1], thrust[2]};
           if (ep.auto_reset && flags != 0u) {
+            if (flags == ML4CA_DONE_TRUNCATED && ep.cut_obs != nullptr) {   // o2 of ppo.py:293 at the cut (ppo.py:311)
+              const float co[9] = {xb, yb, pb, eu, ev, er, div100(pth[0]), div100(pth[1]), div100(pth[2])};
+#pragma unroll
+              for (int c = 0; c < 9; ++c) ep.cut_obs[(int64_t)c * ep.n + env] = co[c];
+            }
             sample_reset(ep.seed, ep.env_off + env, epl, ep.reset_scale, eN, eE, ePsi, eu, ev, er);
             npt[0] = npt[1] = npt[2] = 0.f;
             if (ep.reset_acts) sample_reset_thrust(ep.seed, ep.env_off + env, epl, npt);   // customEnv.py:179-188

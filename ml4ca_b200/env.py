@@ -188,6 +188,7 @@ class Revolt(object):
         self._obs = torch.empty(self.num_states, n, dtype=torch.float32, device=self.device)
         self._rew = torch.empty(n, dtype=torch.float32, device=self.device)
         self._done = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self._has_reset = False          # self._obs holds nothing until the first reset()
         self.EF = _EnvErrorFrame(self)
 
     # -- per-class tables (customEnv.py:58-65); subclasses override --------------------------------
@@ -256,6 +257,7 @@ class Revolt(object):
                                                  _lib.ptr(done), self._stream()), "ml4ca_env_step")
         if new_ref is not None:
             self.EF.update(ref=new_ref)   # :131
+        self._obs = obs                   # the observation of "the last reset() / step()" (rollout(), masked reset())
         info = {'None': 0, 'flags': done}
         d = (done & 1).bool()
         if flat:
@@ -308,7 +310,9 @@ class Revolt(object):
             else:
                 _lib.check(_lib.lib().ml4ca_env_reset(self._handle, _lib.ptr(m), float(fraction), _lib.ptr(obs),
                                                       self._stream()), "ml4ca_env_reset")
-        out = obs.clone()
+        if m is None:
+            self._has_reset = True
+        out = obs.clone()                 # columns outside `mask` keep the observation of the last step()
         if self.num_envs == 1 and (as_numpy or bool(init)):
             return out.reshape(-1).cpu().numpy().astype(np.float64)
         return out.cpu().numpy().astype(np.float64) if as_numpy else out
@@ -323,6 +327,11 @@ class Revolt(object):
         self._ref = r.expand(3, self.num_envs).contiguous()
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().ml4ca_env_set_ref(self._handle, _lib.ptr(self._ref), self._stream()))
+
+    def set_reset_fraction(self, fraction):
+        """The ``fraction`` in-kernel restarts sample with (auto_reset; the reference passes it per reset, ppo.py:319-322)."""
+        self._cfg.reset_fraction = float(fraction)
+        _lib.check(_lib.lib().ml4ca_env_set_reset_fraction(self._handle, float(fraction)), "ml4ca_env_set_reset_fraction")
 
     def observe(self):
         """state() / state_extended() (customEnv.py:196-205) of the current device-side state."""

@@ -18,9 +18,14 @@ class TrajectoryBuffer(object):
     step writes contiguous rows.  ``val`` has T + 1 rows: row T holds the bootstrap values V(s_T)
     (ppo.py:311)."""
 
-    def __init__(self, obs_dim, act_dim, size, num_envs, gamma=0.99, lam=0.95, device=None):
+    def __init__(self, obs_dim, act_dim, size, num_envs, gamma=0.99, lam=0.95, device=None, max_ep_len=None):
         self.device = torch.device(device if device is not None else "cuda")
         T, n = int(size), int(num_envs)
+        # ppo.py:303-311 inside the buffer: `last_val = v(o)` at an episode-length cut.  Two cuts of one env are at least
+        # max_ep_len steps apart, so one bootstrap row per window of (at most) max_ep_len steps is enough (ml4ca_gae,
+        # boot_window).  Without max_ep_len here, rollout() sizes the rows from the env it is given.
+        self.boot_window = min(int(max_ep_len), T) if max_ep_len else None
+        windows = (T + self.boot_window - 1) // self.boot_window if self.boot_window else 0
         f = dict(dtype=torch.float32, device=self.device)
         self._obs_rows = torch.zeros(T + 1, obs_dim, n, **f)   # row t = observation the policy acts on at step t; row T =
         self.obs_buf = self._obs_rows[:T]                      # the observation after the last step (no per-step copy)
@@ -31,19 +36,29 @@ class TrajectoryBuffer(object):
         self.val_buf = torch.zeros(T + 1, n, **f)
         self.logp_buf = torch.zeros(T, n, **f)
         self.done_buf = torch.zeros(T, n, dtype=torch.uint8, device=self.device)
+        self.cut_obs = torch.zeros(obs_dim, n, **f)            # observation returned at the cut (ml4ca_env_set_cut_obs)
+        self.boot_buf = torch.zeros(windows, n, **f) if windows else None   # V(cut_obs), one row per window
+        self._scratch = (torch.empty(act_dim, n, **f), torch.empty(n, **f))   # unused outputs of the bootstrap forward
         self.gamma, self.lam = gamma, lam
         self.ptr, self.max_size, self.num_envs = 0, T, n
         self._sums = torch.zeros(3, dtype=torch.float64, device=self.device)
 
-    def finish_path(self, last_val=None, boot=None):
+    def finish_path(self, last_val=None, boot="buffer", boot_window=None):
         """ppo.py:65-91 for every environment at once: GAE-lambda advantages and rewards-to-go, with the path ends
-        taken from the recorded done flags.  ``last_val`` [n] = V(s_T) for the epoch-end bootstrap (ppo.py:311);
-        by default row T of ``val_buf`` as left by the caller."""
+        taken from the recorded done flags.  ``last_val`` [n] = V(o_T) for the epoch-end bootstrap (ppo.py:311);
+        by default row T of ``val_buf`` as left by the caller.  ``boot`` = V of the observation returned at
+        episode-length cuts inside the buffer: by default ``boot_buf`` as filled by rollout(); a [T, n] tensor with
+        boot_window=1; None = the V(s_t) stand-in."""
         if last_val is not None:
             self.val_buf[self.max_size].copy_(last_val)
+        if isinstance(boot, str):
+            boot, boot_window = self.boot_buf, self.boot_window     # None before the first rollout(): V(s_t) stands in
+        elif boot is not None and boot_window is None:
+            boot_window = 1
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().ml4ca_gae(self.num_envs, self.max_size, _lib.ptr(self.rew_buf), _lib.ptr(self.val_buf),
-                                            _lib.ptr(self.done_buf), _lib.ptr(boot), float(self.gamma), float(self.lam),
+                                            _lib.ptr(self.done_buf), _lib.ptr(boot), int(boot_window or 1),
+                                            float(self.gamma), float(self.lam),
                                             _lib.ptr(self.adv_buf), _lib.ptr(self.ret_buf), _lib.current_stream()),
                        "ml4ca_gae")
 
@@ -65,12 +80,23 @@ def _rollout_launches(env, ac, buf, seed, start_step, deterministic, fused):
     L = _lib.lib()
     T, n = buf.max_size, env.num_envs
     stream = _lib.current_stream()
+    W = buf.boot_window
+
+    def bootstrap_window(t):
+        # ppo.py:311 for the cuts of the window that step t closes: V of the observations the env kernels saved into
+        # buf.cut_obs.  One extra forward per max_ep_len steps; columns without a cut hold stale values nobody reads.
+        if (t + 1) % W == 0 or t == T - 1:
+            _lib.check(L.ml4ca_policy_forward(ac._handle, n, _lib.ptr(buf.cut_obs), seed & 0xFFFFFFFFFFFFFFFF, 0, 1,
+                                              env._cfg.env_id_offset, _lib.ptr(buf._scratch[0]), _lib.ptr(buf.boot_buf[t // W]),
+                                              _lib.ptr(buf._scratch[1]), None, stream), "ml4ca_policy_forward")
+
     if fused:
         for t in range(T):
             _lib.check(L.ml4ca_rollout_step(env._handle, ac._handle, seed & 0xFFFFFFFFFFFFFFFF, start_step + t,
                                             int(bool(deterministic)), _lib.ptr(buf.obs_buf[t]), _lib.ptr(buf.act_buf[t]),
                                             _lib.ptr(buf.rew_buf[t]), _lib.ptr(buf.val_buf[t]), _lib.ptr(buf.logp_buf[t]),
                                             _lib.ptr(buf.done_buf[t]), stream), "ml4ca_rollout_step")
+            bootstrap_window(t)
         return
     rows = buf._obs_rows     # row t = observation acted on at step t; the env kernel writes row t + 1 directly (no per-step copy)
     for t in range(T):
@@ -79,6 +105,7 @@ def _rollout_launches(env, ac, buf, seed, start_step, deterministic, fused):
                                           _lib.ptr(buf.val_buf[t]), _lib.ptr(buf.logp_buf[t]), None, stream),
                    "ml4ca_policy_forward")
         env.step_into(buf.act_buf[t], rows[t + 1], buf.rew_buf[t], buf.done_buf[t])
+        bootstrap_window(t)
 
 
 def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, fused=False, graph=False):
@@ -90,17 +117,31 @@ def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, fused=False
     for small and medium batches the rollout is launch-bound (2T launches through ctypes); the Philox step number then comes
     from a device counter (ml4ca_policy_set_step_counter) that is set to ``start_step`` before every replay, so a graph
     rollout draws exactly the noise of the eager one.  The first call runs eagerly (it also initialises the kernels).
-    The env must have auto_reset=True (finished episodes restart in-kernel).
+    The env must have auto_reset=True (finished episodes restart in-kernel) and must have been reset: both are checked.
+    The observations returned at episode-length cuts go to ``buf.cut_obs`` and their values to ``buf.boot_buf``
+    (ppo.py:311), window by window.
     Returns the observation after the last step (for the bootstrap value); None on the fused path.
     """
     T = buf.max_size
+    if not env._cfg.auto_reset:
+        raise ValueError("rollout() steps every env T times without looking at `done`: the env must be created with "
+                         "auto_reset=True (the reference's caller resets at ppo.py:322; here the kernel does)")
+    if not getattr(env, "_has_reset", False):
+        raise RuntimeError("rollout() before reset(): the env holds no observation yet")
+    if buf.boot_window is None or buf.boot_window > env.max_ep_len:   # at most one cut per env and window
+        buf.boot_window = min(int(env.max_ep_len), T)
+        buf.boot_buf = torch.zeros((T + buf.boot_window - 1) // buf.boot_window, env.num_envs, dtype=torch.float32,
+                                   device=buf.device)
+        buf.__dict__.pop("_rollout_graphs", None)                     # captured graphs hold the old rows
+    _lib.check(_lib.lib().ml4ca_env_set_cut_obs(env._handle, _lib.ptr(buf.cut_obs)), "ml4ca_env_set_cut_obs")
     if not fused:
         buf._obs_rows[0].copy_(env._obs)   # observation returned by the last reset() / step()
     if not graph:
         _rollout_launches(env, ac, buf, seed, start_step, deterministic, fused)
     else:
         cache = buf.__dict__.setdefault("_rollout_graphs", {})
-        key = (id(env), id(ac), int(seed), bool(deterministic), bool(fused))
+        # launch parameters are baked into a captured graph: the restart fraction (curriculum) is part of the key
+        key = (id(env), id(ac), int(seed), bool(deterministic), bool(fused), float(env._cfg.reset_fraction))
         entry = cache.get(key)
         if entry is None:                  # first call: eager, and remember that the next one may capture
             cache[key] = {"graph": None, "counter": torch.zeros(1, dtype=torch.int32, device=buf.device)}
@@ -120,6 +161,7 @@ def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, fused=False
             v = int(start_step) & 0xFFFFFFFF                       # the kernel adds it as uint32
             entry["counter"].fill_(v - (1 << 32) if v >= (1 << 31) else v)
             entry["graph"].replay()
+    _lib.check(_lib.lib().ml4ca_env_set_cut_obs(env._handle, None))   # the launches (or the graph) hold the pointer
     if fused:
         return None
     env._obs = buf._obs_rows[T].clone()
@@ -247,12 +289,15 @@ PPO_COLUMNS = ('LossPi', 'LossV', 'DeltaLossPi', 'DeltaLossV', 'Entropy', 'KL', 
 
 def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2, pi_lr=3e-4, vf_lr=1e-3,
         train_pi_iters=80, train_v_iters=80, lam=0.97, target_kl=0.01, seed=0, hidden_sizes=(64, 64),
-        activation="leaky_relu", fused=False, logger=None, logger_kwargs=None, graph=False):
+        activation="leaky_relu", fused=False, logger=None, logger_kwargs=None, graph=False, curriculum=False,
+        reset_each_epoch=True):
     """ppo.py:107-346 for a batched env: every epoch = ``steps_per_epoch`` steps of EVERY environment of ``env``
     (rollout), GAE-lambda (finish_path), advantage normalisation over all ranks, then the PPO update.
     Hyper-parameter defaults are the reference's config.json.  ``logger_kwargs=dict(output_dir=..., exp_name=...)``
     writes progress.txt / config.json in the reference's format (ppo.py:332-346, logx.py).  ``logger`` may be a callable
-    receiving each epoch's dictionary.  Returns (ac, list of per-epoch dictionaries)."""
+    receiving each epoch's dictionary.  ``curriculum`` (ppo.py:286,319): resets sample from fraction 0 at the start,
+    min(3 epoch / epochs, 0.8) afterwards.  ``reset_each_epoch`` (ppo.py:304,322: the reference also resets the env when
+    the epoch ends).  Returns (ac, list of per-epoch dictionaries)."""
     from . import mpi_tools
     from .core import ActorCritic
     n, dev = env.num_envs, env.device
@@ -261,19 +306,23 @@ def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2,
     params = ac.parameters()
     mpi_tools.sync_all_params(params)             # ppo.py:255
     ac.refresh()
-    buf = TrajectoryBuffer(env.num_states, env.num_actions, steps_per_epoch, n, gamma, lam, device=dev)
+    buf = TrajectoryBuffer(env.num_states, env.num_actions, steps_per_epoch, n, gamma, lam, device=dev,
+                           max_ep_len=env.max_ep_len)
     upd = PPOUpdater(ac, clip_ratio, pi_lr, vf_lr, train_pi_iters, train_v_iters, target_kl)
     config = dict(steps_per_epoch=steps_per_epoch, epochs=epochs, gamma=gamma, clip_ratio=clip_ratio, pi_lr=pi_lr,
                   vf_lr=vf_lr, train_pi_iters=train_pi_iters, train_v_iters=train_v_iters, lam=lam,
                   target_kl=target_kl, seed=seed)
     return run_epochs(env, ac, buf, upd, steps_per_epoch, epochs, seed, fused, logger, logger_kwargs, config, PPO_COLUMNS,
-                      log_std_column=True, graph=graph)
+                      log_std_column=True, graph=graph, curriculum=curriculum, reset_each_epoch=reset_each_epoch)
 
 
 def run_epochs(env, ac, buf, upd, steps_per_epoch, epochs, seed, fused, logger, logger_kwargs, config, columns,
-               log_std_column=False, graph=False):
+               log_std_column=False, graph=False, curriculum=False, reset_each_epoch=True):
     """The epoch loop shared by ppo() (ppo.py:283-346) and trpo() (trpo.py:327-384): rollout of every environment,
-    bootstrap + GAE-lambda, episode / value statistics, ``upd.update(buf)``, the reference's progress.txt columns."""
+    bootstrap + GAE-lambda (cuts inside the buffer bootstrap with V of the observation returned at the cut, the buffer
+    end with V of the last observation: ppo.py:311 both), episode / value statistics, ``upd.update(buf)``, the
+    reference's progress.txt columns.  With ``reset_each_epoch`` every env restarts when the epoch ends, as the
+    reference's loop does (`terminal or t == local_steps_per_epoch - 1` -> env.reset, ppo.py:304,322)."""
     import time as _time
     from . import logx, mpi_tools
     n, dev = env.num_envs, env.device
@@ -287,9 +336,13 @@ def run_epochs(env, ac, buf, upd, steps_per_epoch, epochs, seed, fused, logger, 
     run_len = torch.zeros(n, dtype=torch.int32, device=dev)
     s5 = torch.zeros(3, 5, dtype=torch.float64, device=dev)       # EpRet, EpLen, VVals
     L = _lib.lib()
-    env.reset(fraction=0.8)
+    if not env._cfg.auto_reset:
+        raise ValueError("the training loop needs an env created with auto_reset=True (see rollout())")
+    env.reset(fraction=0.0 if curriculum else 0.8)                    # ppo.py:286
     history, step, start_time = [], 0, _time.time()
     for epoch in range(epochs):
+        fraction = min(3.0 * epoch / epochs, 0.8) if curriculum else 0.8   # ppo.py:319
+        env.set_reset_fraction(fraction)                              # what the restarts inside this epoch sample with
         o_last = rollout(env, ac, buf, seed=seed, start_step=step, fused=fused, graph=graph)
         step += steps_per_epoch
         if o_last is None:                        # fused path: the observation is rebuilt from the env state
@@ -310,6 +363,10 @@ def run_epochs(env, ac, buf, upd, steps_per_epoch, epochs, seed, fused, logger, 
             red[:, 3], red[:, 4] = lo, hi
         red = red.tolist()
         rew_mean = float(mpi_tools.mpi_avg(buf.rew_buf.mean().item()))
+        if reset_each_epoch:                      # ppo.py:322 at t == local_steps_per_epoch - 1 (trajectory cut by the epoch)
+            env.reset(fraction=fraction)
+            run_ret.zero_()
+            run_len.zero_()
         info = upd.update(buf)
         info.update(Epoch=epoch, AverageStepReward=rew_mean,
                     TotalEnvInteracts=(epoch + 1) * steps_per_epoch * n * mpi_tools.num_procs(),

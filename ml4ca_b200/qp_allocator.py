@@ -2,12 +2,14 @@
 
 Mirrors /root/reference/src/qp/ROS/qp_allocator/src/qp_allocator.py: ``QPTA.solve_QP`` (:108-234) and
 ``QPTA.tau_controller_callback_func`` (:247-320), minus the ROS I/O.  One object allocates for
-``num_envs`` independent vessels; the solve is one launch of the warp-cooperative SQP kernel
-(csrc/qp_alloc.cu) through the C ABI (ml4ca_qp_solve / ml4ca_qp_allocate).
+``num_envs`` independent vessels; the solve is one launch of the allocator kernel (csrc/qp_alloc.cu: one thread per
+demand follows SLSQP's own path, csrc/qp_slsqp.cuh) through the C ABI (ml4ca_qp_solve[_ex] / ml4ca_qp_allocate).
 
 Batch layout is struct-of-arrays: ``tau_d [3, n]``, ``x [8, n]``.  With ``num_envs == 1`` a ``(3, 1)``
 NumPy column (the reference's call shape) gives back ``(x (8,), success bool)``.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -60,18 +62,52 @@ class QPTA(object):
         return t.reshape(3, self.num_envs).contiguous(), was_numpy
 
     # -- qp_allocator.py:108-234 -------------------------------------------------------------------------
-    def solve_QP(self, tau_d, weight_matrix=None, reduce_fuel=True, reduce_flickering=True, reduce_angular=True):
+    def _options(self, weight_matrix, reduce_fuel, reduce_flickering, reduce_angular, raw=False):
+        """The objective of :116-150 as the C ABI's diagonal weighting over [s(3), fuel(3), angle(2), flicker(3)]."""
+        opt = _lib.QpOptions()
+        _lib.check(_lib.lib().ml4ca_qp_options_default(ctypes.byref(opt)), "ml4ca_qp_options_default")
+        # positions inside the reference's obj vector (:125-136): s, thrust, then the optional angle / flicker blocks
+        pos = {"ang": 6 if reduce_angular else None,
+               "flick": (8 if reduce_angular else 6) if reduce_flickering else None}
+        size = 6 + (2 if reduce_angular else 0) + (3 if reduce_flickering else 0)
+        if weight_matrix is None:                      # :138-148
+            q = np.ones(size)
+            if reduce_angular:
+                q[6:8] = 0.25
+            if reduce_flickering:
+                q[pos["flick"]:pos["flick"] + 3] = 0.25
+        else:
+            Q = np.asarray(weight_matrix.cpu() if torch.is_tensor(weight_matrix) else weight_matrix, dtype=np.float64)
+            assert Q.shape == (size, size), "weight_matrix must be %d x %d for these switches (:125-136)" % (size, size)
+            if np.any(Q - np.diag(np.diag(Q)) != 0.0):
+                raise NotImplementedError("only diagonal weight matrices are built (the reference never passes another)")
+            q = np.diag(Q)
+        w = np.zeros(11)
+        w[0:6] = q[0:6]
+        if reduce_angular:
+            w[6:8] = q[6:8]
+        if reduce_flickering:
+            w[8:11] = q[pos["flick"]:pos["flick"] + 3]
+        for i in range(11):
+            opt.weights[i] = float(w[i])
+        opt.reduce_fuel = int(bool(reduce_fuel))
+        opt.raw = int(bool(raw))
+        return opt
+
+    def solve_QP(self, tau_d, weight_matrix=None, reduce_fuel=True, reduce_flickering=True, reduce_angular=True, raw=False):
         """-> (x, success).  x [8, n] = [f_port, f_star, f_bow, a_port, a_star, s1, s2, s3] with |x| < 0.01
-        zeroed (:232); success [n] bool.  Never raises on infeasible demands (success False, caller holds)."""
-        if weight_matrix is not None or not (reduce_fuel and reduce_flickering and reduce_angular):
-            raise NotImplementedError("only the shipped objective (fuel + flickering + angular, default Q) is built")
+        zeroed (:232; ``raw=True`` skips that); success [n] bool.  Never raises on infeasible demands (success False,
+        caller holds).  ``weight_matrix`` / ``reduce_*``: the objective switches of :108,116-150 (diagonal Q)."""
         tau, was_numpy = self._tau(tau_d)
         n = self.num_envs
         x = torch.empty(8, n, dtype=torch.float32, device=self.device)
         status = torch.empty(n, dtype=torch.int32, device=self.device)
+        default = weight_matrix is None and reduce_fuel and reduce_flickering and reduce_angular and not raw
+        opt = None if default else self._options(weight_matrix, reduce_fuel, reduce_flickering, reduce_angular, raw)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().ml4ca_qp_solve(n, _lib.ptr(tau), _lib.ptr(self._prev), _lib.ptr(x),
-                                                 _lib.ptr(status), _lib.current_stream()), "ml4ca_qp_solve")
+            _lib.check(_lib.lib().ml4ca_qp_solve_ex(n, _lib.ptr(tau), _lib.ptr(self._prev),
+                                                    None if opt is None else ctypes.byref(opt), _lib.ptr(x),
+                                                    _lib.ptr(status), _lib.current_stream()), "ml4ca_qp_solve_ex")
         self.last_status = status
         success = (status & 1).bool()
         if n == 1 and was_numpy:

@@ -34,8 +34,8 @@ class GAEBuffer(TrajectoryBuffer):
     from the sampling graph (trpo.py:300,336); here ``record_info(ac)`` evaluates them for the whole buffer in one fp32
     pass of the kernel that later evaluates d_kl, so that d_kl(theta_old) is exactly 0."""
 
-    def __init__(self, obs_dim, act_dim, size, num_envs, gamma=0.99, lam=0.95, device=None):
-        super().__init__(obs_dim, act_dim, size, num_envs, gamma, lam, device)
+    def __init__(self, obs_dim, act_dim, size, num_envs, gamma=0.99, lam=0.95, device=None, max_ep_len=None):
+        super().__init__(obs_dim, act_dim, size, num_envs, gamma, lam, device, max_ep_len=max_ep_len)
         self.mu_buf = torch.zeros(size, act_dim, num_envs, dtype=torch.float32, device=self.device)
         self.log_std_buf = torch.zeros(act_dim, dtype=torch.float32, device=self.device)
 
@@ -228,7 +228,7 @@ def trpo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, target_kl=0.01
         ac = ActorCritic(env.num_states, env.num_actions, hidden_sizes, activation, device=dev, seed=seed)
     mpi_tools.sync_all_params(ac.parameters())    # trpo.py:257
     ac.refresh()
-    buf = GAEBuffer(env.num_states, env.num_actions, steps_per_epoch, n, gamma, lam, device=dev)
+    buf = GAEBuffer(env.num_states, env.num_actions, steps_per_epoch, n, gamma, lam, device=dev, max_ep_len=env.max_ep_len)
     upd = TRPOUpdater(ac, vf_lr, train_v_iters, target_kl, damping_coeff, cg_iters, backtrack_iters, backtrack_coeff, algo,
                       kernel=kernel)
     config = dict(steps_per_epoch=steps_per_epoch, epochs=epochs, gamma=gamma, target_kl=target_kl, vf_lr=vf_lr,

@@ -42,19 +42,45 @@ def wrench_rows(f, a):
     return np.array([c1, c2, c3])
 
 
-def _objective(x, prev):
-    obj = np.hstack((x[5:], np.abs(x[0:3]) ** 1.5,
+DEFAULT_WEIGHTS = np.array([1, 1, 1, 1, 1, 1, .25, .25, .25, .25, .25])   # diag Q over [s, thrust, angle, flicker] (:138-148)
+
+
+def weights_from_switches(weight_matrix=None, reduce_fuel=True, reduce_flickering=True, reduce_angular=True):
+    """The objective switches of solve_QP (:108,116-150) as 11 diagonal weights over [s(3), thrust(3), angle(2),
+    flicker(3)] (0 = term switched off) + the fuel flag.  Only diagonal weight matrices."""
+    size = 6 + (2 if reduce_angular else 0) + (3 if reduce_flickering else 0)
+    if weight_matrix is None:
+        q = np.ones(size)
+        if reduce_angular:
+            q[6:8] = 0.25
+        if reduce_flickering:
+            k = 8 if reduce_angular else 6
+            q[k:k + 3] = 0.25
+    else:
+        q = np.diag(np.asarray(weight_matrix, dtype=np.float64))
+    w = np.zeros(11)
+    w[0:6] = q[0:6]
+    if reduce_angular:
+        w[6:8] = q[6:8]
+    if reduce_flickering:
+        k = 8 if reduce_angular else 6
+        w[8:11] = q[k:k + 3]
+    return w, bool(reduce_fuel)
+
+
+def _objective(x, prev, w=DEFAULT_WEIGHTS, fuel=True):
+    thrust = np.abs(x[0:3]) ** 1.5 if fuel else x[0:3]
+    obj = np.hstack((x[5:], thrust,
                      np.abs(x[3] - prev[3]), np.abs(x[4] - prev[4]),
                      np.abs(x[0:3] - np.asarray(prev[0:3]))))
-    q = np.array([1, 1, 1, 1, 1, 1, .25, .25, .25, .25, .25])
-    return 0.5 * float(np.dot(obj * q, obj))
+    return 0.5 * float(np.dot(obj * w, obj))
 
 
-def _objective_grad(x, prev):
+def _objective_grad(x, prev, w=DEFAULT_WEIGHTS, fuel=True):
     g = np.zeros(8)
-    g[5:] = x[5:]
-    g[0:3] = 1.5 * np.abs(x[0:3]) * x[0:3] + C.QP_W_RATE * (x[0:3] - np.asarray(prev[0:3]))
-    g[3:5] = C.QP_W_RATE * (x[3:5] - np.asarray(prev[3:5]))
+    g[5:] = w[0:3] * x[5:]
+    g[0:3] = w[3:6] * (1.5 * np.abs(x[0:3]) * x[0:3] if fuel else x[0:3]) + w[8:11] * (x[0:3] - np.asarray(prev[0:3]))
+    g[3:5] = w[6:8] * (x[3:5] - np.asarray(prev[3:5]))
     return g
 
 
@@ -103,19 +129,39 @@ def _constraints(tau, prev, analytic):
     return cons
 
 
-def solve_stock(tau, prev):
+def objective(x, prev):
+    """The reference objective (:125-150) at x (8,)."""
+    return _objective(np.asarray(x, dtype=np.float64), [float(p) for p in prev])
+
+
+def solve_stock(tau, prev, return_info=False, w=DEFAULT_WEIGHTS, fuel=True):
     """QPTA.solve_QP (:108-234) with rospy.get_time() pinned (retry loop :209 never runs).
 
-    tau (3,), prev (5,) = [f_prev(3), a_prev(2)].  Returns (x (8,) after the |x|<0.01 clean-up, success, raw x).
+    tau (3,), prev (5,) = [f_prev(3), a_prev(2)].  Returns (x (8,) after the |x|<0.01 clean-up, success, raw x)
+    [+ dict(status, nit, message) of SciPy's result with return_info].
     """
     prev = [float(p) for p in prev]
     x0 = np.array([prev[0], prev[1], prev[2], prev[3], prev[4], 0.0, 0.0, 0.0])
-    sol = minimize(lambda x: _objective(x, prev), x0, method='SLSQP', bounds=_bounds(),
+    sol = minimize(lambda x: _objective(x, prev, w, fuel), x0, method='SLSQP', bounds=_bounds(),
                    constraints=_constraints(tau, prev, analytic=False))
     raw = np.array(sol.x, dtype=np.float64)
     x = raw.copy()
     x[np.abs(x) < C.QP_CLEAN_EPS] = 0.0            # :232
+    if return_info:
+        return x, bool(sol.success), raw, {'status': int(sol.status), 'nit': int(sol.nit), 'message': str(sol.message)}
     return x, bool(sol.success), raw
+
+
+def solve_stock_exact_derivatives(tau, prev, w=DEFAULT_WEIGHTS, fuel=True):
+    """The reference's call with ONE change: analytic derivatives instead of SciPy's forward differences (step
+    1.49e-8), everything else at its defaults (ftol 1e-6, maxiter 100).  Separates what the reference's answer owes to
+    finite-difference noise (a stopping test tipped at |f - f0| ~ 1e-6) from what it owes to the algorithm.
+    Returns (raw x, success, nit)."""
+    prev = [float(p) for p in prev]
+    x0 = np.array([prev[0], prev[1], prev[2], prev[3], prev[4], 0.0, 0.0, 0.0])
+    sol = minimize(lambda x: _objective(x, prev, w, fuel), x0, jac=lambda x: _objective_grad(x, prev, w, fuel),
+                   method='SLSQP', bounds=_bounds(), constraints=_constraints(tau, prev, analytic=True))
+    return np.array(sol.x, dtype=np.float64), bool(sol.success), int(sol.nit)
 
 
 def solve_tight(tau, prev, x0=None):

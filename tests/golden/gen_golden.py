@@ -10,8 +10,14 @@ env_<kind>_<mode>.npz : reference customEnv classes driven through the DigiTwin 
                         oracle.vessel.VesselTwin (float64).  mode 'null' = frozen simulator (wrapper
                         arithmetic only), 'hull' = the declared stand-in hull integrated in float64.
 qp_config1.npz        : reference QPTA.solve_QP + tau_controller_callback_func post-processing on the
-                        SURVEY.md section 8(d) config-1 demand distribution (container SciPy, see
-                        oracle/qp_oracle.py header), rospy.get_time() pinned to 0.
+                        SURVEY.md section 8(d) config-1 batch at its stated size (4096 demands; container SciPy, see
+                        oracle/qp_oracle.py header), rospy.get_time() pinned to 0; plus, per demand, SLSQP's exit
+                        status / iteration count, the raw x and the converged KKT point of the reference's basin
+                        (oracle.qp_oracle.solve_converged) with its objective and active set; the same call with tau
+                        moved by 1e-9 (*_pert) and with analytic instead of finite-difference derivatives (*_exact).
+                        Inputs are rounded to fp32-representable values (the CUDA path takes fp32 rows).
+qp_switches.npz       : reference QPTA.solve_QP with weight_matrix / reduce_fuel / reduce_flickering / reduce_angular
+                        (qp_allocator.py:108,116-150), 96 demands per case.
 policy_*.npz          : the shipped TF1 checkpoints' actor/critic weights, read by ml4ca_b200/tf_checkpoint.py
 ros_adapter.npz       : the deployment node RLTA (src/rl/ROS/rl_allocator/src/rl_allocator.py) driven message by message
                         with a stub actor: state vector, ROS-order action, published message fields.
@@ -79,25 +85,107 @@ def gen_env(kind, cls_name, kwargs, frozen, B, T, seed):
     return out
 
 
-def gen_qp(n, seed):
+def _qp_chunk(args):
+    """One worker: the UNMODIFIED reference QPTA on demands [lo, hi) + the converged point of its basin."""
+    lo, hi, n, seed = args
     qp = ref_loader.load_qp_module()
     ta = qp.QPTA()
-    tau, prev = qp_oracle.synth_batch(n, seed=seed)
-    xs, oks, ns, alphas, bows, newprev = [], [], [], [], [], []
-    for j in range(n):
+    tau, prev = _qp_inputs(n, seed)
+    rows = []
+    for j in range(lo, hi):
         ta.previous_thruster_state = [float(v) for v in prev[:, j]] + [np.pi / 2]
         x, ok = ta.solve_QP(tau[:, j].reshape(3, 1))
-        xs.append(np.array(x)); oks.append(bool(ok))
         # full callback (post-processing :267-320) on a fresh object state
         ta.previous_thruster_state = [float(v) for v in prev[:, j]] + [np.pi / 2]
         ta.tau_controller_callback_func(ref_loader.wrench(tau[0, j], tau[1, j], tau[2, j]))
-        ns.append([ta.pub_stern_thruster_setpoints.last.port_effort, ta.pub_stern_thruster_setpoints.last.star_effort])
-        alphas.append([ta.pub_stern_angles.last.port, ta.pub_stern_angles.last.star])
-        bows.append(float(ta.pub_bow_control.last.throttle_bow))
-        newprev.append(list(ta.previous_thruster_state))
-    return {'tau': tau, 'prev': prev, 'x': np.array(xs).T, 'success': np.array(oks),
-            'stern_effort': np.array(ns).T, 'pod_angle_deg': np.array(alphas).T, 'bow_throttle': np.array(bows),
-            'new_prev': np.array(newprev).T, 'scipy_version': np.array(scipy.__version__)}
+        eff = [ta.pub_stern_thruster_setpoints.last.port_effort, ta.pub_stern_thruster_setpoints.last.star_effort]
+        ang = [ta.pub_stern_angles.last.port, ta.pub_stern_angles.last.star]
+        bow = float(ta.pub_bow_control.last.throttle_bow)
+        newprev = list(ta.previous_thruster_state)
+        # the restated stock solve (bit-identical, tests/test_oracle_pinning.py) exposes what solve_QP hides: the raw x,
+        # SLSQP's exit status and iteration count
+        xs, oks, raw, info = qp_oracle.solve_stock(tau[:, j], prev[:, j], return_info=True)
+        assert oks == bool(ok) and np.array_equal(xs, np.array(x))
+        # converged KKT point of the basin the reference lands in (float64; what the 1e-5 tolerance is measured against)
+        xc, okc, rc = qp_oracle.solve_converged(tau[:, j], prev[:, j])
+        viol_c = qp_oracle.kkt_residual(xc, tau[:, j], prev[:, j])[1] if okc else np.inf
+        # how sharply the reference itself depends on its input: the same call with tau moved by 1e-9 (relative), far below
+        # the fp32 resolution of the demand.  Rows where that changes the flag or the end point are rows no independent
+        # implementation can be expected to reproduce.
+        _, okp, rawp = qp_oracle.solve_stock(tau[:, j] * (1.0 + 1e-9), prev[:, j])
+        # ... and how much it owes to its finite-difference derivatives: the same call with analytic derivatives
+        xa, oka, nita = qp_oracle.solve_stock_exact_derivatives(tau[:, j], prev[:, j])
+        rows.append((np.array(x), bool(ok), eff, ang, bow, newprev, raw, info['status'], info['nit'],
+                     xc, rc, viol_c, qp_oracle.objective(raw, prev[:, j]), qp_oracle.objective(xc, prev[:, j]),
+                     qp_oracle.active_set(xc, prev[:, j], tol=2e-5), qp_oracle.active_set(raw, prev[:, j], tol=1e-5),
+                     bool(okp), rawp, xa, bool(oka), nita))
+    return lo, rows
+
+
+QP_SWITCH_CASES = {   # solve_QP(tau_d, weight_matrix, reduce_fuel, reduce_flickering, reduce_angular), :108
+    'nofuel': dict(reduce_fuel=False),
+    'noflick': dict(reduce_flickering=False),
+    'noang': dict(reduce_angular=False),
+    'bare': dict(reduce_fuel=False, reduce_flickering=False, reduce_angular=False),
+    'weighted': dict(weight_matrix=np.diag([2.0, 1.0, 0.5, 1.0, 0.5, 2.0, 0.1, 0.4, 0.3, 0.2, 0.5])),
+}
+
+
+def gen_qp_switches(n=96, seed=9):
+    """The reference's QPTA.solve_QP with its objective switches, per case on n demands of the config-1 law (fp32-
+    representable inputs): cleaned x, success, and the restated stock / exact-derivative solves for the raw x."""
+    qp = ref_loader.load_qp_module()
+    ta = qp.QPTA()
+    tau, prev = _qp_inputs(n, seed)
+    out = {'tau': tau, 'prev': prev}
+    for tag, kw in QP_SWITCH_CASES.items():
+        w, fuel = qp_oracle.weights_from_switches(**kw)
+        xs, oks, raws, xes, okes = [], [], [], [], []
+        for j in range(n):
+            ta.previous_thruster_state = [float(v) for v in prev[:, j]] + [np.pi / 2]
+            x, ok = ta.solve_QP(tau[:, j].reshape(3, 1), **kw)
+            xo, oko, raw = qp_oracle.solve_stock(tau[:, j], prev[:, j], w=w, fuel=fuel)
+            assert oko == bool(ok) and np.array_equal(xo, np.array(x)), (tag, j)      # the restatement IS the reference
+            xe, oke, _ = qp_oracle.solve_stock_exact_derivatives(tau[:, j], prev[:, j], w=w, fuel=fuel)
+            xs.append(np.array(x)); oks.append(bool(ok)); raws.append(raw); xes.append(xe); okes.append(oke)
+        out[tag + '__x'] = np.array(xs).T
+        out[tag + '__success'] = np.array(oks)
+        out[tag + '__x_raw'] = np.array(raws).T
+        out[tag + '__x_raw_exact'] = np.array(xes).T
+        out[tag + '__success_exact'] = np.array(okes)
+        out[tag + '__weights'] = w
+        out[tag + '__fuel'] = np.array(fuel)
+    return out
+
+
+def _qp_inputs(n, seed):
+    """SURVEY 8(d) config 1, rounded to fp32-representable values: the CUDA path takes fp32 rows, and the reference is
+    run on exactly those numbers."""
+    tau, prev = qp_oracle.synth_batch(n, seed=seed)
+    return tau.astype(np.float32).astype(np.float64), prev.astype(np.float32).astype(np.float64)
+
+
+def gen_qp(n, seed, workers=None):
+    import multiprocessing as mp
+    tau, prev = _qp_inputs(n, seed)
+    workers = workers or os.cpu_count() or 1
+    step = max(1, (n + 4 * workers - 1) // (4 * workers))
+    jobs = [(lo, min(lo + step, n), n, seed) for lo in range(0, n, step)]
+    with mp.get_context("fork").Pool(workers) as pool:
+        parts = sorted(pool.map(_qp_chunk, jobs), key=lambda t: t[0])
+    rows = [r for _, part in parts for r in part]
+    col = lambda i: [r[i] for r in rows]   # noqa: E731
+    return {'tau': tau, 'prev': prev, 'x': np.array(col(0)).T, 'success': np.array(col(1)),
+            'stern_effort': np.array(col(2)).T, 'pod_angle_deg': np.array(col(3)).T, 'bow_throttle': np.array(col(4)),
+            'new_prev': np.array(col(5)).T, 'x_raw': np.array(col(6)).T,
+            'slsqp_status': np.array(col(7), dtype=np.int32), 'slsqp_nit': np.array(col(8), dtype=np.int32),
+            'x_conv': np.array(col(9)).T, 'kkt_conv': np.array(col(10)), 'viol_conv': np.array(col(11)),
+            'obj_raw': np.array(col(12)), 'obj_conv': np.array(col(13)),
+            'mask_conv': np.array(col(14), dtype=np.int32), 'mask_raw': np.array(col(15), dtype=np.int32),
+            'success_pert': np.array(col(16)), 'x_raw_pert': np.array(col(17)).T,
+            'x_raw_exact': np.array(col(18)).T, 'success_exact': np.array(col(19)),
+            'nit_exact': np.array(col(20), dtype=np.int32),
+            'scipy_version': np.array(scipy.__version__)}
 
 
 def gen_gae(seed):
@@ -224,6 +312,15 @@ def main():
         np.savez_compressed(os.path.join(HERE, 'resetacts_final.npz'), **gen_reset_acts())
         print('wrote resetacts_final.npz')
         return
+    if "--only-qp" in sys.argv:
+        out = gen_qp(4096, seed=0)
+        np.savez_compressed(os.path.join(HERE, 'qp_config1.npz'), **out)
+        print('wrote qp_config1.npz  success rate %.4f' % out['success'].mean())
+        return
+    if "--only-qp-switches" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, 'qp_switches.npz'), **gen_qp_switches())
+        print('wrote qp_switches.npz')
+        return
     if "--only-ros" in sys.argv:
         np.savez_compressed(os.path.join(HERE, 'ros_adapter.npz'), **gen_ros_adapter())
         print('wrote ros_adapter.npz')
@@ -245,9 +342,11 @@ def main():
             path = os.path.join(HERE, 'env_%s_%s.npz' % (tag, mode))
             np.savez_compressed(path, **out)
             print('wrote', path)
-    out = gen_qp(256, seed=0)
+    out = gen_qp(4096, seed=0)    # BASELINE configs[0] / SURVEY 8(d): the full 4096-demand batch
     np.savez_compressed(os.path.join(HERE, 'qp_config1.npz'), **out)
     print('wrote qp_config1.npz  success rate %.3f' % out['success'].mean())
+    np.savez_compressed(os.path.join(HERE, 'qp_switches.npz'), **gen_qp_switches())
+    print('wrote qp_switches.npz')
     np.savez_compressed(os.path.join(HERE, 'resetacts_final.npz'), **gen_reset_acts())
     print('wrote resetacts_final.npz')
     np.savez_compressed(os.path.join(HERE, 'gae.npz'), **gen_gae(7))

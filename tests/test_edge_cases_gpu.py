@@ -23,8 +23,8 @@ def test_empty_batches_are_no_ops(cuda_device):
     assert L.ml4ca_pinv_pid(0, p, p, p, p, p, p, p, st) == 0
     assert L.ml4ca_pinv_allocate(0, p, p, p, st) == 0
     assert L.ml4ca_error_frame(0, p, p, p, st) == 0
-    assert L.ml4ca_gae(0, 5, p, p, p, None, 0.99, 0.97, p, p, st) == 0
-    assert L.ml4ca_gae(7, 0, p, p, p, None, 0.99, 0.97, p, p, st) == 0
+    assert L.ml4ca_gae(0, 5, p, p, p, None, 1, 0.99, 0.97, p, p, st) == 0
+    assert L.ml4ca_gae(7, 0, p, p, p, None, 1, 0.99, 0.97, p, p, st) == 0
     import ml4ca_b200 as M
     ac = M.ActorCritic(9, 7, (64, 64), "leaky_relu", device=cuda_device)
     before = _lib.launch_count()
