@@ -31,11 +31,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 # stdout carries exactly one JSON line.  NCCL writes its version / debug banner to file descriptor 1 from C (at WARN level
 # too), so descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a duplicate of the real stdout.
+# NCCL_DEBUG is left exactly as the caller set it (the driver reads the rank count out of an INFO log).
 _REAL_STDOUT = os.fdopen(os.dup(1), "w")
 sys.stdout.flush()
 os.dup2(2, 1)
-if not os.environ.get("ML4CA_KEEP_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = "WARN"
 
 
 def emit(line):
@@ -178,12 +177,68 @@ def cpu_qp_allocations_per_s(n_solves=512, cores=None):
     cores = cores or os.cpu_count() or 1
     per = max(1, n_solves // cores)
     ctx = mp.get_context("fork")
+    use_ref = reference_code_available()
     with ctx.Pool(cores) as pool:
-        busy = pool.map(_cpu_qp_worker, [(i * per, (i + 1) * per) for i in range(cores)])
+        busy = pool.map(_refcode_qp_worker if use_ref else _cpu_qp_worker, [(i * per, (i + 1) * per) for i in range(cores)])
     wall = max(busy)          # slowest worker's solve loop (process start-up and imports excluded)
-    return {"value": per * cores / wall, "unit": "allocations/s", "cores": cores, "kind": "port",
+    return {"value": per * cores / wall, "unit": "allocations/s", "cores": cores, "kind": "reference" if use_ref else "port",
             "single_core_ms_per_solve": 1e3 * sum(busy) / (per * cores),
-            "sample": "first %d demands of the 4096-sample config-1 batch, SciPy SLSQP (reference defaults), %d processes" % (per * cores, cores)}
+            "sample": "first %d demands of the 4096-sample config-1 batch, %s on SciPy SLSQP (reference defaults), %d processes"
+                      % (per * cores, "the reference's QPTA.solve_QP" if use_ref else "oracle restatement of QPTA.solve_QP", cores)}
+
+
+def reference_code_available():
+    from oracle import ref_loader
+    return ref_loader.available()
+
+
+def _refcode_env_worker(args):
+    """The REFERENCE CODE: customEnv.RevoltFinal objects (imported unmodified from /root/reference or from the byte-compiled
+    oracle/_ref) stepped one env at a time, as the reference does, on the float64 stand-in twin."""
+    n_envs, steps, seed = args
+    import numpy as np
+    from oracle import ref_loader, vessel
+    mod = ref_loader.load_env_module()
+    np.random.seed(seed)
+    envs = [mod.RevoltFinal(vessel.VesselTwin(), cont_ang=True, extended_state=True) for _ in range(n_envs)]
+    for e in envs:
+        e.reset(fraction=0.8)
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(-1, 1, (steps, n_envs, 7))
+    t0 = time.perf_counter()
+    for t in range(steps):
+        for k, e in enumerate(envs):
+            o, r, d, _ = e.step(acts[t, k])
+            if d:
+                e.reset(fraction=0.8)
+    return time.perf_counter() - t0
+
+
+def refcode_env_steps_per_s(envs_per_core=8, steps=100, cores=None):
+    import multiprocessing as mp
+    from oracle import ref_loader
+    cores = cores or os.cpu_count() or 1
+    with mp.get_context("fork").Pool(cores) as pool:
+        busy = pool.map(_refcode_env_worker, [(envs_per_core, steps, 7000 + i) for i in range(cores)])
+    wall = max(busy)
+    return envs_per_core * cores * steps / wall, cores, (
+        "%d reference RevoltFinal objects (%s) x %d steps on the float64 stand-in twin, %d processes"
+        % (envs_per_core * cores, ref_loader.source(), steps, cores))
+
+
+def _refcode_qp_worker(args):
+    lo, hi = args
+    import numpy as np
+    from ml4ca_b200 import synth
+    from oracle import ref_loader
+    qp = ref_loader.load_qp_module()
+    ta = qp.QPTA()
+    tau, prev = synth.qp_batch(4096, seed=0)
+    t0 = time.perf_counter()
+    for j in range(lo, hi):
+        ta.previous_thruster_state = [float(v) for v in prev[:, j]] + [np.pi / 2]
+        ta.solve_QP(tau[:, j].reshape(3, 1))
+    return time.perf_counter() - t0
 
 
 _REF_STATE = {}
@@ -220,6 +275,8 @@ def run_reference(args, rank, world):
     workers across steps, so a bench step times stepping only).  One bench step = `inner` env steps of 64 Ki envs."""
     if rank != 0:
         return
+    if reference_code_available() and not os.environ.get("ML4CA_REFERENCE_PORT"):
+        return run_reference_code(args, world)
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     n_total, inner = 1 << 16, 8
@@ -274,6 +331,81 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def run_reference_code(args, world):
+    """--impl reference with the reference's own code on the box (oracle/_ref or the checkout): customEnv.RevoltFinal
+    objects stepped one by one, as ppo.py:293 does, one persistent process per core.  kind = "reference".  The vectorised
+    NumPy port (what --impl reference timed in round 1; ML4CA_REFERENCE_PORT=1 still selects it) is ~300x faster per core
+    than the reference code and is reported next to it."""
+    import multiprocessing as mp
+    from oracle import ref_loader
+    cores = os.cpu_count() or 1
+    per, inner = 8, 25
+    ctx = mp.get_context("fork")
+
+    def serve(conn, idx):
+        import numpy as np
+        from oracle import vessel
+        mod = ref_loader.load_env_module()
+        np.random.seed(9000 + idx)
+        envs = [mod.RevoltFinal(vessel.VesselTwin(), cont_ang=True, extended_state=True) for _ in range(per)]
+        for e in envs:
+            e.reset(fraction=0.8)
+        rng = np.random.default_rng(9000 + idx)
+        while True:
+            k = conn.recv()
+            if k <= 0:
+                break
+            acts = rng.uniform(-1, 1, (k, per, 7))
+            t0 = time.perf_counter()
+            for t in range(k):
+                for j, e in enumerate(envs):
+                    o, r, d, _ = e.step(acts[t, j])
+                    if d:
+                        e.reset(fraction=0.8)
+            conn.send(time.perf_counter() - t0)
+
+    pipes, procs = [], []
+    for c in range(cores):
+        a, b = ctx.Pipe()
+        pr = ctx.Process(target=serve, args=(b, c), daemon=True)
+        pr.start()
+        pipes.append(a), procs.append(pr)
+
+    def step_all(k):
+        for a in pipes:
+            a.send(k)
+        return [a.recv() for a in pipes]
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_all(2)
+    t0 = time.perf_counter()
+    done_steps = 0
+    for _ in range(args.steps):
+        step_all(inner)
+        done_steps += 1
+        if time.perf_counter() - t0 > 120.0:
+            break
+    wall = time.perf_counter() - t0
+    for a in pipes:
+        a.send(0)
+    for pr in procs:
+        pr.join(timeout=5)
+    value = per * cores * inner * done_steps / wall
+    sample = ("%d reference RevoltFinal objects (%s) x %d env-steps per bench step, %d bench steps, %d persistent processes; "
+              "simulator = the float64 stand-in twin" % (per * cores, ref_loader.source(), inner, done_steps, cores))
+    port_val, _, port_sample = cpu_env_steps_per_s(1 << 16, 8)
+    emit({
+        "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": done_steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / done_steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "reference", "sample": sample,
+                         "port": {"value": port_val, "unit": "env-steps/s", "kind": "port", "sample": port_sample}},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    })
 
 
 def workload_config(args, world):
@@ -341,7 +473,7 @@ def run_b200(args, rank, local_rank, world):
     env.reset(fraction=0.8)
     gen = torch.Generator(device=dev)
     gen.manual_seed(2 + rank)
-    room = ACTION_SHIFT * (max(args.steps, 16) // ACTION_POOL + 2)
+    room = ACTION_SHIFT * ((max(args.steps, 16) + 200 + args.warmup) // ACTION_POOL + 2)
     flat = [torch.rand(7 * n + room, device=dev, generator=gen) * 2 - 1 for _ in range(ACTION_POOL)]
 
     def actions(i):
@@ -375,6 +507,17 @@ def run_b200(args, rank, local_rank, world):
     kernel_ms = ms / args.steps
     achieved = ENV_STEP_BYTES * n / (kernel_ms * 1e-3) / 1e9
 
+    # ---- sustained leg: 200 back-to-back launches (the driver's 20-step run ends before the clock and the restart rate settle)
+    sustained_ms = None
+    if not args.skip_extra:
+        sus = 200
+        ev0.record()
+        for i in range(sus):
+            env.step_into(actions(args.warmup + args.steps + i), *out)
+        ev1.record()
+        torch.cuda.synchronize()
+        sustained_ms = max_over_ranks(ev0.elapsed_time(ev1)) / sus
+
     # ---- end to end through the public API with host buffers ----------------------------------------------------
     e2e_steps = max(3, min(args.steps, 10))
     h_act = [(torch.rand(7, n) * 2 - 1).pin_memory() for _ in range(2)]
@@ -398,6 +541,33 @@ def run_b200(args, rank, local_rank, world):
     e2e_value = n * world * e2e_steps / e2e_s
     h2d = 7 * n * 4
     d2h = (9 * 4 + 4 + 1) * n
+    # plain-copy ceiling of this box at this rank count: the same bytes per step, both directions at once, no kernel,
+    # no chunking (one cudaMemcpyAsync per buffer on two streams).  e2e / ceiling says whether the pipeline or the box limits.
+    d_act, d_out = torch.empty(7, n, device=dev), torch.empty(d2h, dtype=torch.uint8, device=dev)
+    h_out = torch.empty(d2h, dtype=torch.uint8).pin_memory()
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def copy_step(i):
+        with torch.cuda.stream(s_in):
+            d_act.copy_(h_act[i % 2], non_blocking=True)
+        with torch.cuda.stream(s_out):
+            h_out.copy_(d_out, non_blocking=True)
+
+    copy_step(0)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    s_in.wait_event(c0), s_out.wait_event(c0)
+    for i in range(e2e_steps):
+        copy_step(i)
+    e_in, e_out = torch.cuda.Event(), torch.cuda.Event()
+    e_in.record(s_in), e_out.record(s_out)
+    torch.cuda.current_stream().wait_event(e_in), torch.cuda.current_stream().wait_event(e_out)
+    c1.record()
+    torch.cuda.synchronize()
+    ceil_s = max_over_ranks(c0.elapsed_time(c1) * 1e-3)
+    copy_ceiling = n * world * e2e_steps / ceil_s
+    del d_act, d_out, h_out
 
     # ---- secondary kernels (rank-local, reported under "extra") -------------------------------------------------
     extra = {}
@@ -421,6 +591,24 @@ def run_b200(args, rank, local_rank, world):
                                          "an L2-resident figure, not an HBM one)",
                              "value": m / t, "unit": "allocations/s", "us_per_launch": t * 1e6,
                              "achieved_GBs": PINV_PID_BYTES * m / t / 1e9}
+        m16 = 1 << 24                       # HBM-sized batch: 1.3 GB of rows per launch
+        eta16 = (torch.rand(3, m16, device=dev, generator=gen) * 2 - 1) * torch.tensor([[8.0], [8.0], [0.785]], device=dev)
+        nu16 = (torch.rand(3, m16, device=dev, generator=gen) * 2 - 1) * torch.tensor([[1.4], [0.3], [0.52]], device=dev)
+        ref16, integ16 = torch.zeros(3, m16, device=dev), torch.zeros(3, m16, device=dev)
+        for _ in range(3):
+            M.pinv_pid(eta16, nu16, ref16, integ16)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(20):
+            M.pinv_pid(eta16, nu16, ref16, integ16)
+        ev1.record()
+        torch.cuda.synchronize()
+        t16 = ev0.elapsed_time(ev1) / 20 * 1e-3
+        extra["pinv_pid_16Mi"] = {"workload": "pseudoinverse + PID, 16 Mi setpoints (1.3 GB of rows: an HBM figure)",
+                                  "value": m16 / t16, "unit": "allocations/s", "ms_per_launch": t16 * 1e3,
+                                  "achieved_GBs": PINV_PID_BYTES * m16 / t16 / 1e9,
+                                  "hbm_frac": PINV_PID_BYTES * m16 / t16 / 1e9 / peak_gbs}
+        del eta16, nu16, ref16, integ16
     except Exception as e:  # noqa: BLE001
         extra["pinv_pid"] = {"error": repr(e)}
 
@@ -446,10 +634,13 @@ def run_b200(args, rank, local_rank, world):
             tau_t = torch.as_tensor(np.tile(tau_np, reps_t), dtype=torch.float32, device=dev).contiguous()
             qp = M.QPTA(num_envs=m, device=dev)
             qp.previous_thruster_state = np.tile(prev_np, reps_t)
-            t = timed(lambda: qp.solve_QP(tau_t), 5)
-            extra["qp_allocate"] = {"workload": "BASELINE configs[0] demand law tiled to 1 Mi allocations (QPTA.solve_QP)",
-                                    "value": m / t, "unit": "allocations/s", "ms_per_launch": t * 1e3,
-                                    "achieved_GBs": QP_BYTES * m / t / 1e9, "bound": "issue/latency (~1e4 instr per solve)"}
+            barrier()
+            t = max_over_ranks(timed(lambda: qp.solve_QP(tau_t), 5))
+            extra["qp_allocate"] = {"workload": "BASELINE configs[0] demand law tiled to 1 Mi allocations per GPU (QPTA.solve_QP), "
+                                                "SLSQP path in float64, aggregate over all ranks",
+                                    "value": m * world / t, "unit": "allocations/s", "ms_per_launch": t * 1e3, "dtype": "f64",
+                                    "achieved_GBs": QP_BYTES * m / t / 1e9, "hbm_frac": QP_BYTES * m / t / 1e9 / peak_gbs,
+                                    "bound": "issue (FP64 pipe + divergence inside the active-set loops)"}
             del qp, tau_t
         except Exception as e:  # noqa: BLE001
             extra["qp_allocate"] = {"error": repr(e)}
@@ -555,10 +746,15 @@ def run_b200(args, rank, local_rank, world):
     clocks = sampler.summary()
 
     if rank == 0:
+        cpu_kind, cpu_port = "port", None
         if args.skip_cpu:
             cpu_val, cpu_cores, cpu_sample = None, 0, "skipped (--skip-cpu)"
         else:
             cpu_val, cpu_cores, cpu_sample = cpu_env_steps_per_s(1 << 16, 8)
+            if reference_code_available():          # the reference's own code is on the box: it is the baseline, the port is a note
+                cpu_port = {"value": cpu_val, "unit": "env-steps/s", "cores": cpu_cores, "kind": "port", "sample": cpu_sample}
+                cpu_val, cpu_cores, cpu_sample = refcode_env_steps_per_s(8, 100)
+                cpu_kind = "reference"
             try:
                 if "qp_allocate" in extra and "error" not in extra["qp_allocate"]:
                     extra["qp_allocate"]["cpu_baseline"] = cpu_qp_allocations_per_s(512)
@@ -566,6 +762,27 @@ def run_b200(args, rank, local_rank, world):
                 extra["cpu_env_single_core"] = {"value": one[0], "unit": "env-steps/s", "cores": 1, "sample": one[2]}
             except Exception as e:  # noqa: BLE001
                 extra["cpu_baselines_error"] = repr(e)
+        # compact per-kernel figures inside the object the driver keeps (BASELINE's metric names env-steps/s AND QP allocations/s)
+        kernels = {}
+
+        def pick(name, keys):
+            e = extra.get(name)
+            if isinstance(e, dict) and "error" not in e:
+                kernels[name] = {k: e[k] for k in keys if k in e}
+        pick("qp_allocate", ("value", "unit", "ms_per_launch", "dtype", "hbm_frac", "bound"))
+        if "qp_allocate" in kernels and isinstance(extra["qp_allocate"].get("cpu_baseline"), dict):
+            cb = extra["qp_allocate"]["cpu_baseline"]
+            kernels["qp_allocate"]["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind")}
+        pick("pinv_pid", ("value", "unit", "us_per_launch"))
+        pick("pinv_pid_16Mi", ("value", "unit", "ms_per_launch", "hbm_frac"))
+        pick("policy_forward", ("value", "unit", "ms_per_launch", "achieved_TFLOPs"))
+        for k in ("rollout_two_kernel", "rollout_fused"):
+            pick(k, ("value", "unit", "ms_per_step", "achieved_GBs"))
+            if k in kernels:
+                kernels[k]["hbm_frac"] = kernels[k]["achieved_GBs"] / peak_gbs
+        pick("gae", ("value", "unit", "ms_per_launch", "hbm_frac"))
+        for k in ("ppo_train", "trpo_train", "trpo_train_tc"):
+            pick(k, ("value", "unit", "s_per_epoch"))
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -575,11 +792,17 @@ def run_b200(args, rank, local_rank, world):
                          "frac": achieved / peak_gbs, "traffic": ENV_STEP_TRAFFIC, "peak_source": peak_src,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/env_step_r1.md",
                          "kernel": "env_step_kernel<FINAL,cont,ext,2 envs/thread>", "bytes_per_env_step": ENV_STEP_BYTES,
-                         "kernel_ms": kernel_ms},
-            "cpu_baseline": {"value": cpu_val, "unit": "env-steps/s", "cores": cpu_cores, "kind": "port",
-                             "sample": cpu_sample},
+                         "kernel_ms": kernel_ms,
+                         "sustained_ms": sustained_ms,
+                         "sustained_frac": (ENV_STEP_BYTES * n / (sustained_ms * 1e-3) / 1e9 / peak_gbs) if sustained_ms else None,
+                         "sustained_note": "200 further back-to-back launches (stationary clock and restart rate)",
+                         "kernels": kernels},
+            "cpu_baseline": dict({"value": cpu_val, "unit": "env-steps/s", "cores": cpu_cores, "kind": cpu_kind,
+                                  "sample": cpu_sample}, **({"port": cpu_port} if cpu_port else {})),
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "note": "RevoltFinal.step_host: pinned host actions in, obs+reward+done out, every step, chunked H2D|kernel|D2H pipeline",
+                    "steps": e2e_steps, "copy_ceiling": copy_ceiling, "frac_of_copy_ceiling": e2e_value / copy_ceiling,
+                    "copy_ceiling_note": "same bytes per step, pinned host <-> device both ways at once, no kernel, measured at this rank count in this run",
+                    "note": "RevoltFinal.step_host: pinned host actions in, obs+reward+done out, every step, chunked H2D|kernel|D2H pipeline",
                     "cpu_binding": numa_note},
             "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
         }

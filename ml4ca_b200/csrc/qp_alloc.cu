@@ -32,8 +32,8 @@
 namespace ml4ca {
 
 constexpr int kQpThreads = 64;         // per CTA
-constexpr int kQpPerThread = 8;        // demands per thread in a CTA's chunk
-constexpr int kQpChunk = kQpThreads * kQpPerThread;
+constexpr int kQpMaxPerThread = 64;    // demands per thread in a CTA's chunk (upper limit; the host sizes the chunk)
+constexpr int kQpTableau = 45;         // packed lower triangle of the 9 x 9 pivoting tableau
 
 __device__ __forceinline__ float map_to_pi(float a) {  // qp_allocator.py:101-106
   const float two_pi = 2.0f * (float)ML4CA_PI;
@@ -90,38 +90,70 @@ __device__ __forceinline__ void emit_result(int64_t n, int64_t env, const slsqp:
   }
 }
 
+// Fetch demand `local` of the chunk, or signal the end.
+__device__ __forceinline__ void load_demand(int64_t n, int64_t env, const float* __restrict__ tau, const float* __restrict__ prev,
+                                            const slsqp::Objective& obj, slsqp::Problem<double>& P, slsqp::State<double>& S) {
+  double t3[3], p5[5];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) t3[i] = (double)tau[(int64_t)i * n + env];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) p5[i] = (double)prev[(int64_t)i * n + env];
+  slsqp::make_problem(t3, p5, P);
+  slsqp::slsqp_init(P, obj, S);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kQpThreads) qp_kernel(int64_t n, const float* __restrict__ tau, float* __restrict__ prev,
                                                         float* __restrict__ out, uint32_t* __restrict__ status,
-                                                        const slsqp::Objective obj) {
-  extern __shared__ double Gs_all[];          // [81][kQpThreads]: entry e of thread t at e * kQpThreads + t
-  __shared__ int next_in_chunk;
-  if (threadIdx.x == 0) next_in_chunk = kQpThreads;   // the first kQpThreads demands are taken statically
+                                                        const slsqp::Objective obj, int per_thread) {
+  extern __shared__ double smem_d[];          // tableau [45][kQpThreads]: entry e of thread t at e * kQpThreads + t
+  int* hard = reinterpret_cast<int*>(smem_d + kQpTableau * kQpThreads);   // [chunk]: demands deferred to phase 2
+  __shared__ int next_in_chunk, n_hard, next_hard;
+  if (threadIdx.x == 0) next_in_chunk = kQpThreads, n_hard = 0, next_hard = kQpThreads;   // first round taken statically
   __syncthreads();
-  const int64_t chunk0 = (int64_t)blockIdx.x * kQpChunk;
-  const int64_t chunk_n = (n - chunk0 < kQpChunk) ? (n - chunk0) : kQpChunk;
-  double* G = Gs_all + threadIdx.x;
-  int local = threadIdx.x;
+  const int chunk = kQpThreads * per_thread;
+  const int64_t chunk0 = (int64_t)blockIdx.x * chunk;
+  const int chunk_n = (int)((n - chunk0 < chunk) ? (n - chunk0) : chunk);
+  double* G = smem_d + threadIdx.x;
   slsqp::Problem<double> P;
   slsqp::State<double> S;
-  bool have = false;
-  while (true) {
-    if (!have) {
-      if (local >= chunk_n) break;
-      const int64_t env = chunk0 + local;
-      double t3[3], p5[5];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) t3[i] = (double)tau[(int64_t)i * n + env];
-#pragma unroll
-      for (int i = 0; i < 5; ++i) p5[i] = (double)prev[(int64_t)i * n + env];
-      slsqp::make_problem(t3, p5, P);
-      slsqp::slsqp_init(P, obj, S);
-      have = true;
+  // ---- phase 1: every demand of the chunk, until it finishes or meets an inconsistent linearisation ----------------------
+  {
+    int local = threadIdx.x;
+    bool have = false;
+    while (true) {
+      if (!have) {
+        if (local >= chunk_n) break;
+        load_demand(n, chunk0 + local, tau, prev, obj, P, S);
+        have = true;
+      }
+      if (slsqp::slsqp_iterate<double, double, false>(P, obj, S, G, kQpThreads)) {
+        if (S.mode == slsqp::kDeferred) hard[atomicAdd(&n_hard, 1)] = local;
+        else emit_result<MODE>(n, chunk0 + local, P, obj, S, prev, out, status);
+        have = false;
+        local = atomicAdd(&next_in_chunk, 1);
+      }
     }
-    if (slsqp::slsqp_iterate<double, double>(P, obj, S, G, kQpThreads)) {
-      emit_result<MODE>(n, chunk0 + local, P, obj, S, prev, out, status);
-      have = false;
-      local = atomicAdd(&next_in_chunk, 1);
+  }
+  __syncthreads();
+  // ---- phase 2: the deferred demands, restarted; every lane may now run the augmented sub-problem ------------------------
+  {
+    const int nh = n_hard;
+    int slot = threadIdx.x;
+    int local = 0;
+    bool have = false;
+    while (true) {
+      if (!have) {
+        if (slot >= nh) break;
+        local = hard[slot];
+        load_demand(n, chunk0 + local, tau, prev, obj, P, S);
+        have = true;
+      }
+      if (slsqp::slsqp_iterate<double, double, true>(P, obj, S, G, kQpThreads)) {
+        emit_result<MODE>(n, chunk0 + local, P, obj, S, prev, out, status);
+        have = false;
+        slot = atomicAdd(&next_hard, 1);
+      }
     }
   }
 }
@@ -129,10 +161,15 @@ __global__ void __launch_bounds__(kQpThreads) qp_kernel(int64_t n, const float* 
 template <int MODE>
 static int launch_qp(int64_t n, const float* tau, float* prev, float* out, uint32_t* status, const slsqp::Objective& obj,
                      cudaStream_t st) {
-  const size_t smem = (size_t)81 * kQpThreads * sizeof(double);
+  // chunk per CTA: large enough that the deferred demands of a chunk fill its lanes in phase 2, small enough that the
+  // grid covers the GPU (4 CTAs per SM at 255 registers)
+  int64_t per_thread = (n + (int64_t)kNumSMs * 4 * kQpThreads - 1) / ((int64_t)kNumSMs * 4 * kQpThreads);
+  per_thread = per_thread < 1 ? 1 : (per_thread > kQpMaxPerThread ? kQpMaxPerThread : per_thread);
+  const int64_t chunk = kQpThreads * per_thread;
+  const size_t smem = (size_t)kQpTableau * kQpThreads * sizeof(double) + (size_t)chunk * sizeof(int);
   ML4CA_CUDA(cudaFuncSetAttribute(qp_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
-  const int64_t blocks = (n + kQpChunk - 1) / kQpChunk;
-  qp_kernel<MODE><<<(unsigned)blocks, kQpThreads, smem, st>>>(n, tau, prev, out, status, obj);
+  const int64_t blocks = (n + chunk - 1) / chunk;
+  qp_kernel<MODE><<<(unsigned)blocks, kQpThreads, smem, st>>>(n, tau, prev, out, status, obj, (int)per_thread);
   return check_launch("qp_kernel");
 }
 

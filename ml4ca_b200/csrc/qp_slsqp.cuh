@@ -268,53 +268,81 @@ ML4CA_HD_CALL void ldl_update(LDL<real>& B, real (&z)[8], real sigma) {
 }
 
 // ---- the reduced QP: min 1/2 d'Hd + q'd  s.t. lo_b <= a_b'd <= hi_b, b < NV: a_b = e_b; b >= NV: a_b = A[b - NV] ------
-// Goldfarb-Idnani dual active set in constraint space.  G (NC x NC, NC = NV + 3) lives behind a strided pointer (shared
-// memory on the device: dynamic indexing by the active list).  Returns false when the constraints are inconsistent.
+// Goldfarb-Idnani dual active set in constraint space, carried out as PRINCIPAL PIVOTING on the Gram matrix
+// G = A H^-1 A' (NC x NC, NC = NV + 3): with the active set swept in (symmetric sweep operator), the tableau S holds
+//   S[a][a'] = -(G_AA^-1)     S[a][c] = (G_AA^-1 G_Ac)     S[c][c'] = G_cc' - G_cA G_AA^-1 G_Ac'     (a active, c inactive)
+// so column b of S is everything a dual step on the entering constraint b needs: its Schur complement S[b][b], the change of
+// every inactive constraint value, and the change of every active multiplier.  Adding a constraint = one sweep, dropping
+// one = one reverse sweep: NC (NC + 1) / 2 fused multiply-adds and one reciprocal, no factorisation, no triangular solves.
+// S (lower triangle, packed) lives behind a strided pointer (shared memory on the device): the pivot index is the only
+// thing indexed dynamically.  Returns false when the constraints are inconsistent.
 // lam: signed multipliers (> 0 at the upper side, < 0 at the lower side):  H d + q + sum_b lam_b a_b = 0.
+#define ML4CA_SIDX(i, j) ((i) >= (j) ? (i) * ((i) + 1) / 2 + (j) : (j) * ((j) + 1) / 2 + (i))
+
+template <typename real, typename greal, int NC>
+ML4CA_HD void tableau_row(const greal* __restrict__ S, int gs, int k, real (&row)[NC]) {
+#pragma unroll
+  for (int j = 0; j < NC; ++j) row[j] = (real)S[ML4CA_SIDX(k, j) * gs];
+}
+
+// sweep (dir = +1: index k enters the active set) or reverse sweep (dir = -1: k leaves it)
+template <typename real, typename greal, int NC>
+ML4CA_HD void tableau_sweep(greal* __restrict__ S, int gs, int k, const real (&row)[NC], real dir) {
+  real dkk = row[0];
+#pragma unroll
+  for (int j = 1; j < NC; ++j)
+    if (j == k) dkk = row[j];
+  const real inv = (real)1 / dkk;
+  real scaled[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) scaled[j] = row[j] * inv;
+#pragma unroll
+  for (int i = 0; i < NC; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      const int e = i * (i + 1) / 2 + j;
+      real v = (real)S[e * gs] - row[i] * scaled[j];
+      if (i == k) v = dir * scaled[j];
+      if (j == k) v = dir * scaled[i];
+      if (i == k && j == k) v = -inv;
+      S[e * gs] = (greal)v;
+    }
+}
+
 template <typename real, typename greal, int NV>
 ML4CA_HD_CALL bool solve_reduced_qp(real (&H)[NV][NV] /* lower triangle; destroyed */, const real (&q)[NV], const real (&A)[3][NV],
                                real (&lo)[NV + 3], real (&hi)[NV + 3], greal* __restrict__ G, int gs, real (&d)[NV],
                                real (&lam)[NV + 3]) {
   constexpr int NC = NV + 3;
-  // Cholesky H = C C' (C lower, diagonal stored inverted)
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    real dj = H[j][j];
-#pragma unroll
-    for (int k = 0; k < j; ++k) dj -= H[j][k] * H[j][k];
-    const real inv = (real)1 / sqrt(fmax(dj, (real)1e-30));
-    H[j][j] = inv;
-#pragma unroll
-    for (int i = j + 1; i < NV; ++i) {
-      real v = H[i][j];
-#pragma unroll
-      for (int k = 0; k < j; ++k) v -= H[i][k] * H[j][k];
-      H[i][j] = v * inv;
-    }
-  }
-  // Ci = C^-1 (lower), K = H^-1 = Ci' Ci
-  real Ci[NV][NV];
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    Ci[j][j] = H[j][j];
-#pragma unroll
-    for (int i = j + 1; i < NV; ++i) {
-      real v = (real)0;
-#pragma unroll
-      for (int k = j; k < i; ++k) v -= H[i][k] * Ci[k][j];
-      Ci[i][j] = v * H[i][i];
-    }
-  }
+  // K = H^-1 by NV symmetric sweeps of H (Gaussian elimination of an SPD matrix: stable without pivoting)
   real K[NV][NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
-    for (int j = 0; j <= i; ++j) {
-      real v = (real)0;
+    for (int j = 0; j <= i; ++j) K[i][j] = H[i][j], K[j][i] = H[i][j];
 #pragma unroll
-      for (int k = i; k < NV; ++k) v += Ci[k][i] * Ci[k][j];
-      K[i][j] = v, K[j][i] = v;
-    }
+  for (int k = 0; k < NV; ++k) {
+    const real inv = (real)1 / K[k][k];
+    real sc[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) sc[j] = K[k][j] * inv;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        if (i == k || j == k) continue;
+        const real v = K[i][j] - K[i][k] * sc[j];
+        K[i][j] = v, K[j][i] = v;
+      }
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      if (j != k) K[k][j] = sc[j], K[j][k] = sc[j];
+    K[k][k] = -inv;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < NV; ++j) K[i][j] = -K[i][j];
   // V[r] = K A[r]',  G = [K, V'; V, A V'],  p = a_b' d0 with d0 = -K q
   real V[3][NV];
 #pragma unroll
@@ -326,13 +354,14 @@ ML4CA_HD_CALL bool solve_reduced_qp(real (&H)[NV][NV] /* lower triangle; destroy
       for (int k = 0; k < NV; ++k) v += K[i][k] * A[r][k];
       V[r][i] = v;
     }
-  real p[NC];
+  real p[NC], gdiag[NC];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     real v = (real)0;
 #pragma unroll
     for (int k = 0; k < NV; ++k) v -= K[i][k] * q[k];
     p[i] = v;
+    gdiag[i] = K[i][i];
   }
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -342,151 +371,106 @@ ML4CA_HD_CALL bool solve_reduced_qp(real (&H)[NV][NV] /* lower triangle; destroy
     p[NV + r] = v;
   }
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
+  for (int i = 0; i < NV; ++i)
 #pragma unroll
-    for (int j = 0; j < NV; ++j) G[(i * NC + j) * gs] = (greal)K[i][j];
+    for (int j = 0; j <= i; ++j) G[(i * (i + 1) / 2 + j) * gs] = (greal)K[i][j];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) G[(i * NC + NV + r) * gs] = (greal)V[r][i], G[((NV + r) * NC + i) * gs] = (greal)V[r][i];
-  }
+  for (int r = 0; r < 3; ++r) {
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+    for (int i = 0; i < NV; ++i) G[((NV + r) * (NV + r + 1) / 2 + i) * gs] = (greal)V[r][i];
 #pragma unroll
     for (int s = 0; s <= r; ++s) {
       real v = (real)0;
 #pragma unroll
       for (int k = 0; k < NV; ++k) v += A[r][k] * V[s][k];
-      G[((NV + r) * NC + NV + s) * gs] = (greal)v, G[((NV + s) * NC + NV + r) * gs] = (greal)v;
+      G[((NV + r) * (NV + r + 1) / 2 + NV + s) * gs] = (greal)v;
+      if (s == r) gdiag[NV + r] = v;
     }
+  }
 
-  // ---- dual active set ---------------------------------------------------------------------------------------------
+  // ---- dual active set by principal pivoting -------------------------------------------------------------------------
   const real eps = machine_eps<real>();
   const real vtol = (real)256 * eps;  // relative feasibility tolerance of the sub-problem
-  int act[NV];
-  int q_n = 0;
+  real iscale[NC];
+#pragma unroll
+  for (int b = 0; b < NC; ++b) {
+    lam[b] = (real)0;
+    iscale[b] = (real)1 / ((real)1 + fmax(fabs(lo[b]), fabs(hi[b])));
+  }
   unsigned in_act = 0u;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) act[i] = 0;
-#pragma unroll
-  for (int b = 0; b < NC; ++b) lam[b] = (real)0;
+  int n_act = 0;
+  int bs = -1;          // entering constraint; stays pending across drops until it has been added
+  real sig = (real)1;
   bool feasible = true;
-  for (int gi = 0; gi < 12 * NC; ++gi) {
-    // most violated inactive constraint (violation relative to the size of its bounds)
-    int bs = -1;
-    real worst = vtol;
-    real sig = (real)1;
+  for (int gi = 0; gi < 8 * NC; ++gi) {
+    if (bs < 0) {
+      // most violated inactive constraint (violation relative to the size of its bounds)
+      real worst = vtol;
 #pragma unroll
-    for (int b = 0; b < NC; ++b) {
-      const real vhi = p[b] - hi[b], vlo = lo[b] - p[b];
-      const real v = fmax(vhi, vlo) / ((real)1 + fmax(fabs(lo[b]), fabs(hi[b])));
-      if (!((in_act >> b) & 1u) && v > worst) worst = v, bs = b, sig = (vhi > vlo) ? (real)1 : (real)-1;
+      for (int b = 0; b < NC; ++b) {
+        const real vhi = p[b] - hi[b], vlo = lo[b] - p[b];
+        const real v = fmax(vhi, vlo) * iscale[b];
+        if (!((in_act >> b) & 1u) && v > worst) worst = v, bs = b, sig = (vhi > vlo) ? (real)1 : (real)-1;
+      }
+      if (bs < 0) break;
     }
-    if (bs < 0) break;
-    bool added = false;
-    for (int inner = 0; inner <= NV + 1 && !added; ++inner) {
-      // y = M^-1 r,  M = G[act, act], r = G[act, bs]
-      real M[NV][NV], r[NV], y[NV];
+    real col[NC];
+    tableau_row<real, greal, NC>(G, gs, bs, col);
+    real rho_s = (real)0, need = (real)0, gbb = (real)0;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        r[i] = (i < q_n) ? (real)G[(act[i] * NC + bs) * gs] : (real)0;
+    for (int c = 0; c < NC; ++c)
+      if (c == bs) rho_s = col[c], gbb = gdiag[c], need = (sig > (real)0) ? (p[c] - hi[c]) : (lo[c] - p[c]);
+    // the entering normal is linearly dependent on the active ones when its Schur complement vanishes (always when the
+    // active set is full): no primal step, only multipliers can move
+    const real t2 = (n_act < NV && rho_s > kDepTol<real>() * gbb) ? need / rho_s : (real)1e300;
+    // blocking ratio: the signed multiplier of an active constraint must keep its sign
+    real t1 = (real)1e300;
+    int drop = -1;
 #pragma unroll
-        for (int j = 0; j <= i; ++j) M[i][j] = (i < q_n) ? (real)G[(act[i] * NC + act[j]) * gs] : (i == j ? (real)1 : (real)0);
-      }
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        real dj = M[j][j];
-#pragma unroll
-        for (int k = 0; k < j; ++k) dj -= M[j][k] * M[j][k];
-        const real inv = (real)1 / sqrt(fmax(dj, (real)1e-30));
-        M[j][j] = inv;
-#pragma unroll
-        for (int i = j + 1; i < NV; ++i) {
-          real v = M[i][j];
-#pragma unroll
-          for (int k = 0; k < j; ++k) v -= M[i][k] * M[j][k];
-          M[i][j] = v * inv;
+    for (int c = 0; c < NC; ++c) {
+      if ((in_act >> c) & 1u) {
+        const real dl = -sig * col[c];
+        const real l = lam[c];
+        if ((l > (real)0 && dl < (real)0) || (l < (real)0 && dl > (real)0)) {
+          const real tt = -l / dl;
+          if (tt < t1) t1 = tt, drop = c;
         }
       }
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        real t = r[i];
-#pragma unroll
-        for (int k = 0; k < i; ++k) t -= M[i][k] * y[k];
-        y[i] = t * M[i][i];
-      }
-#pragma unroll
-      for (int i = NV - 1; i >= 0; --i) {
-        real t = y[i];
-#pragma unroll
-        for (int k = i + 1; k < NV; ++k) t -= M[k][i] * y[k];
-        y[i] = t * M[i][i];
-      }
-      const real gbb = (real)G[(bs * NC + bs) * gs];
-      real rho_s = gbb;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) rho_s -= r[i] * y[i];
-      const real need = (sig > (real)0) ? (p[bs] - hi[bs]) : (lo[bs] - p[bs]);
-      // the entering normal is linearly dependent on the active ones when its Schur complement vanishes (always when the
-      // active set is full): no primal step, only multipliers can move
-      const real t2 = (q_n < NV && rho_s > kDepTol<real>() * gbb) ? need / rho_s : (real)1e300;
-      // blocking ratio: the signed multiplier of an active constraint must keep its sign
-      real t1 = (real)1e300;
-      int drop = -1;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        if (i < q_n) {
-          const real dl = -sig * y[i];
-          const real l = lam[act[i]];
-          if ((l > (real)0 && dl < (real)0) || (l < (real)0 && dl > (real)0)) {
-            const real tt = -l / dl;
-            if (tt < t1) t1 = tt, drop = i;
-          }
-        }
-      }
-      const real t = fmin(t1, t2);
+    }
+    const real t = fmin(t1, t2);
 #if defined(ML4CA_GI_DEBUG)
-      printf("  gi NV=%d bs=%d sig=%+.0f q=%d need=%.3e rho_s=%.3e gbb=%.3e t1=%.3e t2=%.3e drop=%d act:", NV, bs, (double)sig, q_n,
-             (double)need, (double)rho_s, (double)gbb, (double)t1, (double)t2, drop);
-      for (int i = 0; i < q_n; ++i) printf(" %d(%.2e)", act[i], (double)lam[act[i]]);
-      printf("\n");
+    printf("  gi NV=%d bs=%d sig=%+.0f q=%d need=%.3e rho_s=%.3e gbb=%.3e t1=%.3e t2=%.3e drop=%d mask=%x\n", NV, bs, (double)sig,
+           n_act, (double)need, (double)rho_s, (double)gbb, (double)t1, (double)t2, drop, in_act);
 #endif
-      if (t >= (real)1e299) {
-        feasible = false;
-        break;
-      }
-      // move: p_c -= sig rho_c t,  multipliers of the active constraints += dl t,  of the entering one += sig t
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        real rho = (real)G[(c * NC + bs) * gs];
-#pragma unroll
-        for (int i = 0; i < NV; ++i)
-          if (i < q_n) rho -= (real)G[(c * NC + act[i]) * gs] * y[i];
-        p[c] -= sig * rho * t;
-      }
-#pragma unroll
-      for (int i = 0; i < NV; ++i)
-        if (i < q_n) lam[act[i]] -= sig * y[i] * t;
-      lam[bs] += sig * t;
-      if (t2 <= t1) {
-        if (q_n < NV) {
-#pragma unroll
-          for (int i = 0; i < NV; ++i)
-            if (i == q_n) act[i] = bs;
-          q_n += 1;
-          in_act |= 1u << bs;
-          p[bs] = (sig > (real)0) ? hi[bs] : lo[bs];   // exactly on its bound
-        }
-        added = true;
-      } else {
-        const int gone = act[drop];
-#pragma unroll
-        for (int i = 0; i < NV - 1; ++i)
-          if (i >= drop) act[i] = act[i + 1];
-        q_n -= 1;
-        in_act &= ~(1u << gone);
-        lam[gone] = (real)0;
-      }
+    if (t >= (real)1e299) {
+      feasible = false;
+      break;
     }
-    if (!feasible) break;
+    // move: inactive values p_c -= sig S[c][bs] t, active multipliers += dl t, the entering one += sig t
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if ((in_act >> c) & 1u) lam[c] -= sig * col[c] * t;
+      else p[c] -= sig * col[c] * t;
+      if (c == bs) lam[c] += sig * t;
+    }
+    if (t2 <= t1) {
+      tableau_sweep<real, greal, NC>(G, gs, bs, col, (real)1);
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (c == bs) p[c] = (sig > (real)0) ? hi[c] : lo[c];   // exactly on its bound
+      in_act |= 1u << bs;
+      n_act += 1;
+      bs = -1;
+    } else {
+      real rowd[NC];
+      tableau_row<real, greal, NC>(G, gs, drop, rowd);
+      tableau_sweep<real, greal, NC>(G, gs, drop, rowd, (real)-1);
+      in_act &= ~(1u << drop);
+      n_act -= 1;
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (c == drop) lam[c] = (real)0;
+    }
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) d[i] = p[i];
@@ -494,7 +478,7 @@ ML4CA_HD_CALL bool solve_reduced_qp(real (&H)[NV][NV] /* lower triangle; destroy
 }
 
 // ---- SLSQPB ----------------------------------------------------------------------------------------------------------
-enum Mode { kRunning = -1, kSuccess = 0, kIncompatible = 4, kPosDirDeriv = 8, kIterLimit = 9 };
+enum Mode { kDeferred = -2, kRunning = -1, kSuccess = 0, kIncompatible = 4, kPosDirDeriv = 8, kIterLimit = 9 };
 
 template <typename real>
 struct State {
@@ -524,7 +508,10 @@ ML4CA_HD void slsqp_init(const Problem<real>& P, const Objective& o, State<real>
 }
 
 // One major iteration (QP, merit line search, BFGS update).  Returns true when the solve has finished (S.mode set).
-template <typename real, typename greal>
+// ALLOW_AUG = false: an inconsistent linearisation does not run the augmented sub-problem but returns with
+// S.mode = kDeferred and the state untouched (the kernel solves such demands in a second phase, so that the lanes of a warp
+// either all skip or all run the 6-variable problem).
+template <typename real, typename greal, bool ALLOW_AUG = true>
 ML4CA_HD bool slsqp_iterate(const Problem<real>& P, const Objective& o, State<real>& S, greal* __restrict__ G, int gs) {
   const real acc = (real)kAcc, tol = (real)10 * acc, sb = (real)ML4CA_QP_SLACK_BOUND;
   Point<real>& pt = S.pt;
@@ -577,6 +564,11 @@ ML4CA_HD bool slsqp_iterate(const Problem<real>& P, const Objective& o, State<re
     ok = solve_reduced_qp<real, greal, 5>(H, q, S.J, lo, hi, G, gs, dz, lam);
 #pragma unroll
     for (int r = 0; r < 3; ++r) lamrow[r] = lam[5 + r];
+  }
+  if (!ok && !ALLOW_AUG) {
+    S.iter -= 1;
+    S.mode = kDeferred;
+    return true;
   }
   if (!ok) {
     // inconsistent linearisation: augmented problem in (dz, w), w = 1 - delta in [0, 1]

@@ -1,8 +1,9 @@
 """Import the UNMODIFIED reference modules from /root/reference behind stub modules.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  Only works in the build container, where the
-read-only reference checkout exists; on the GPU box ``available()`` is False and callers fall back
-to the committed golden vectors under tests/golden/.
+TEST INFRASTRUCTURE (see oracle/__init__.py).  In the build container the modules come from the
+read-only checkout; on the GPU box, where /root/reference does not exist, the env wrapper and the QP
+allocator come from oracle/_ref/ (byte-compiled from the checkout by oracle/build_ref.py, travels with the
+repository snapshot), everything else from the committed golden vectors under tests/golden/.
 
 Stubbed third-party modules (absent here, and irrelevant to the arithmetic on the hot path):
   gym / gym.spaces   -> ``Env`` base class and a ``Box`` record   (customEnv.py:1-2,62-64)
@@ -20,10 +21,56 @@ import types
 REFERENCE_ROOT = os.environ.get("ML4CA_REFERENCE_ROOT", "/root/reference")
 _RL_ROOT = os.path.join(REFERENCE_ROOT, "src", "rl", "windows_workspace")
 _QP_ROOT = os.path.join(REFERENCE_ROOT, "src", "qp", "ROS", "qp_allocator", "src")
+# oracle/_ref/: the same modules byte-compiled from the checkout by oracle/build_ref.py (travels to the GPU box)
+_REF_COMPILED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def have_checkout():
+    return os.path.isfile(os.path.join(_RL_ROOT, "specific", "customEnv.py"))
+
+
+_COMPILED_MODULES = ("specific.customEnv", "specific.errorFrame", "specific.misc.mathematics", "specific.misc.simtools",
+                     "qp_allocator")
+
+
+def have_compiled():
+    return all(os.path.isfile(os.path.join(_REF_COMPILED, m + ".refbin")) for m in _COMPILED_MODULES)
+
+
+class _CompiledFinder(object):
+    """Meta-path finder for oracle/_ref/<dotted name>.refbin (sourceless byte code of the reference modules; `specific` and
+    `specific.misc` are empty namespace packages, as in the reference)."""
+
+    @staticmethod
+    def find_spec(name, path=None, target=None):
+        import importlib.machinery as mach
+        if name in ("specific", "specific.misc"):
+            spec = mach.ModuleSpec(name, None, is_package=True)
+            spec.submodule_search_locations = []
+            return spec
+        if name in _COMPILED_MODULES:
+            f = os.path.join(_REF_COMPILED, name + ".refbin")
+            return importlib.util.spec_from_file_location(name, f, loader=mach.SourcelessFileLoader(name, f))
+        return None
 
 
 def available():
-    return os.path.isfile(os.path.join(_RL_ROOT, "specific", "customEnv.py"))
+    """The reference's env wrapper and QP allocator can be imported (from the checkout, else from oracle/_ref)."""
+    return have_checkout() or have_compiled()
+
+
+def source():
+    return "checkout" if have_checkout() else ("oracle/_ref" if have_compiled() else None)
+
+
+def _prepare_import():
+    """Make `specific.*` and `qp_allocator` importable from the checkout, else from oracle/_ref."""
+    if have_checkout():
+        for root in (_RL_ROOT, _QP_ROOT):
+            if root not in sys.path:
+                sys.path.insert(0, root)
+    elif not any(isinstance(f, type) and f is _CompiledFinder for f in sys.meta_path):
+        sys.meta_path.insert(0, _CompiledFinder)
 
 
 def _install_stubs():
@@ -105,10 +152,9 @@ def _install_stubs():
 def load_env_module():
     """-> the reference ``specific.customEnv`` module (Revolt, RevoltFinal, ...)."""
     if not available():
-        raise RuntimeError("reference checkout not present at %s" % REFERENCE_ROOT)
+        raise RuntimeError("reference not present (neither %s nor oracle/_ref)" % REFERENCE_ROOT)
     _install_stubs()
-    if _RL_ROOT not in sys.path:
-        sys.path.insert(0, _RL_ROOT)
+    _prepare_import()
     return importlib.import_module("specific.customEnv")
 
 
@@ -120,10 +166,9 @@ def load_error_frame_module():
 def load_qp_module():
     """-> the reference ROS ``qp_allocator`` module (class QPTA)."""
     if not available():
-        raise RuntimeError("reference checkout not present at %s" % REFERENCE_ROOT)
+        raise RuntimeError("reference not present (neither %s nor oracle/_ref)" % REFERENCE_ROOT)
     _install_stubs()
-    if _QP_ROOT not in sys.path:
-        sys.path.insert(0, _QP_ROOT)
+    _prepare_import()
     return importlib.import_module("qp_allocator")
 
 
@@ -131,7 +176,7 @@ def load_rl_allocator_module():
     """-> the reference deployment node module ``rl_allocator`` (class RLTA) with its siblings ``errorFrame`` and
     ``utils`` (src/rl/ROS/rl_allocator/src).  TensorFlow, ROS messages and the policy loader are stubbed; construct
     ``RLTA()`` after setting ``module.load_policy`` to a function returning the actor stub."""
-    if not available():
+    if not have_checkout():
         raise RuntimeError("reference checkout not present at %s" % REFERENCE_ROOT)
     _install_stubs()
     cmsg = sys.modules["custom_msgs.msg"]

@@ -20,7 +20,7 @@ static Objective g_obj = default_objective();
 template <typename real, typename greal>
 static void run(int64_t n, const double* tau, const double* prev, double* x, int32_t* mode, int32_t* iter, int32_t* mask) {
   const Objective obj = g_obj;
-  std::vector<greal> G(81);
+  std::vector<greal> G(45);
   for (int64_t j = 0; j < n; ++j) {
     real t[3], p[5];
     for (int i = 0; i < 3; ++i) t[i] = (real)tau[i * n + j];

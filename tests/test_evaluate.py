@@ -12,7 +12,7 @@ from oracle import eval_oracle as EV
 from oracle import ref_loader
 
 
-@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present")
+@pytest.mark.skipif(not ref_loader.have_checkout(), reason="reference checkout not present")
 def test_iae_oracle_equals_reference_common_py():
     """results/all_plots/common.py IAE itself (matplotlib stubbed out) on a random run."""
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.gridspec"):
