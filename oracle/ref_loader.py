@@ -225,6 +225,59 @@ def load_rl_allocator_module():
                 sys.modules[k] = v
 
 
+def load_ppo_module():
+    """-> the reference ``spinup.algos.tf1.ppo.ppo`` module (TrajectoryBuffer, and through it core.discount_cumsum and
+    mpi_tools.mpi_statistics_scalar), imported UNMODIFIED behind stubs for tensorflow (only touched inside functions that
+    build graphs, and for default arguments), gym and mpi4py (one process: Allreduce copies).  Checkout only."""
+    if not have_checkout():
+        raise RuntimeError("reference checkout not present at %s" % REFERENCE_ROOT)
+    _install_stubs()
+
+    class _Anything(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            child = _Anything(self.__name__ + "." + name)
+            setattr(self, name, child)
+            return child
+
+        def __call__(self, *a, **k):
+            return self
+
+    if "tensorflow" not in sys.modules or not isinstance(sys.modules["tensorflow"], _Anything):
+        tf = _Anything("tensorflow")
+        tf.train.AdamOptimizer = type("AdamOptimizer", (object,), {})    # base class of mpi_tf.MpiAdamOptimizer (:29)
+        sys.modules["tensorflow"] = tf
+    gym_spaces = sys.modules["gym.spaces"]
+    if "mpi4py" not in sys.modules:
+        import numpy as np
+        mpi4py = types.ModuleType("mpi4py")
+        MPI = types.ModuleType("mpi4py.MPI")
+
+        class _Comm(object):
+            def Get_rank(self):
+                return 0
+
+            def Get_size(self):
+                return 1
+
+            def Allreduce(self, sendbuf, recvbuf, op=None):
+                np.copyto(recvbuf, sendbuf)
+
+            def Bcast(self, x, root=0):
+                pass
+
+        MPI.COMM_WORLD = _Comm()
+        MPI.SUM, MPI.MIN, MPI.MAX = "sum", "min", "max"
+        mpi4py.MPI = MPI
+        sys.modules["mpi4py"] = mpi4py
+        sys.modules["mpi4py.MPI"] = MPI
+    assert hasattr(gym_spaces, "Box") and hasattr(gym_spaces, "Discrete")
+    if _RL_ROOT not in sys.path:
+        sys.path.insert(0, _RL_ROOT)
+    return importlib.import_module("spinup.algos.tf1.ppo.ppo")
+
+
 def wrench(fx, fy, tz):
     _install_stubs()
     return sys.modules["geometry_msgs.msg"].Wrench(fx, fy, tz)

@@ -23,8 +23,11 @@ ros_adapter.npz       : the deployment node RLTA (src/rl/ROS/rl_allocator/src/rl
                         with a stub actor: state vector, ROS-order action, published message fields.
 resetacts_final.npz   : RevoltFinal(reset_acts=True): reset observation with the N(0, 0.1) previous thrust
                         (customEnv.py:179-188) and the first steps after it.
-gae.npz               : reference core.discount_cumsum formulation (scipy.signal.lfilter) and the
-                        TrajectoryBuffer.finish_path arithmetic (ppo.py:82-91).
+error_frame.npz       : the reference's ErrorFrame class on poses with |heading| and |heading error| up to 400 (the deg=True
+                        quirk of wrap_angle on radians only wraps beyond +-180).
+gae.npz               : the reference's own TrajectoryBuffer (ppo.py:21-105) with core.discount_cumsum and
+                        mpi_statistics_scalar, imported unmodified behind tensorflow / gym / mpi4py stubs: store(),
+                        finish_path(last_val) per path (died / cut / epoch end), get().
 """
 import os
 import sys
@@ -189,24 +192,61 @@ def gen_qp(n, seed, workers=None):
 
 
 def gen_gae(seed):
-    """Reference formulas: core.py:48-63 (lfilter) and ppo.py:82-91 -- evaluated directly (TF1 import impossible)."""
+    """The reference's OWN TrajectoryBuffer (ppo.py:21-105; core.discount_cumsum core.py:48-63; mpi_statistics_scalar
+    mpi_tools.py:71-93), imported unmodified behind tensorflow / gym / mpi4py stubs (oracle.ref_loader.load_ppo_module):
+    one buffer of 64 steps filled through store(), closed path by path through finish_path(last_val) -- a died episode
+    (last_val 0), two cut ones (last_val = V) and the epoch end -- then get()."""
+    ppo = ref_loader.load_ppo_module()
     rng = np.random.default_rng(seed)
-    T = 37
+    T = 64
+    gamma, lam = 0.99, 0.97
+    buf = ppo.TrajectoryBuffer(9, 7, T, gamma, lam)
     rews = rng.normal(size=T).astype(np.float32)
     vals = rng.normal(size=T).astype(np.float32)
-    last_val = np.float32(0.37)
-    gamma, lam = 0.99, 0.97
+    ends = {17: 0.0, 30: 0.41, 46: -0.83, 63: 0.37}       # path end (inclusive step) -> last_val handed to finish_path
+    flags = np.zeros(T, dtype=np.uint8)                     # this build's flag byte: 1 terminal, 2 episode-length cut
+    boot = np.zeros(T, dtype=np.float32)
+    for t in range(T):
+        buf.store(rng.normal(size=9), rng.normal(size=7), rews[t], vals[t], 0.0)
+        if t in ends:
+            buf.finish_path(ends[t])
+            if t != T - 1:
+                flags[t] = 1 if ends[t] == 0.0 else 2
+                boot[t] = ends[t]
+    adv_raw, ret = buf.adv_buf.copy(), buf.ret_buf.copy()
+    obs, act, adv_norm, ret2, logp = buf.get()
+    # the single-path case of round 1 (one finish_path at the end)
+    buf1 = ppo.TrajectoryBuffer(9, 7, 37, gamma, lam)
+    r1, v1 = rng.normal(size=37).astype(np.float32), rng.normal(size=37).astype(np.float32)
+    for t in range(37):
+        buf1.store(np.zeros(9), np.zeros(7), r1[t], v1[t], 0.0)
+    buf1.finish_path(np.float32(0.37))
+    return {'rews': r1, 'vals': v1, 'last_val': np.float32(0.37), 'gamma': np.array(gamma), 'lam': np.array(lam),
+            'adv': buf1.adv_buf.copy(), 'ret': buf1.ret_buf.copy(),
+            'multi_rews': rews, 'multi_vals': vals, 'multi_flags': flags, 'multi_boot': boot,
+            'multi_last_val': np.float32(ends[T - 1]), 'multi_adv': adv_raw, 'multi_ret': ret,
+            'multi_adv_normalized': np.asarray(adv_norm, dtype=np.float32)}
 
-    def discount_cumsum(x, discount):
-        return scipy.signal.lfilter([1], [1, float(-discount)], x[::-1], axis=0)[::-1]
 
-    r = np.append(rews, last_val)
-    v = np.append(vals, last_val)
-    deltas = r[:-1] + gamma * v[1:] - v[:-1]
-    adv = discount_cumsum(deltas, gamma * lam).astype(np.float32)
-    ret = discount_cumsum(r, gamma)[:-1].astype(np.float32)
-    return {'rews': rews, 'vals': vals, 'last_val': last_val, 'gamma': np.array(gamma), 'lam': np.array(lam),
-            'adv': adv, 'ret': ret}
+def gen_error_frame(n=512, seed=41):
+    """The reference's ErrorFrame itself (errorFrame.py:4-38; rotation_matrix / wrap_angle mathematics.py:7-17) on poses
+    whose heading and heading error run far beyond +-pi and beyond +-180 (where the deg=True quirk of wrap_angle, applied to
+    radians, finally wraps)."""
+    ef_mod = ref_loader.load_error_frame_module()
+    rng = np.random.default_rng(seed)
+    pos = rng.uniform(-1, 1, (3, n)) * np.array([[8.0], [8.0], [4.0]])
+    ref = rng.uniform(-1, 1, (3, n)) * np.array([[8.0], [8.0], [4.0]])
+    big = slice(n // 2, None)
+    pos[2, big] = rng.uniform(-400.0, 400.0, n - n // 2)            # |psi| >= 180 included
+    ref[2, big] = rng.uniform(-400.0, 400.0, n - n // 2)
+    pos[2, n // 2] = 180.0                                           # exactly on the wrap point: (180 + 180) mod 360 - 180
+    ref[2, n // 2] = 0.0
+    pos, ref = pos.astype(np.float32).astype(np.float64), ref.astype(np.float32).astype(np.float64)
+    err = np.zeros((3, n))
+    for j in range(n):
+        ef = ef_mod.ErrorFrame(pos=list(pos[:, j]), ref=list(ref[:, j]))
+        err[:, j] = np.asarray(ef.get_pose(), dtype=np.float64).ravel()
+    return {'pos': pos, 'ref': ref, 'err': err}
 
 
 def gen_policy():
@@ -317,6 +357,14 @@ def main():
         np.savez_compressed(os.path.join(HERE, 'qp_config1.npz'), **out)
         print('wrote qp_config1.npz  success rate %.4f' % out['success'].mean())
         return
+    if "--only-error-frame" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, 'error_frame.npz'), **gen_error_frame())
+        print('wrote error_frame.npz')
+        return
+    if "--only-gae" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, 'gae.npz'), **gen_gae(7))
+        print('wrote gae.npz')
+        return
     if "--only-qp-switches" in sys.argv:
         np.savez_compressed(os.path.join(HERE, 'qp_switches.npz'), **gen_qp_switches())
         print('wrote qp_switches.npz')
@@ -351,6 +399,8 @@ def main():
     print('wrote resetacts_final.npz')
     np.savez_compressed(os.path.join(HERE, 'gae.npz'), **gen_gae(7))
     print('wrote gae.npz')
+    np.savez_compressed(os.path.join(HERE, 'error_frame.npz'), **gen_error_frame())
+    print('wrote error_frame.npz')
     gen_policy()
     np.savez_compressed(os.path.join(HERE, 'ros_adapter.npz'), **gen_ros_adapter())
     print('wrote ros_adapter.npz')

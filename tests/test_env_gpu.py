@@ -278,3 +278,22 @@ def test_bad_arguments_raise(cuda_device):
         E.RevoltLimited(E.StandInHull(), cont_ang=True)
     with pytest.raises(AssertionError):
         E.RevoltSimple(E.StandInHull(), extended_state=True)
+
+
+def test_error_frame_against_the_reference_class(cuda_device):
+    """ml4ca_error_frame / ErrorFrame directly (errorFrame.py:25-32) on the reference's own outputs, including headings and
+    heading errors beyond +-pi (NOT wrapped: wrap_angle's deg=True default on radians) and beyond +-180 (wrapped by 360)."""
+    import ml4ca_b200 as M
+    g = golden("error_frame.npz")
+    ef = M.ErrorFrame(g['pos'], g['ref'], device=cuda_device)
+    err = ef.get_pose().cpu().numpy().astype(np.float64)
+    small = (np.abs(g['pos'][2]) < 10) & (np.abs(g['ref'][2]) < 10)
+    assert small.sum() > 100 and (~small).sum() > 100
+    np.testing.assert_allclose(err[:, small], g['err'][:, small], rtol=0, atol=5e-5)
+    # large arguments: fp32 carries the heading itself to ~2e-5 rad at 400 rad; the position error (<= 23 m) rotates with it
+    np.testing.assert_allclose(err[:, ~small], g['err'][:, ~small], rtol=0, atol=2e-3)
+    big_err = np.abs(g['pos'][2] - g['ref'][2]) >= 180
+    assert big_err.sum() > 10
+    np.testing.assert_allclose(err[2, big_err], g['err'][2, big_err], rtol=0, atol=1e-4)      # wrapped by 360, not by 2 pi
+    between = (np.abs(g['pos'][2] - g['ref'][2]) > np.pi) & ~big_err
+    np.testing.assert_allclose(err[2, between], (g['pos'][2] - g['ref'][2])[between], rtol=0, atol=1e-4)   # not wrapped at all

@@ -21,6 +21,24 @@ def test_golden_single_trajectory(cuda_device):
     np.testing.assert_allclose(buf.ret_buf.cpu().numpy()[:, 0], g['ret'], rtol=0, atol=5e-6)
 
 
+def test_golden_reference_buffer_with_cut_and_died_paths(cuda_device):
+    """The reference's own TrajectoryBuffer (store / finish_path(last_val) per path / get), one env: a died path, two cut
+    paths bootstrapped with last_val = V, the epoch end."""
+    import ml4ca_b200 as M
+    g = golden("gae.npz")
+    T = len(g['multi_rews'])
+    buf = M.TrajectoryBuffer(9, 7, T, 1, gamma=float(g['gamma']), lam=float(g['lam']), device=cuda_device)
+    buf.rew_buf.copy_(torch.as_tensor(g['multi_rews'])[:, None])
+    buf.val_buf[:T].copy_(torch.as_tensor(g['multi_vals'])[:, None])
+    buf.done_buf.copy_(torch.as_tensor(g['multi_flags'])[:, None])
+    buf.finish_path(last_val=torch.tensor([float(g['multi_last_val'])], device=cuda_device),
+                    boot=torch.as_tensor(g['multi_boot'], device=cuda_device)[:, None].contiguous())
+    np.testing.assert_allclose(buf.adv_buf.cpu().numpy()[:, 0], g['multi_adv'], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(buf.ret_buf.cpu().numpy()[:, 0], g['multi_ret'], rtol=0, atol=5e-6)
+    adv_n = buf.get()[2]
+    np.testing.assert_allclose(adv_n.cpu().numpy()[:, 0], g['multi_adv_normalized'], rtol=0, atol=1e-5)
+
+
 @pytest.mark.parametrize("n,T", [(1, 5), (37, 64), (4099, 400)])
 def test_batched_with_path_ends(cuda_device, n, T):
     import ml4ca_b200 as M
