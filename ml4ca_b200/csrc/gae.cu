@@ -46,7 +46,14 @@ __global__ void __launch_bounds__(256) gae_kernel(int64_t n, int T, const float*
 }
 
 // [sum, sum of squares, count] of x in double (mpi_statistics_scalar, mpi_tools.py:71-93: the caller all-reduces the
-// three numbers over ranks before forming mean / std).
+// three numbers over ranks before forming mean / std).  DETERMINISTIC: every block writes its partial sums to a scratch
+// slot, and the block that finishes last adds the slots in index order -- no floating-point atomics, so the advantage
+// normalisation (ppo.py:100-103) is bit-identical run to run.  The scratch is per device and not re-entrant: calls for one
+// device must be ordered on one stream (the training loop's), like every other call on a handle.
+constexpr int kStatsMaxBlocks = 4 * kNumSMs;
+__device__ double g_stats_partial[2 * kStatsMaxBlocks];
+__device__ unsigned int g_stats_ticket = 0;
+
 __global__ void __launch_bounds__(256) stats_kernel(int64_t m, const float* __restrict__ x, double* __restrict__ out3) {
   double s = 0.0, q = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
@@ -60,15 +67,28 @@ __global__ void __launch_bounds__(256) stats_kernel(int64_t m, const float* __re
     q += __shfl_xor_sync(0xFFFFFFFFu, q, off);
   }
   __shared__ double ss[8], qq[8];
+  __shared__ bool last;
   const int w = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) ss[w] = s, qq[w] = q;
   __syncthreads();
   if (threadIdx.x == 0) {
     double S = 0.0, Q = 0.0;
     for (int k = 0; k < 8; ++k) S += ss[k], Q += qq[k];
-    atomicAdd(out3, S);
-    atomicAdd(out3 + 1, Q);
-    if (blockIdx.x == 0) atomicAdd(out3 + 2, (double)m);
+    g_stats_partial[2 * blockIdx.x] = S;
+    g_stats_partial[2 * blockIdx.x + 1] = Q;
+    __threadfence();
+    last = (atomicAdd(&g_stats_ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double S = 0.0, Q = 0.0;
+    for (unsigned k = 0; k < gridDim.x; ++k) {
+      S += *(volatile double*)&g_stats_partial[2 * k];
+      Q += *(volatile double*)&g_stats_partial[2 * k + 1];
+    }
+    out3[0] = S, out3[1] = Q, out3[2] = (double)m;
+    g_stats_ticket = 0;
   }
 }
 

@@ -26,6 +26,7 @@
 #include <stdlib.h>
 
 #include "common.h"
+#include "ppo_generic.h"
 #include "ppo_tc.h"
 
 namespace ml4ca {
@@ -551,9 +552,16 @@ static int ppo_args(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const ch
   int32_t device = 0;
   int rc = ml4ca_policy_describe(p, &cfg, &device);
   if (rc != ML4CA_OK) return rc;
+  *cfg_out = cfg, *device_out = device;
   if (!(cfg.hidden == 64 && cfg.n_hidden == 2 && cfg.obs_dim <= ppo::XR)) {
-    set_error("%s: the training kernels are built for the 64 x 64 networks of the BASELINE config", who);
-    return ML4CA_ERR_UNSUPPORTED;
+    // not the 64 x 64 config the specialised kernels are built for: the caller takes the generic fp32 kernel
+    // (ppo_update_generic.cu: any width <= 96, 1..3 hidden layers -- the reference's 80^3 and 64^3 networks)
+    if (cfg.hidden > 96 || cfg.n_hidden < 1 || cfg.n_hidden > 3 || cfg.obs_dim > 15) {
+      set_error("%s: training kernels exist for hidden widths <= 96 and 1..3 hidden layers", who);
+      return ML4CA_ERR_UNSUPPORTED;
+    }
+    out->params = nullptr;     // marks "generic"
+    return ML4CA_OK;
   }
   const int H = ppo::H, O = cfg.obs_dim, Ad = cfg.act_dim;
   const int pi_size = O * H + H + H * H + H + H * Ad + Ad;
@@ -567,6 +575,21 @@ static int ppo_args(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const ch
   a.n = n, a.T = T;
   *out = a, *cfg_out = cfg, *device_out = device;
   return ML4CA_OK;
+}
+
+// Argument block of the generic kernel for one net of policy p.
+static ppogen::Args generic_args(ml4ca_policy* p, const ml4ca_policy_cfg& cfg, int32_t net, int64_t n, int32_t T) {
+  const int H = cfg.hidden, O = cfg.obs_dim, Ad = cfg.act_dim, NL = cfg.n_hidden;
+  auto net_size = [&](int outw) { return O * H + H + (NL - 1) * (H * H + H) + H * outw + outw; };
+  ppogen::Args g = {};
+  g.params = ml4ca_policy_params(p);
+  g.obs = O, g.act = Ad, g.nout = net == 0 ? Ad : 1;
+  g.hidden = H, g.n_hidden = NL;
+  g.net_off = net == 0 ? 0 : net_size(Ad) + Ad;
+  g.net_params = net_size(g.nout);
+  g.off_ls = net_size(Ad);
+  g.n = n, g.T = T;
+  return g;
 }
 
 static int ppo_launch_fp32(const ppo::Args& a, int activation, int net, cudaStream_t st) {
@@ -600,12 +623,18 @@ int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const flo
   int32_t device = 0;
   int rc = ppo_args(p, net, n, T, "ml4ca_ppo_grad", &a, &cfg, &device);
   if (rc != ML4CA_OK) return rc;
-  a.obs_buf = obs, a.act_buf = act, a.adv = adv, a.logp_old = logp_old, a.ret = ret;
-  a.clip = clip_ratio;
-  a.grad = grad, a.stats = stats;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ML4CA_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)ml4ca_policy_num_params(&cfg), st));
   ML4CA_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 8, st));
+  if (a.params == nullptr) {     // 64^3 / 80^3 ...: generic fp32 kernel
+    ppogen::Args g = generic_args(p, cfg, net, n, T);
+    g.obs_buf = obs, g.act_buf = act, g.adv = adv, g.logp_old = logp_old, g.ret = ret;
+    g.clip = clip_ratio, g.grad = grad, g.stats = stats;
+    return ml4ca_ppo_grad_generic_launch(g, cfg.activation, net, st);
+  }
+  a.obs_buf = obs, a.act_buf = act, a.adv = adv, a.logp_old = logp_old, a.ret = ret;
+  a.clip = clip_ratio;
+  a.grad = grad, a.stats = stats;
   const int64_t tiles = ((n + ppo::TS - 1) / ppo::TS) * T;
   if (tiles == 0) return ML4CA_OK;
   // Default: the tcgen05 kernel (fp16 operands, fp32 TMEM accumulation).  ML4CA_PPO_FP32=1 selects the fp32
@@ -626,6 +655,11 @@ int ml4ca_trpo_policy_mu(ml4ca_policy* p, int64_t n, int32_t T, const float* obs
   int32_t device = 0;
   int rc = ppo_args(p, 0, n, T, "ml4ca_trpo_policy_mu", &a, &cfg, &device);
   if (rc != ML4CA_OK) return rc;
+  if (a.params == nullptr) {
+    ppogen::Args g = generic_args(p, cfg, 0, n, T);
+    g.obs_buf = obs, g.mu_out = mu;
+    return ml4ca_ppo_grad_generic_launch(g, cfg.activation, 0, static_cast<cudaStream_t>(stream));
+  }
   a.obs_buf = obs, a.mu_out = mu;
   if (g_trpo_tc && ((n + ppo::TS - 1) / ppo::TS) * T > 0) {
     __half* blob = nullptr;
@@ -644,11 +678,17 @@ int ml4ca_trpo_kl_grad(ml4ca_policy* p, int64_t n, int32_t T, const float* obs, 
   int32_t device = 0;
   int rc = ppo_args(p, 0, n, T, "ml4ca_trpo_kl_grad", &a, &cfg, &device);
   if (rc != ML4CA_OK) return rc;
-  a.obs_buf = obs, a.act_buf = mu_old, a.kl_ls_old = log_std_old, a.loss_mode = 1;
-  a.grad = grad, a.stats = stats;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ML4CA_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)ml4ca_policy_num_params(&cfg), st));
   ML4CA_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 8, st));
+  if (a.params == nullptr) {
+    ppogen::Args g = generic_args(p, cfg, 0, n, T);
+    g.obs_buf = obs, g.act_buf = mu_old, g.kl_ls_old = log_std_old, g.loss_mode = 1;
+    g.grad = grad, g.stats = stats;
+    return ml4ca_ppo_grad_generic_launch(g, cfg.activation, 0, st);
+  }
+  a.obs_buf = obs, a.act_buf = mu_old, a.kl_ls_old = log_std_old, a.loss_mode = 1;
+  a.grad = grad, a.stats = stats;
   if (g_trpo_tc && ((n + ppo::TS - 1) / ppo::TS) * T > 0) {
     __half* blob = nullptr;
     rc = tc_blob(device, &blob);

@@ -31,6 +31,9 @@
 
 namespace ml4ca {
 
+#ifndef ML4CA_QP_MINBLOCKS
+#define ML4CA_QP_MINBLOCKS 4           // CTAs per SM the register allocation must allow
+#endif
 constexpr int kQpThreads = 64;         // per CTA
 constexpr int kQpMaxPerThread = 64;    // demands per thread in a CTA's chunk (upper limit; the host sizes the chunk)
 constexpr int kQpTableau = 45;         // packed lower triangle of the 9 x 9 pivoting tableau
@@ -103,7 +106,7 @@ __device__ __forceinline__ void load_demand(int64_t n, int64_t env, const float*
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kQpThreads) qp_kernel(int64_t n, const float* __restrict__ tau, float* __restrict__ prev,
+__global__ void __launch_bounds__(kQpThreads, ML4CA_QP_MINBLOCKS) qp_kernel(int64_t n, const float* __restrict__ tau, float* __restrict__ prev,
                                                         float* __restrict__ out, uint32_t* __restrict__ status,
                                                         const slsqp::Objective obj, int per_thread) {
   extern __shared__ double smem_d[];          // tableau [45][kQpThreads]: entry e of thread t at e * kQpThreads + t
@@ -163,11 +166,14 @@ static int launch_qp(int64_t n, const float* tau, float* prev, float* out, uint3
                      cudaStream_t st) {
   // chunk per CTA: large enough that the deferred demands of a chunk fill its lanes in phase 2, small enough that the
   // grid covers the GPU (4 CTAs per SM at 255 registers)
-  int64_t per_thread = (n + (int64_t)kNumSMs * 4 * kQpThreads - 1) / ((int64_t)kNumSMs * 4 * kQpThreads);
+  int64_t per_thread = (n + (int64_t)kNumSMs * ML4CA_QP_MINBLOCKS * kQpThreads - 1) / ((int64_t)kNumSMs * ML4CA_QP_MINBLOCKS * kQpThreads);
   per_thread = per_thread < 1 ? 1 : (per_thread > kQpMaxPerThread ? kQpMaxPerThread : per_thread);
   const int64_t chunk = kQpThreads * per_thread;
   const size_t smem = (size_t)kQpTableau * kQpThreads * sizeof(double) + (size_t)chunk * sizeof(int);
   ML4CA_CUDA(cudaFuncSetAttribute(qp_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
+#ifdef ML4CA_QP_CARVEOUT
+  ML4CA_CUDA(cudaFuncSetAttribute(qp_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, ML4CA_QP_CARVEOUT));
+#endif
   const int64_t blocks = (n + chunk - 1) / chunk;
   qp_kernel<MODE><<<(unsigned)blocks, kQpThreads, smem, st>>>(n, tau, prev, out, status, obj, (int)per_thread);
   return check_launch("qp_kernel");

@@ -47,6 +47,9 @@
 #define ML4CA_HD_CALL inline
 #endif
 
+#ifndef ML4CA_ITERATE_ATTR
+#define ML4CA_ITERATE_ATTR ML4CA_HD
+#endif
 #ifndef ML4CA_QP_TOPTEST
 #define ML4CA_QP_TOPTEST(h1, h2, acc) ((h1) < (acc) && (h2) < (acc))
 #endif
@@ -185,20 +188,21 @@ ML4CA_HD void eval_grad(const Problem<real>& P, const Objective& o, const Point<
   J[0][2] = (real)0, J[1][2] = (real)1, J[2][2] = (real)ML4CA_LX_BOW;
 }
 
-// ---- B = L D L' (unit lower L packed by rows: L(i, j), i > j, at i (i - 1) / 2 + j) ----------------------------------
+// ---- B = L D L' (unit lower L stored as a full 8 x 8 matrix: unit diagonal, zeros above; rolled loops index it freely) ----
 template <typename real>
 struct LDL {
   real D[8];
-  real L[28];
+  real L[8][8];
 };
-#define ML4CA_LIDX(i, j) ((i) * ((i)-1) / 2 + (j))
 
 template <typename real>
 ML4CA_HD void ldl_identity(LDL<real>& B) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) B.D[i] = (real)1;
-#pragma unroll
-  for (int i = 0; i < 28; ++i) B.L[i] = (real)0;
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    B.D[i] = (real)1;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) B.L[i][j] = (i == j) ? (real)1 : (real)0;
+  }
 }
 
 template <typename real>
@@ -216,230 +220,214 @@ template <>
 ML4CA_HD float machine_eps<float>() { return 1.1920929e-07f; }
 
 // Kraft's LDL: factors of L D L' + sigma z z' (Fletcher-Powell composite t-method; a negative update keeps D > 0).
+// Rolled loops (the factors live in memory anyway); one reciprocal per column instead of Kraft's four divisions.
 template <typename real>
-ML4CA_HD_CALL void ldl_update(LDL<real>& B, real (&z)[8], real sigma) {
+ML4CA_HD_CALL void ldl_update(LDL<real>& B, real* z /* [8], destroyed */, real sigma) {
   if (sigma == (real)0) return;
   real w[8];
   real t = (real)1 / sigma;
   if (sigma < (real)0) {
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 8; ++i) w[i] = z[i];
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 8; ++i) {
       const real v = w[i];
       t += v * v / B.D[i];
-#pragma unroll
-      for (int j = i + 1; j < 8; ++j) w[j] -= v * B.L[ML4CA_LIDX(j, i)];
+#pragma unroll 1
+      for (int j = i + 1; j < 8; ++j) w[j] -= v * B.L[j][i];
     }
     if (t >= (real)0) t = machine_eps<real>() / sigma;
-#pragma unroll
+#pragma unroll 1
     for (int i = 7; i >= 0; --i) {
       const real u = w[i];
       w[i] = t;
       t -= u * u / B.D[i];
     }
   }
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 8; ++i) {
     const real v = z[i];
     const real delta = v / B.D[i];
     const real tp = (sigma < (real)0) ? w[i] : t + delta * v;
-    const real alpha = tp / t;
+    const real rt = (real)1 / t;
+    const real alpha = tp * rt;
     B.D[i] *= alpha;
     if (i == 7) break;
     const real beta = delta / tp;
     if (alpha > (real)4) {
       const real gamma = t / tp;
-#pragma unroll
+#pragma unroll 1
       for (int j = i + 1; j < 8; ++j) {
-        const real u = B.L[ML4CA_LIDX(j, i)];
-        B.L[ML4CA_LIDX(j, i)] = gamma * u + beta * z[j];
+        const real u = B.L[j][i];
+        B.L[j][i] = gamma * u + beta * z[j];
         z[j] -= v * u;
       }
     } else {
-#pragma unroll
+#pragma unroll 1
       for (int j = i + 1; j < 8; ++j) {
-        z[j] -= v * B.L[ML4CA_LIDX(j, i)];
-        B.L[ML4CA_LIDX(j, i)] += beta * z[j];
+        z[j] -= v * B.L[j][i];
+        B.L[j][i] += beta * z[j];
       }
     }
     t = tp;
   }
 }
 
-// ---- the reduced QP: min 1/2 d'Hd + q'd  s.t. lo_b <= a_b'd <= hi_b, b < NV: a_b = e_b; b >= NV: a_b = A[b - NV] ------
+// ---- the reduced QP: min 1/2 d'Hd + q'd  s.t. lo_b <= a_b'd <= hi_b, b < nv: a_b = e_b; b >= nv: a_b = A[b - nv] ------
 // Goldfarb-Idnani dual active set in constraint space, carried out as PRINCIPAL PIVOTING on the Gram matrix
-// G = A H^-1 A' (NC x NC, NC = NV + 3): with the active set swept in (symmetric sweep operator), the tableau S holds
+// G = A H^-1 A' (nc x nc, nc = nv + 3): with the active set swept in (symmetric sweep operator), the tableau S holds
 //   S[a][a'] = -(G_AA^-1)     S[a][c] = (G_AA^-1 G_Ac)     S[c][c'] = G_cc' - G_cA G_AA^-1 G_Ac'     (a active, c inactive)
-// so column b of S is everything a dual step on the entering constraint b needs: its Schur complement S[b][b], the change of
+// so row b of S is everything a dual step on the entering constraint b needs: its Schur complement S[b][b], the change of
 // every inactive constraint value, and the change of every active multiplier.  Adding a constraint = one sweep, dropping
-// one = one reverse sweep: NC (NC + 1) / 2 fused multiply-adds and one reciprocal, no factorisation, no triangular solves.
-// S (lower triangle, packed) lives behind a strided pointer (shared memory on the device): the pivot index is the only
-// thing indexed dynamically.  Returns false when the constraints are inconsistent.
-// lam: signed multipliers (> 0 at the upper side, < 0 at the lower side):  H d + q + sum_b lam_b a_b = 0.
-#define ML4CA_SIDX(i, j) ((i) >= (j) ? (i) * ((i) + 1) / 2 + (j) : (j) * ((j) + 1) / 2 + (i))
+// one = one reverse sweep: nc (nc + 1) / 2 fused multiply-adds and one reciprocal, no factorisation, no triangular solves.
+// The same sweep inverts H (nv sweeps) in the same storage: S (lower triangle, packed; shared memory on the device, strided
+// by the CTA size) is the only thing the pivot index addresses.  Everything is written with ROLLED loops over small arrays
+// in memory: one compact copy of the code serves nv = 5 and nv = 6 (the fully unrolled, register-resident variant of
+// this file was 13 k instructions per kernel and spent most of its time waiting for instruction fetches).
+template <typename real>
+struct QP {
+  int nv;            // 5, or 6 with the relaxation variable of the augmented problem
+  real H[21];        // packed lower triangle, nv x nv
+  real q[6];
+  real A[3][6];      // normals of the three slack rows
+  real lo[9], hi[9];
+  real d[6];         // out: the step
+  real lam[9];       // out: signed multipliers (> 0 at the upper side, < 0 at the lower side): H d + q + sum lam_b a_b = 0
+};
 
-template <typename real, typename greal, int NC>
-ML4CA_HD void tableau_row(const greal* __restrict__ S, int gs, int k, real (&row)[NC]) {
-#pragma unroll
-  for (int j = 0; j < NC; ++j) row[j] = (real)S[ML4CA_SIDX(k, j) * gs];
+ML4CA_HD int sidx(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+template <typename real, typename greal>
+ML4CA_HD void tableau_row(const greal* __restrict__ S, int gs, int n, int k, real* row) {
+#pragma unroll 1
+  for (int j = 0; j < n; ++j) row[j] = (real)S[sidx(k, j) * gs];
 }
 
-// sweep (dir = +1: index k enters the active set) or reverse sweep (dir = -1: k leaves it)
-template <typename real, typename greal, int NC>
-ML4CA_HD void tableau_sweep(greal* __restrict__ S, int gs, int k, const real (&row)[NC], real dir) {
-  real dkk = row[0];
-#pragma unroll
-  for (int j = 1; j < NC; ++j)
-    if (j == k) dkk = row[j];
-  const real inv = (real)1 / dkk;
-  real scaled[NC];
-#pragma unroll
-  for (int j = 0; j < NC; ++j) scaled[j] = row[j] * inv;
-#pragma unroll
-  for (int i = 0; i < NC; ++i)
-#pragma unroll
-    for (int j = 0; j <= i; ++j) {
-      const int e = i * (i + 1) / 2 + j;
-      real v = (real)S[e * gs] - row[i] * scaled[j];
-      if (i == k) v = dir * scaled[j];
-      if (j == k) v = dir * scaled[i];
-      if (i == k && j == k) v = -inv;
+// sweep (dir = +1: index k enters) or reverse sweep (dir = -1: k leaves); row = row k of S before the sweep
+template <typename real, typename greal>
+ML4CA_HD_CALL void tableau_sweep(greal* __restrict__ S, int gs, int n, int k, real dir, const real* row) {
+  const real inv = (real)1 / row[k];
+  int e = 0;
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    const real ri = row[i] * inv;
+#pragma unroll 1
+    for (int j = 0; j <= i; ++j, ++e) {
+      real v;
+      if (i == k) v = (j == k) ? -inv : dir * row[j] * inv;
+      else if (j == k) v = dir * ri;
+      else v = (real)S[e * gs] - ri * row[j];
       S[e * gs] = (greal)v;
     }
+  }
 }
 
-template <typename real, typename greal, int NV>
-ML4CA_HD_CALL bool solve_reduced_qp(real (&H)[NV][NV] /* lower triangle; destroyed */, const real (&q)[NV], const real (&A)[3][NV],
-                               real (&lo)[NV + 3], real (&hi)[NV + 3], greal* __restrict__ G, int gs, real (&d)[NV],
-                               real (&lam)[NV + 3]) {
-  constexpr int NC = NV + 3;
-  // K = H^-1 by NV symmetric sweeps of H (Gaussian elimination of an SPD matrix: stable without pivoting)
-  real K[NV][NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i)
-#pragma unroll
-    for (int j = 0; j <= i; ++j) K[i][j] = H[i][j], K[j][i] = H[i][j];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const real inv = (real)1 / K[k][k];
-    real sc[NV];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) sc[j] = K[k][j] * inv;
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-#pragma unroll
-      for (int j = 0; j <= i; ++j) {
-        if (i == k || j == k) continue;
-        const real v = K[i][j] - K[i][k] * sc[j];
-        K[i][j] = v, K[j][i] = v;
-      }
-#pragma unroll
-    for (int j = 0; j < NV; ++j)
-      if (j != k) K[k][j] = sc[j], K[j][k] = sc[j];
-    K[k][k] = -inv;
-  }
-#pragma unroll
-  for (int i = 0; i < NV; ++i)
-#pragma unroll
-    for (int j = 0; j < NV; ++j) K[i][j] = -K[i][j];
-  // V[r] = K A[r]',  G = [K, V'; V, A V'],  p = a_b' d0 with d0 = -K q
-  real V[3][NV];
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      real v = (real)0;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) v += K[i][k] * A[r][k];
-      V[r][i] = v;
+template <typename real, typename greal>
+ML4CA_HD_CALL bool solve_reduced_qp(QP<real>& Q, greal* __restrict__ S, int gs) {
+  const int nv = Q.nv, nc = nv + 3;
+  real row[9];
+  // K = H^-1: copy H into the tableau storage and sweep every index (Gaussian elimination of an SPD matrix: stable
+  // without pivoting); the swept matrix is -K
+  {
+    const int ne = nv * (nv + 1) / 2;
+#pragma unroll 1
+    for (int e = 0; e < ne; ++e) S[e * gs] = (greal)Q.H[e];
+#pragma unroll 1
+    for (int k = 0; k < nv; ++k) {
+      tableau_row<real, greal>(S, gs, nv, k, row);
+      tableau_sweep<real, greal>(S, gs, nv, k, (real)1, row);
     }
-  real p[NC], gdiag[NC];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    real v = (real)0;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) v -= K[i][k] * q[k];
-    p[i] = v;
-    gdiag[i] = K[i][i];
+#pragma unroll 1
+    for (int e = 0; e < ne; ++e) S[e * gs] = -S[e * gs];
   }
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    real v = (real)0;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) v -= V[r][k] * q[k];
-    p[NV + r] = v;
+  // G = [K, V'; V, A V'] with V[r] = K A[r]' (its leading block IS K, already in place);  p = a_b' d0 with d0 = -K q
+  real p[9], gdiag[9], V[3][6];
+#pragma unroll 1
+  for (int i = 0; i < nv; ++i) {
+    real pv = (real)0, v0 = (real)0, v1 = (real)0, v2 = (real)0;
+#pragma unroll 1
+    for (int k = 0; k < nv; ++k) {
+      const real kik = (real)S[sidx(i, k) * gs];
+      pv -= kik * Q.q[k];
+      v0 += kik * Q.A[0][k], v1 += kik * Q.A[1][k], v2 += kik * Q.A[2][k];
+      if (k == i) gdiag[i] = kik;
+    }
+    p[i] = pv;
+    V[0][i] = v0, V[1][i] = v1, V[2][i] = v2;
   }
-#pragma unroll
-  for (int i = 0; i < NV; ++i)
-#pragma unroll
-    for (int j = 0; j <= i; ++j) G[(i * (i + 1) / 2 + j) * gs] = (greal)K[i][j];
-#pragma unroll
+#pragma unroll 1
   for (int r = 0; r < 3; ++r) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) G[((NV + r) * (NV + r + 1) / 2 + i) * gs] = (greal)V[r][i];
-#pragma unroll
+    real pv = (real)0;
+    const int base = (nv + r) * (nv + r + 1) / 2;
+#pragma unroll 1
+    for (int i = 0; i < nv; ++i) {
+      S[(base + i) * gs] = (greal)V[r][i];
+      pv -= V[r][i] * Q.q[i];
+    }
+    p[nv + r] = pv;
+#pragma unroll 1
     for (int s = 0; s <= r; ++s) {
       real v = (real)0;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) v += A[r][k] * V[s][k];
-      G[((NV + r) * (NV + r + 1) / 2 + NV + s) * gs] = (greal)v;
-      if (s == r) gdiag[NV + r] = v;
+#pragma unroll 1
+      for (int k = 0; k < nv; ++k) v += Q.A[r][k] * V[s][k];
+      S[(base + nv + s) * gs] = (greal)v;
+      if (s == r) gdiag[nv + r] = v;
     }
   }
 
   // ---- dual active set by principal pivoting -------------------------------------------------------------------------
-  const real eps = machine_eps<real>();
-  const real vtol = (real)256 * eps;  // relative feasibility tolerance of the sub-problem
-  real iscale[NC];
-#pragma unroll
-  for (int b = 0; b < NC; ++b) {
-    lam[b] = (real)0;
-    iscale[b] = (real)1 / ((real)1 + fmax(fabs(lo[b]), fabs(hi[b])));
-  }
+  const real vtol = (real)256 * machine_eps<real>();  // relative feasibility tolerance of the sub-problem
+#pragma unroll 1
+  for (int b = 0; b < nc; ++b) Q.lam[b] = (real)0;
   unsigned in_act = 0u;
   int n_act = 0;
   int bs = -1;          // entering constraint; stays pending across drops until it has been added
   real sig = (real)1;
   bool feasible = true;
-  for (int gi = 0; gi < 8 * NC; ++gi) {
+#if defined(ML4CA_GI_STATS)
+  int n_steps_dbg = 0;
+#endif
+#pragma unroll 1
+  for (int gi = 0; gi < 8 * nc; ++gi) {
+#if defined(ML4CA_GI_STATS)
+    n_steps_dbg = gi;
+#endif
     if (bs < 0) {
       // most violated inactive constraint (violation relative to the size of its bounds)
-      real worst = vtol;
-#pragma unroll
-      for (int b = 0; b < NC; ++b) {
-        const real vhi = p[b] - hi[b], vlo = lo[b] - p[b];
-        const real v = fmax(vhi, vlo) * iscale[b];
-        if (!((in_act >> b) & 1u) && v > worst) worst = v, bs = b, sig = (vhi > vlo) ? (real)1 : (real)-1;
+      real worst = (real)0;
+#pragma unroll 1
+      for (int b = 0; b < nc; ++b) {
+        if ((in_act >> b) & 1u) continue;
+        const real vhi = p[b] - Q.hi[b], vlo = Q.lo[b] - p[b];
+        const real v = fmax(vhi, vlo);
+        if (v > worst && v > vtol * ((real)1 + fmax(fabs(Q.lo[b]), fabs(Q.hi[b])))) worst = v, bs = b, sig = (vhi > vlo) ? (real)1 : (real)-1;
       }
       if (bs < 0) break;
     }
-    real col[NC];
-    tableau_row<real, greal, NC>(G, gs, bs, col);
-    real rho_s = (real)0, need = (real)0, gbb = (real)0;
-#pragma unroll
-    for (int c = 0; c < NC; ++c)
-      if (c == bs) rho_s = col[c], gbb = gdiag[c], need = (sig > (real)0) ? (p[c] - hi[c]) : (lo[c] - p[c]);
+    tableau_row<real, greal>(S, gs, nc, bs, row);
+    const real rho_s = row[bs], gbb = gdiag[bs];
+    const real need = (sig > (real)0) ? (p[bs] - Q.hi[bs]) : (Q.lo[bs] - p[bs]);
     // the entering normal is linearly dependent on the active ones when its Schur complement vanishes (always when the
     // active set is full): no primal step, only multipliers can move
-    const real t2 = (n_act < NV && rho_s > kDepTol<real>() * gbb) ? need / rho_s : (real)1e300;
-    // blocking ratio: the signed multiplier of an active constraint must keep its sign
-    real t1 = (real)1e300;
+    const real t2 = (n_act < nv && rho_s > kDepTol<real>() * gbb) ? need / rho_s : (real)1e300;
+    // blocking ratio |lam_a| / |d lam_a| over the active constraints whose multiplier moves towards zero (compared by cross
+    // multiplication: one division for the winner)
+    real num = (real)1e300, den = (real)1;
     int drop = -1;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      if ((in_act >> c) & 1u) {
-        const real dl = -sig * col[c];
-        const real l = lam[c];
-        if ((l > (real)0 && dl < (real)0) || (l < (real)0 && dl > (real)0)) {
-          const real tt = -l / dl;
-          if (tt < t1) t1 = tt, drop = c;
-        }
+#pragma unroll 1
+    for (int c = 0; c < nc; ++c) {
+      if (!((in_act >> c) & 1u)) continue;
+      const real dl = -sig * row[c];
+      const real l = Q.lam[c];
+      if ((l > (real)0 && dl < (real)0) || (l < (real)0 && dl > (real)0)) {
+        const real an = fabs(l), ad = fabs(dl);
+        if (an * den < num * ad) num = an, den = ad, drop = c;
       }
     }
+    const real t1 = (drop >= 0) ? num / den : (real)1e300;
     const real t = fmin(t1, t2);
 #if defined(ML4CA_GI_DEBUG)
-    printf("  gi NV=%d bs=%d sig=%+.0f q=%d need=%.3e rho_s=%.3e gbb=%.3e t1=%.3e t2=%.3e drop=%d mask=%x\n", NV, bs, (double)sig,
+    printf("  gi nv=%d bs=%d sig=%+.0f q=%d need=%.3e rho_s=%.3e gbb=%.3e t1=%.3e t2=%.3e drop=%d mask=%x\n", nv, bs, (double)sig,
            n_act, (double)need, (double)rho_s, (double)gbb, (double)t1, (double)t2, drop, in_act);
 #endif
     if (t >= (real)1e299) {
@@ -447,33 +435,32 @@ ML4CA_HD_CALL bool solve_reduced_qp(real (&H)[NV][NV] /* lower triangle; destroy
       break;
     }
     // move: inactive values p_c -= sig S[c][bs] t, active multipliers += dl t, the entering one += sig t
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      if ((in_act >> c) & 1u) lam[c] -= sig * col[c] * t;
-      else p[c] -= sig * col[c] * t;
-      if (c == bs) lam[c] += sig * t;
+    const real st = sig * t;
+#pragma unroll 1
+    for (int c = 0; c < nc; ++c) {
+      if ((in_act >> c) & 1u) Q.lam[c] -= st * row[c];
+      else p[c] -= st * row[c];
     }
+    Q.lam[bs] += st;
     if (t2 <= t1) {
-      tableau_sweep<real, greal, NC>(G, gs, bs, col, (real)1);
-#pragma unroll
-      for (int c = 0; c < NC; ++c)
-        if (c == bs) p[c] = (sig > (real)0) ? hi[c] : lo[c];   // exactly on its bound
+      tableau_sweep<real, greal>(S, gs, nc, bs, (real)1, row);
+      p[bs] = (sig > (real)0) ? Q.hi[bs] : Q.lo[bs];   // exactly on its bound
       in_act |= 1u << bs;
       n_act += 1;
       bs = -1;
     } else {
-      real rowd[NC];
-      tableau_row<real, greal, NC>(G, gs, drop, rowd);
-      tableau_sweep<real, greal, NC>(G, gs, drop, rowd, (real)-1);
+      tableau_row<real, greal>(S, gs, nc, drop, row);
+      tableau_sweep<real, greal>(S, gs, nc, drop, (real)-1, row);
       in_act &= ~(1u << drop);
       n_act -= 1;
-#pragma unroll
-      for (int c = 0; c < NC; ++c)
-        if (c == drop) lam[c] = (real)0;
+      Q.lam[drop] = (real)0;
     }
   }
-#pragma unroll
-  for (int i = 0; i < NV; ++i) d[i] = p[i];
+#if defined(ML4CA_GI_STATS)
+  ML4CA_GI_STATS(nv, n_steps_dbg, feasible);
+#endif
+#pragma unroll 1
+  for (int i = 0; i < nv; ++i) Q.d[i] = p[i];
   return feasible;
 }
 
@@ -500,11 +487,20 @@ ML4CA_HD void slsqp_init(const Problem<real>& P, const Objective& o, State<real>
   eval_point(P, o, S.pt);
   eval_grad(P, o, S.pt, S.g, S.J);
   S.mu[0] = S.mu[1] = S.mu[2] = (real)0;
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 8; ++i) S.s[i] = (real)0;
   ldl_identity(S.B);
   S.f0 = S.pt.f;
   S.iter = 0, S.ireset = 1, S.mode = kRunning;
+}
+
+// row k of Y = L' T (T = [I; J]) and of y0 = L' e (e = [0; c])
+template <typename real>
+ML4CA_HD void y_row(const State<real>& S, int k, real (&Yk)[5], real& y0k) {
+  const real l5 = S.B.L[5][k], l6 = S.B.L[6][k], l7 = S.B.L[7][k];
+#pragma unroll
+  for (int a = 0; a < 5; ++a) Yk[a] = S.B.L[a][k] + l5 * S.J[0][a] + l6 * S.J[1][a] + l7 * S.J[2][a];
+  y0k = l5 * S.pt.c[0] + l6 * S.pt.c[1] + l7 * S.pt.c[2];
 }
 
 // One major iteration (QP, merit line search, BFGS update).  Returns true when the solve has finished (S.mode set).
@@ -512,7 +508,7 @@ ML4CA_HD void slsqp_init(const Problem<real>& P, const Objective& o, State<real>
 // S.mode = kDeferred and the state untouched (the kernel solves such demands in a second phase, so that the lanes of a warp
 // either all skip or all run the 6-variable problem).
 template <typename real, typename greal, bool ALLOW_AUG = true>
-ML4CA_HD bool slsqp_iterate(const Problem<real>& P, const Objective& o, State<real>& S, greal* __restrict__ G, int gs) {
+ML4CA_ITERATE_ATTR bool slsqp_iterate(const Problem<real>& P, const Objective& o, State<real>& S, greal* __restrict__ G, int gs) {
   const real acc = (real)kAcc, tol = (real)10 * acc, sb = (real)ML4CA_QP_SLACK_BOUND;
   Point<real>& pt = S.pt;
   S.iter += 1;
@@ -521,129 +517,103 @@ ML4CA_HD bool slsqp_iterate(const Problem<real>& P, const Objective& o, State<re
     S.mode = kIterLimit;
     return true;
   }
-  // ---- Y = L' T, y0 = L' e  (T = [I; J], e = [0; c]) -------------------------------------------------------------------
-  real Y[8][5], y0[8];
+  // ---- H = T'BT = Y' D Y,  hw = Y' D y0,  hww = y0' D y0   (B = L D L', Y = L' T, y0 = L' e) ------------------------------
+  real H5[15], hw[5], hww = (real)0;
 #pragma unroll
+  for (int e = 0; e < 15; ++e) H5[e] = (real)0;
+#pragma unroll
+  for (int a = 0; a < 5; ++a) hw[a] = (real)0;
+#pragma unroll 1
   for (int k = 0; k < 8; ++k) {
-    real cf[3];   // L(5 + r, k) with the unit diagonal
-#pragma unroll
-    for (int r = 0; r < 3; ++r) cf[r] = (5 + r == k) ? (real)1 : ((5 + r > k) ? S.B.L[ML4CA_LIDX(5 + r, k)] : (real)0);
+    real Yk[5], y0k;
+    y_row(S, k, Yk, y0k);
+    const real dk = S.B.D[k];
 #pragma unroll
     for (int a = 0; a < 5; ++a) {
-      real v = (a == k) ? (real)1 : ((a > k) ? S.B.L[ML4CA_LIDX(a, k)] : (real)0);
+      const real t = dk * Yk[a];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) v += cf[r] * S.J[r][a];
-      Y[k][a] = v;
+      for (int b = 0; b <= a; ++b) H5[a * (a + 1) / 2 + b] += t * Yk[b];
+      hw[a] += t * y0k;
     }
-    y0[k] = cf[0] * pt.c[0] + cf[1] * pt.c[1] + cf[2] * pt.c[2];
+    hww += dk * y0k * y0k;
   }
   real gz[5];   // T' g
 #pragma unroll
   for (int a = 0; a < 5; ++a) gz[a] = S.g[a] + S.J[0][a] * S.g[5] + S.J[1][a] * S.g[6] + S.J[2][a] * S.g[7];
-  real dz[5], lamrow[3], w = (real)1;
-  bool ok;
-  {
-    real H[5][5], q[5], lo[8], hi[8], lam[8];
+  QP<real> Q;
+  Q.nv = 5;
 #pragma unroll
-    for (int a = 0; a < 5; ++a) {
+  for (int e = 0; e < 15; ++e) Q.H[e] = H5[e];
 #pragma unroll
-      for (int b = 0; b <= a; ++b) {
-        real v = (real)0;
+  for (int a = 0; a < 5; ++a) {
+    Q.q[a] = gz[a] + hw[a];
+    Q.lo[a] = P.lo[a] - pt.x[a], Q.hi[a] = P.hi[a] - pt.x[a];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v += S.B.D[k] * Y[k][a] * Y[k][b];
-        H[a][b] = v;
-      }
-      real v = gz[a];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v += S.B.D[k] * Y[k][a] * y0[k];
-      q[a] = v;
-      lo[a] = P.lo[a] - pt.x[a], hi[a] = P.hi[a] - pt.x[a];
-    }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) lo[5 + r] = -sb - pt.x[5 + r] - pt.c[r], hi[5 + r] = sb - pt.x[5 + r] - pt.c[r];
-    ok = solve_reduced_qp<real, greal, 5>(H, q, S.J, lo, hi, G, gs, dz, lam);
-#pragma unroll
-    for (int r = 0; r < 3; ++r) lamrow[r] = lam[5 + r];
+    for (int r = 0; r < 3; ++r) Q.A[r][a] = S.J[r][a];
   }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) Q.lo[5 + r] = -sb - pt.x[5 + r] - pt.c[r], Q.hi[5 + r] = sb - pt.x[5 + r] - pt.c[r];
+  bool ok = solve_reduced_qp<real, greal>(Q, G, gs);
+  real w = (real)1;
   if (!ok && !ALLOW_AUG) {
     S.iter -= 1;
     S.mode = kDeferred;
     return true;
   }
   if (!ok) {
-    // inconsistent linearisation: augmented problem in (dz, w), w = 1 - delta in [0, 1]
-    real rho = (real)kRhoAug;
-    for (int incons = 0; incons <= 5 && !ok; ++incons, rho *= (real)10) {
-      real H[6][6], q[6], A6[3][6], lo[9], hi[9], lam[9], d6[6];
+    // inconsistent linearisation: augmented problem in (dz, w), w = 1 - delta in [0, 1].  It is always feasible (dz = 0,
+    // w = 0), so Kraft's retry with a ten times larger weight (taken when LSQ reports incompatibility) never changes the
+    // outcome here: a failure of the active-set method on it is numerical and ends the solve like SLSQP's mode 4.
+    const real rho = (real)kRhoAug;
+    Q.nv = 6;
 #pragma unroll
-      for (int a = 0; a < 5; ++a) {
+    for (int e = 0; e < 15; ++e) Q.H[e] = H5[e];
 #pragma unroll
-        for (int b = 0; b <= a; ++b) {
-          real v = (real)0;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v += S.B.D[k] * Y[k][a] * Y[k][b];
-          H[a][b] = v;
-        }
-        real v = (real)0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v += S.B.D[k] * Y[k][a] * y0[k];
-        H[5][a] = v;
-        q[a] = gz[a];
-        lo[a] = P.lo[a] - pt.x[a], hi[a] = P.hi[a] - pt.x[a];
-      }
-      real v = rho;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v += S.B.D[k] * y0[k] * y0[k];
-      H[5][5] = v;
-      q[5] = S.g[5] * pt.c[0] + S.g[6] * pt.c[1] + S.g[7] * pt.c[2] - rho;
-      lo[5] = (real)0, hi[5] = (real)1;
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-#pragma unroll
-        for (int a = 0; a < 5; ++a) A6[r][a] = S.J[r][a];
-        A6[r][5] = pt.c[r];
-        lo[6 + r] = -sb - pt.x[5 + r], hi[6 + r] = sb - pt.x[5 + r];
-      }
-      ok = solve_reduced_qp<real, greal, 6>(H, q, A6, lo, hi, G, gs, d6, lam);
-#pragma unroll
-      for (int a = 0; a < 5; ++a) dz[a] = d6[a];
-      w = d6[5];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) lamrow[r] = lam[6 + r];
+    for (int a = 0; a < 5; ++a) {
+      Q.H[15 + a] = hw[a];
+      Q.q[a] = gz[a];
+      Q.lo[a] = P.lo[a] - pt.x[a], Q.hi[a] = P.hi[a] - pt.x[a];
     }
+    Q.H[20] = hww + rho;
+    Q.q[5] = S.g[5] * pt.c[0] + S.g[6] * pt.c[1] + S.g[7] * pt.c[2] - rho;
+    Q.lo[5] = (real)0, Q.hi[5] = (real)1;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      Q.A[r][5] = pt.c[r];
+      Q.lo[6 + r] = -sb - pt.x[5 + r], Q.hi[6 + r] = sb - pt.x[5 + r];
+    }
+    ok = solve_reduced_qp<real, greal>(Q, G, gs);
     if (!ok) {
       S.mode = kIncompatible;
       return true;
     }
+    w = Q.d[5];
   }
   const real h4 = w;   // 1 - delta
+  const int row0 = Q.nv;   // first slack row among the constraints
   // full step d = [dz, J dz + c w],  B d = L (D (Y dz + y0 w)),  multipliers of the equality rows
   real d[8], Bd[8];
 #pragma unroll
-  for (int a = 0; a < 5; ++a) d[a] = dz[a];
+  for (int a = 0; a < 5; ++a) d[a] = Q.d[a];
 #pragma unroll
   for (int r = 0; r < 3; ++r)
-    d[5 + r] = S.J[r][0] * dz[0] + S.J[r][1] * dz[1] + S.J[r][2] * dz[2] + S.J[r][3] * dz[3] + S.J[r][4] * dz[4] + pt.c[r] * w;
-  {
-    real t[8];
+    d[5 + r] = S.J[r][0] * d[0] + S.J[r][1] * d[1] + S.J[r][2] * d[2] + S.J[r][3] * d[3] + S.J[r][4] * d[4] + pt.c[r] * w;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      real v = y0[k] * w;
+  for (int i = 0; i < 8; ++i) Bd[i] = (real)0;
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    real Yk[5], y0k;
+    y_row(S, k, Yk, y0k);
+    real v = y0k * w;
 #pragma unroll
-      for (int a = 0; a < 5; ++a) v += Y[k][a] * dz[a];
-      t[k] = S.B.D[k] * v;
-    }
+    for (int a = 0; a < 5; ++a) v += Yk[a] * d[a];
+    const real tk = S.B.D[k] * v;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      real v = t[i];
-#pragma unroll
-      for (int k = 0; k < i; ++k) v += S.B.L[ML4CA_LIDX(i, k)] * t[k];
-      Bd[i] = v;
-    }
+    for (int i = 0; i < 8; ++i) Bd[i] += S.B.L[i][k] * tk;     // L[i][k] = 0 above the diagonal
   }
   real r[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) r[k] = -(Bd[5 + k] + S.g[5 + k]) - lamrow[k];
+  for (int k = 0; k < 3; ++k) r[k] = -(Bd[5 + k] + S.g[5 + k]) - Q.lam[row0 + k];
   // ---- l1 test, penalties, directional derivative -------------------------------------------------------------------
   S.f0 = pt.f;
   real gs_ = (real)0;
@@ -681,14 +651,13 @@ ML4CA_HD bool slsqp_iterate(const Problem<real>& P, const Objective& o, State<re
   }
   // ---- inexact line search on the l1 merit function -------------------------------------------------------------------
   Point<real> trial;
-  real x0[8], alpha = (real)1, scale = (real)1;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) x0[i] = pt.x[i];
+  real alpha = (real)1, scale = (real)1;
+#pragma unroll 1
   for (int line = 1;; ++line) {
     h3 = alpha * h3;
     scale *= alpha;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) trial.x[i] = x0[i] + scale * d[i];
+    for (int i = 0; i < 8; ++i) trial.x[i] = pt.x[i] + scale * d[i];
     eval_point(P, o, trial);
     const real t = trial.f + S.mu[0] * fabs(trial.c[0]) + S.mu[1] * fabs(trial.c[1]) + S.mu[2] * fabs(trial.c[2]);
     h1 = t - t0;
@@ -727,8 +696,8 @@ ML4CA_HD bool slsqp_iterate(const Problem<real>& P, const Objective& o, State<re
 #pragma unroll
       for (int i = 0; i < 8; ++i) u[i] = h4b * u[i] + ((real)1 - h4b) * v[i];
     }
-    ldl_update(S.B, u, (real)1 / hu);
-    ldl_update(S.B, v, (real)-1 / hv);
+    ldl_update(S.B, &u[0], (real)1 / hu);
+    ldl_update(S.B, &v[0], (real)-1 / hv);
   }
   pt = trial;
 #pragma unroll

@@ -75,6 +75,59 @@ def test_gradients_and_statistics(cuda_device, precision, activation, T, n):
     assert abs(s[1] / N - info["v_loss"]) < stol * info["v_loss"]
 
 
+@pytest.mark.parametrize("hidden", [(80, 80, 80), (64, 64, 64), (48,)])
+@pytest.mark.parametrize("activation", ["leaky_relu", "tanh"])
+def test_gradients_of_the_reference_network_shapes(cuda_device, hidden, activation):
+    """The reference trains 80 x 80 x 80 by default (train.py:30-32; every shipped checkpoint is 80^3 or 64^3): those shapes
+    take the generic fp32 gradient kernel (csrc/ppo_update_generic.cu).  Same float64 restatement, fp32 tolerance; batch
+    sizes around the reference's own (4 x 400 samples) and one ragged multi-tile case."""
+    import ml4ca_b200 as M
+    if len(hidden) == 1:
+        pytest.skip("the forward kernel (policy.cu) is built for 2 and 3 hidden layers")
+    dims = dict(obs_dim=9, act_dim=7, hidden=hidden[0], n_hidden=len(hidden))
+    flat = MO.glorot_params(dims, seed=11)
+    flat = (flat + np.random.default_rng(2).normal(size=flat.size).astype(np.float32) * 0.05).astype(np.float32)
+    ac = M.ActorCritic(9, 7, hidden, activation, params=flat, device=cuda_device)
+    for T, n in ((4, 400), (3, 1037)):
+        obs, act, adv, ret = _batch(T, n, seed=T * n + 1)
+        fo = MO.forward((flat * 1.02).astype(np.float32), dims, _flatten(obs).T, activation)
+        logp_old = MO.gaussian_likelihood(_flatten(act), fo["mu"].T, fo["log_std"]).astype(np.float32).reshape(T, n)
+        g64, info = PO.ppo_gradients(flat.astype(np.float64), dims, _flatten(obs), _flatten(act), adv.reshape(-1).astype(np.float64),
+                                     ret.reshape(-1).astype(np.float64), logp_old.reshape(-1).astype(np.float64), 0.2, activation)
+        upd = M.PPOUpdater(ac)
+        dev = lambda x: torch.as_tensor(x, device=cuda_device).contiguous()
+        data = (dev(obs), dev(act), dev(adv), dev(ret), dev(logp_old))
+        n_pi, N = ac.var_counts[0], float(T * n)
+        s, c = upd._grad(0, data, T, n)
+        assert c == N
+        g_pi = upd.flat[:ac.num_params].cpu().numpy().astype(np.float64) / N
+        assert (g_pi[n_pi:] == 0).all()
+        np.testing.assert_allclose(g_pi[:n_pi], g64[:n_pi], rtol=0, atol=2e-4 * np.abs(g64[:n_pi]).max())
+        assert abs(-s[0] / N - info["pi_loss"]) < 1e-5 * max(1, abs(info["pi_loss"]))
+        assert abs(s[2] / N - info["approx_kl"]) < 1e-5 * max(1e-3, info["approx_kl"]) + 1e-7
+        assert abs(s[3] / N - info["approx_ent"]) < 1e-5 * abs(info["approx_ent"])
+        assert abs(s[4] / N - info["clipfrac"]) <= 2.0 / N + 1e-4
+        s, c = upd._grad(1, data, T, n)
+        g_v = upd.flat[:ac.num_params].cpu().numpy().astype(np.float64) / N
+        assert (g_v[:n_pi] == 0).all()
+        np.testing.assert_allclose(g_v[n_pi:], g64[n_pi:], rtol=0, atol=2e-4 * np.abs(g64[n_pi:]).max())
+        assert abs(s[1] / N - info["v_loss"]) < 1e-5 * info["v_loss"]
+
+
+def test_ppo_trains_the_shipped_architecture(cuda_device):
+    """ppo() end to end with the reference's default network (80 x 80 x 80, leaky-ReLU) at the reference's batch size
+    (4 envs x 400 steps, config.json): the update runs, stops on KL, and the value loss falls within an epoch."""
+    import ml4ca_b200 as M
+    from ml4ca_b200.env import RevoltFinal, StandInHull
+    env = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=4, device=cuda_device, seed=3, auto_reset=True)
+    ac, hist = M.ppo(env, steps_per_epoch=400, epochs=2, seed=3, hidden_sizes=(80, 80, 80), activation="leaky_relu")
+    assert ac.hidden_sizes == (80, 80, 80)
+    for h in hist:
+        assert np.isfinite(h["LossPi"]) and np.isfinite(h["LossV"]) and np.isfinite(h["KL"])
+        assert h["DeltaLossV"] < 0 and 0 <= h["StopIter"] < 80
+    assert hist[-1]["TotalEnvInteracts"] == 2 * 400 * 4
+
+
 def test_adam_step_matches_tf1_formula(cuda_device):
     from ml4ca_b200 import _lib
     rng = np.random.default_rng(0)
