@@ -664,7 +664,7 @@ def run_b200(args, rank, local_rank, world):
             env2 = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=m, device=dev, seed=4,
                                auto_reset=True, env_id_offset=rank * m)
             env2.reset(fraction=0.8)
-            buf = M.TrajectoryBuffer(9, 7, 4, m, device=dev)
+            buf = M.TrajectoryBuffer(9, 7, 32, m, device=dev)     # 32 steps per call: the per-window bootstrap forward (ppo.py:311) is 1 / 32 of a policy pass
             state = {"t": 0}
 
             def roll(fused):
@@ -672,7 +672,7 @@ def run_b200(args, rank, local_rank, world):
                 state["t"] += buf.max_size
             for fused in (False, True):
                 env2.reset(fraction=0.8)
-                t = timed(lambda: roll(fused), 5) / buf.max_size
+                t = timed(lambda: roll(fused), 3, warm=1) / buf.max_size
                 extra["rollout_fused" if fused else "rollout_two_kernel"] = {
                     "workload": "configs[3]: policy forward + env step + trajectory record, 8 Mi envs/GPU, training mode",
                     "value": m / t, "unit": "env-steps/s", "ms_per_step": t * 1e3,

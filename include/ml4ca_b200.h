@@ -263,6 +263,31 @@ ML4CA_API int ml4ca_alloc_to_action(int64_t n, int32_t cont_ang, float ang_bound
 ML4CA_API int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const float* obs, const float* act,
                              const float* adv, const float* ret, const float* logp_old, float clip_ratio, float* grad,
                              double* stats, void* stream);
+/* ---- the whole update() of ppo.py:260-280 as ONE CUDA graph ------------------------------------------------------------------
+ * The early stop of the policy iterations (ppo.py:268-271: `if kl > 1.5 * target_kl: break`, after the step of that
+ * iteration has been applied) needs no host round trip when the flag lives on the device: every pass of iteration i is
+ * skipped when ctl->stop != 0 && ctl->stop_iter < i.  ctl is caller-owned DEVICE memory. */
+typedef struct ml4ca_ppo_ctl {
+  int32_t stop;        /* set by ml4ca_adam_step_dev when the rank-summed approx-KL exceeds the limit */
+  int32_t stop_iter;   /* the iteration whose step was the last one applied */
+  int32_t t_pi, t_v;   /* Adam step counts of the two optimizers (bias correction), advanced by ml4ca_ppo_ctl_end */
+  float first[8];      /* statistics sums of iteration 0: [0..4] of the pi pass, [5] sum (ret - v)^2 of the v pass */
+} ml4ca_ppo_ctl;
+/* stop = 0, stop_iter = INT_MAX (start of an update; t_pi / t_v are kept). */
+ML4CA_API int ml4ca_ppo_ctl_begin(ml4ca_ppo_ctl* ctl, void* stream);
+/* t_pi += iterations actually applied, t_v += v_iters; stop_iter = pi_iters - 1 if the loop ran to its end. */
+ML4CA_API int ml4ca_ppo_ctl_end(ml4ca_ppo_ctl* ctl, int32_t pi_iters, int32_t v_iters, void* stream);
+/* ml4ca_ppo_grad that does nothing when ctl says the loop has stopped before `iter` (ctl = NULL: never skips). */
+ML4CA_API int ml4ca_ppo_grad_ex(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const float* obs, const float* act,
+                                const float* adv, const float* ret, const float* logp_old, float clip_ratio, float* grad,
+                                double* stats, const ml4ca_ppo_ctl* ctl, int32_t iter, void* stream);
+/* ml4ca_adam_step with everything the host loop decided moved to the device: the step count is ctl->t_pi (net 0) or
+ * ctl->t_v (net 1) + iter + 1; skipped like ml4ca_ppo_grad_ex; stats_tail (device, 5 floats: the rank-summed statistics of
+ * this iteration's pass) feeds ctl->first at iter 0 and, for net 0 with kl_limit > 0, the stop test
+ * stats_tail[2] / count > kl_limit (count = global sample count; grad_scale = 1 / count). */
+ML4CA_API int ml4ca_adam_step_dev(int64_t m, float* params, const float* grad, float* m1, float* m2, float lr, float beta1,
+                                  float beta2, float eps, float grad_scale, int32_t net, int32_t iter, const float* stats_tail,
+                                  float count, float kl_limit, ml4ca_ppo_ctl* ctl, void* stream);
 /* ml4ca_ppo_grad runs on the tensor cores by default (tcgen05, fp16 operands, fp32 accumulation: gradients to ~1e-3 of
  * the largest component).  enable = 1 selects the fp32 CUDA-core kernel (1e-5), 0 the tensor-core one, -1 only
  * queries; returns the previous setting.  Initial value: environment variable ML4CA_PPO_FP32. */

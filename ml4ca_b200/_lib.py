@@ -91,6 +91,14 @@ _SIGNATURES = {
     "ml4ca_policy_describe": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PolicyCfg), ctypes.POINTER(ctypes.c_int32)]),
     "ml4ca_ppo_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_f32p,
                                       c_f32p, c_f32p, ctypes.c_float, c_f32p, ctypes.c_void_p, c_stream]),
+    "ml4ca_ppo_grad_ex": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_f32p,
+                                         c_f32p, c_f32p, ctypes.c_float, c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                         c_stream]),
+    "ml4ca_ppo_ctl_begin": (ctypes.c_int, [ctypes.c_void_p, c_stream]),
+    "ml4ca_ppo_ctl_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_stream]),
+    "ml4ca_adam_step_dev": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_float, ctypes.c_float,
+                                           ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int32, ctypes.c_int32,
+                                           c_f32p, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, c_stream]),
     "ml4ca_ppo_use_fp32": (ctypes.c_int, [ctypes.c_int]),
     "ml4ca_trpo_use_tensor_cores": (ctypes.c_int, [ctypes.c_int]),
     "ml4ca_trpo_policy_mu": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_stream]),

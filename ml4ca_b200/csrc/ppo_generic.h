@@ -22,6 +22,8 @@ struct Args {
   float* mu_out;           // forward only
   float* grad;
   double* stats;
+  const int32_t* ctl;       // ml4ca_ppo_ctl (device) or NULL: skip the pass when ctl[0] != 0 && ctl[1] < iter
+  int iter;
 };
 
 }  // namespace ppogen

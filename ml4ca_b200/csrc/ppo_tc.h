@@ -23,6 +23,8 @@ struct Args {
   float* mu_out;
   float* grad;
   double* stats;
+  const int32_t* ctl;       // ml4ca_ppo_ctl (device) or NULL: skip the pass when ctl[0] != 0 && ctl[1] < iter
+  int iter;
 };
 
 constexpr int kBlobHalves = 64 * 16 + 64 * 80 + 16 * 80 + 64 * 16 + 64 * 64;

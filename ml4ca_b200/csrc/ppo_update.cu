@@ -59,7 +59,14 @@ struct Args {
   float* grad;             // flat, same layout as params; this net's block is accumulated into (caller zeroes)
   double* stats;           // [8]: 0 sum pi objective, 1 sum (ret - v)^2, 2 sum 0.5 (logp_old - logp)^2, 3 sum -logp,
                            //      4 clipped count, 5 sample count
+  const int32_t* ctl;      // ml4ca_ppo_ctl (device) or NULL: skip the pass when ctl[0] != 0 && ctl[1] < iter
+  int iter;
 };
+
+// the device-side early stop of the policy loop (include/ml4ca_b200.h: ml4ca_ppo_ctl)
+__device__ __forceinline__ bool pass_skipped(const int32_t* ctl, int iter) {
+  return ctl != nullptr && ctl[0] != 0 && ctl[1] < iter;
+}
 
 struct Smem {
   float w1p[XR][H];     // w1p[k][4 tx + b] = W1[k][tx + 16 b]
@@ -112,6 +119,7 @@ __device__ __forceinline__ void gemm_tile(float (&acc)[8][4], const float (*in)[
 
 template <int ACTIVATION, int NET>
 __global__ void __launch_bounds__(256, 1) ppo_grad_kernel(const Args A) {
+  if (pass_skipped(A.ctl, A.iter)) return;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -493,6 +501,55 @@ __global__ void __launch_bounds__(256) adam_kernel(int64_t m, float* __restrict_
   p[i] -= lr_t * a / (sqrtf(v) + eps);
 }
 
+// Adam step of one optimizer inside the update graph: step count and early stop come from the control block.
+__global__ void __launch_bounds__(256) adam_dev_kernel(int64_t m, float* __restrict__ p, const float* __restrict__ grad,
+                                                       float* __restrict__ m1, float* __restrict__ m2, float lr, float b1, float b2,
+                                                       float eps, float gscale, int net, int iter,
+                                                       const float* __restrict__ tail, float count, float kl_limit,
+                                                       ml4ca_ppo_ctl* __restrict__ ctl) {
+  const int32_t* c32 = reinterpret_cast<const int32_t*>(ctl);
+  if (net == 0 && pass_skipped(c32, iter)) return;
+  __shared__ float lr_t_s;
+  if (threadIdx.x == 0) {
+    const int t = (net == 0 ? ctl->t_pi : ctl->t_v) + iter + 1;
+    lr_t_s = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+  }
+  __syncthreads();
+  const float lr_t = lr_t_s;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) {
+    const float g = grad[i] * gscale;
+    const float a = b1 * m1[i] + (1.0f - b1) * g;
+    const float v = b2 * m2[i] + (1.0f - b2) * g * g;
+    m1[i] = a, m2[i] = v;
+    p[i] -= lr_t * a / (sqrtf(v) + eps);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (iter == 0) {
+      if (net == 0) {
+        for (int q = 0; q < 5; ++q) ctl->first[q] = tail[q];
+      } else {
+        ctl->first[5] = tail[1];
+      }
+    }
+    if (net == 0 && kl_limit > 0.f && tail[2] / count > kl_limit) {     // ppo.py:269-271; the step above stays applied
+      ctl->stop_iter = iter;
+      __threadfence();
+      ctl->stop = 1;
+    }
+  }
+}
+
+__global__ void ppo_ctl_kernel(ml4ca_ppo_ctl* ctl, int begin, int pi_iters, int v_iters) {
+  if (begin) {
+    ctl->stop = 0, ctl->stop_iter = 0x7fffffff;
+  } else {
+    if (!ctl->stop) ctl->stop_iter = pi_iters - 1;
+    ctl->t_pi += ctl->stop_iter + 1;
+    ctl->t_v += v_iters;
+  }
+}
+
 }  // namespace ppo
 }  // namespace ml4ca
 
@@ -535,6 +592,7 @@ static ppotc::Args tc_args(const ppo::Args& a) {
   t.obs_buf = a.obs_buf, t.act_buf = a.act_buf, t.adv = a.adv, t.logp_old = a.logp_old, t.ret = a.ret;
   t.clip = a.clip, t.loss_mode = a.loss_mode, t.kl_ls_old = a.kl_ls_old, t.mu_out = a.mu_out;
   t.grad = a.grad, t.stats = a.stats;
+  t.ctl = a.ctl, t.iter = a.iter;
   return t;
 }
 
@@ -614,6 +672,35 @@ static int ppo_launch_fp32(const ppo::Args& a, int activation, int net, cudaStre
 
 int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const float* obs, const float* act, const float* adv,
                    const float* ret, const float* logp_old, float clip_ratio, float* grad, double* stats, void* stream) {
+  return ml4ca_ppo_grad_ex(p, net, n, T, obs, act, adv, ret, logp_old, clip_ratio, grad, stats, nullptr, 0, stream);
+}
+
+int ml4ca_ppo_ctl_begin(ml4ca_ppo_ctl* ctl, void* stream) {
+  ML4CA_REQUIRE(ctl != nullptr, "ctl is NULL");
+  ppo::ppo_ctl_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(ctl, 1, 0, 0);
+  return check_launch("ppo_ctl_kernel");
+}
+
+int ml4ca_ppo_ctl_end(ml4ca_ppo_ctl* ctl, int32_t pi_iters, int32_t v_iters, void* stream) {
+  ML4CA_REQUIRE(ctl != nullptr && pi_iters >= 1 && v_iters >= 0, "bad arguments");
+  ppo::ppo_ctl_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(ctl, 0, pi_iters, v_iters);
+  return check_launch("ppo_ctl_kernel");
+}
+
+int ml4ca_adam_step_dev(int64_t m, float* params, const float* grad, float* m1, float* m2, float lr, float beta1, float beta2,
+                        float eps, float grad_scale, int32_t net, int32_t iter, const float* stats_tail, float count,
+                        float kl_limit, ml4ca_ppo_ctl* ctl, void* stream) {
+  ML4CA_REQUIRE(m >= 0 && params && grad && m1 && m2 && stats_tail && ctl && iter >= 0 && (net == 0 || net == 1) && count > 0.f,
+                "bad arguments");
+  if (m == 0) return ML4CA_OK;
+  ppo::adam_dev_kernel<<<(unsigned)((m + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      m, params, grad, m1, m2, lr, beta1, beta2, eps, grad_scale, net, iter, stats_tail, count, kl_limit, ctl);
+  return check_launch("adam_dev_kernel");
+}
+
+int ml4ca_ppo_grad_ex(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const float* obs, const float* act, const float* adv,
+                      const float* ret, const float* logp_old, float clip_ratio, float* grad, double* stats,
+                      const ml4ca_ppo_ctl* ctl, int32_t iter, void* stream) {
   ML4CA_REQUIRE(p != nullptr && grad != nullptr && stats != nullptr && obs != nullptr, "policy, obs, grad and stats are required");
   ML4CA_REQUIRE(net == 0 || net == 1, "net: 0 = pi, 1 = v");
   if (net == 0) ML4CA_REQUIRE(act && adv && logp_old, "pi pass needs act, adv and logp_old");
@@ -630,11 +717,13 @@ int ml4ca_ppo_grad(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const flo
     ppogen::Args g = generic_args(p, cfg, net, n, T);
     g.obs_buf = obs, g.act_buf = act, g.adv = adv, g.logp_old = logp_old, g.ret = ret;
     g.clip = clip_ratio, g.grad = grad, g.stats = stats;
+    g.ctl = reinterpret_cast<const int32_t*>(ctl), g.iter = iter;
     return ml4ca_ppo_grad_generic_launch(g, cfg.activation, net, st);
   }
   a.obs_buf = obs, a.act_buf = act, a.adv = adv, a.logp_old = logp_old, a.ret = ret;
   a.clip = clip_ratio;
   a.grad = grad, a.stats = stats;
+  a.ctl = reinterpret_cast<const int32_t*>(ctl), a.iter = iter;
   const int64_t tiles = ((n + ppo::TS - 1) / ppo::TS) * T;
   if (tiles == 0) return ML4CA_OK;
   // Default: the tcgen05 kernel (fp16 operands, fp32 TMEM accumulation).  ML4CA_PPO_FP32=1 selects the fp32

@@ -50,6 +50,7 @@ __host__ __device__ inline size_t smem_floats(int obs, int H, int NL, int P) {
 
 template <int ACTIVATION, int NET>
 __global__ void __launch_bounds__(NW * 32, 1) ppo_grad_generic_kernel(const Args A) {
+  if (A.ctl != nullptr && A.ctl[0] != 0 && A.ctl[1] < A.iter) return;   // the policy loop has stopped (ml4ca_ppo_ctl)
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int obs = A.obs, H = A.hidden, NL = A.n_hidden, nout = A.nout, P = A.net_params;

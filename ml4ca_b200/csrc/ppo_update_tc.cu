@@ -76,6 +76,7 @@ __host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn, int b_mn) {
 __global__ void pack_kernel(Args A, __half* __restrict__ blob) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= BLOB_E) return;
+  if (A.ctl != nullptr && A.ctl[0] != 0 && A.ctl[1] < A.iter) return;   // the policy loop has stopped (ml4ca_ppo_ctl)
   auto inv = [](int f, int K, int& row, int& k) {   // invert canon()
     const int rg = f / (K * 8), rem = f % (K * 8);
     row = rg * 8 + (rem % 64) / 8, k = (rem / 64) * 8 + rem % 8;
@@ -130,6 +131,7 @@ __device__ __forceinline__ float2 act_grad2(uint32_t h2) {
 // S97: the 9 -> 7 (pi) / 9 -> 1 (v) networks of RevoltFinal(extended_state, cont_ang) with the dims known at compile time.
 template <int ACTIVATION, int NET, bool S97>
 __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
+  if (A.ctl != nullptr && A.ctl[0] != 0 && A.ctl[1] < A.iter) return;   // uniform: before any barrier / TMEM allocation
   extern __shared__ __align__(128) uint8_t smem[];
   // warp index through a shuffle: warp-uniform for the compiler, so the group index and every MMA descriptor derived from it
   // live in uniform registers (tcgen05.mma then issues back to back, without a per-thread waterfall loop)

@@ -255,8 +255,85 @@ class PPOUpdater(object):
                 info["LossV"] = s[1] / c
             self._adam(1, c)
 
-    def update(self, buf):
-        """ppo.py:260-280.  ``buf`` = a TrajectoryBuffer after finish_path(); returns the logger's dictionary."""
+    # -- the whole update as one CUDA graph ------------------------------------------------------------------------------
+    def _capture_update(self, data, T, n):
+        """Capture [ctl_begin | pi loop | v loop | ctl_end | refresh | the two loss passes] into one CUDA graph.  The early
+        stop of the policy loop lives on the device (ml4ca_ppo_ctl): the passes of the iterations behind the stopping one
+        return at once, so the host neither launches per iteration nor waits for a KL.  Returns (graph, ctl, out)."""
+        from . import mpi_tools
+        ac, L = self.ac, _lib.lib()
+        dev, P = ac.device, ac.num_params
+        obs, act, adv, ret, logp = data
+        ctl = getattr(self, "_ctl", None)
+        if ctl is None:
+            ctl = self._ctl = torch.zeros(12, dtype=torch.int32, device=dev)       # struct ml4ca_ppo_ctl
+            ctl[2], ctl[3] = self.t_pi, self.t_v
+        out = torch.zeros(16, dtype=torch.float32, device=dev)                      # statistics of the closing loss passes
+        count = float(T) * float(n) * mpi_tools.num_procs()
+        flat, stats, params = self.flat, self.stats, ac.parameters()
+        kl_limit = 1.5 * self.target_kl
+
+        def one_pass(net, it, use_ctl):
+            _lib.check(L.ml4ca_ppo_grad_ex(ac._handle, net, int(n), int(T), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(adv), _lib.ptr(ret),
+                                           _lib.ptr(logp), self.clip_ratio, _lib.ptr(flat), _lib.ptr(stats),
+                                           _lib.ptr(ctl) if use_ctl else None, it, _lib.current_stream()), "ml4ca_ppo_grad_ex")
+            flat[P:P + 5].copy_(stats[:5])
+            mpi_tools.allreduce_sum_(flat)
+
+        def launches():
+            st = _lib.current_stream()
+            _lib.check(L.ml4ca_ppo_ctl_begin(_lib.ptr(ctl), st))
+            for net, iters, lr, limit in ((0, self.train_pi_iters, self.pi_lr, kl_limit), (1, self.train_v_iters, self.vf_lr, 0.0)):
+                lo, hi = (0, self.n_pi) if net == 0 else (self.n_pi, P)
+                for it in range(iters):
+                    one_pass(net, it, net == 0)
+                    _lib.check(L.ml4ca_adam_step_dev(hi - lo, _lib.ptr(params[lo:hi]), _lib.ptr(flat[lo:hi]), _lib.ptr(self.m1[lo:hi]),
+                                                     _lib.ptr(self.m2[lo:hi]), lr, 0.9, 0.999, 1e-8, 1.0 / count, net, it,
+                                                     _lib.ptr(flat[P:P + 5]), count, limit, _lib.ptr(ctl), st), "ml4ca_adam_step_dev")
+            _lib.check(L.ml4ca_ppo_ctl_end(_lib.ptr(ctl), self.train_pi_iters, self.train_v_iters, st))
+            _lib.check(L.ml4ca_policy_refresh(ac._handle, st), "ml4ca_policy_refresh")
+            one_pass(0, 0, False)
+            out[0:5].copy_(flat[P:P + 5])
+            one_pass(1, 0, False)
+            out[5:10].copy_(flat[P:P + 5])
+
+        with torch.cuda.device(dev):
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="relaxed"):
+                launches()
+        return g, ctl, out
+
+    def update_graph(self, buf):
+        """update() replayed from one CUDA graph (captured on the first call per buffer): same arithmetic, same early stop
+        (ppo.py:268-271: the step of the stopping iteration is applied), one launch and one read-back per epoch."""
+        data = buf.get()
+        T, n = buf.max_size, buf.num_envs
+        cache = self.__dict__.setdefault("_update_graphs", {})
+        key = (id(buf), T, n)
+        if key not in cache:
+            cache[key] = self._capture_update(data, T, n)
+        g, ctl, out = cache[key]
+        ctl[2], ctl[3] = self.t_pi, self.t_v        # eager updates in between advance the host-side step counts
+        g.replay()
+        c = float(T) * float(n) * __import__("ml4ca_b200").mpi_tools.num_procs()
+        host = torch.cat([ctl.view(torch.float32).clone(), out]).cpu()             # the one read-back of the epoch
+        ints = host[:4].view(torch.int32).tolist()
+        first, o = host[4:12].tolist(), host[12:28].tolist()
+        self.t_pi, self.t_v = ints[2], ints[3]
+        info = {"StopIter": ints[1], "LossPi": -first[0] / c, "Entropy": first[3] / c, "LossV": first[5] / c,
+                "KL": o[2] / c, "ClipFrac": o[4] / c}
+        info["DeltaLossPi"] = -o[0] / c - info["LossPi"]
+        info["DeltaLossV"] = o[6] / c - info["LossV"]
+        return info
+
+    def update(self, buf, graph=False):
+        """ppo.py:260-280.  ``buf`` = a TrajectoryBuffer after finish_path(); returns the logger's dictionary.
+        graph=True: the whole update from one CUDA graph with a device-side KL stop (update_graph)."""
+        if graph:
+            return self.update_graph(buf)
+        if getattr(self, "_ctl", None) is not None:          # keep the device-side step counts in step with the host's
+            self._ctl[2], self._ctl[3] = self.t_pi, self.t_v
         data = buf.get()
         T, n = buf.max_size, buf.num_envs
         info, stop = {}, 0
@@ -284,13 +361,23 @@ class PPOUpdater(object):
         return info
 
 
+class _GraphUpdater(object):
+    """PPOUpdater whose update() replays the captured graph (what run_epochs calls)."""
+
+    def __init__(self, upd):
+        self.inner = upd
+
+    def update(self, buf):
+        return self.inner.update_graph(buf)
+
+
 PPO_COLUMNS = ('LossPi', 'LossV', 'DeltaLossPi', 'DeltaLossV', 'Entropy', 'KL', 'ClipFrac', 'StopIter')   # ppo.py:339-346
 
 
 def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2, pi_lr=3e-4, vf_lr=1e-3,
         train_pi_iters=80, train_v_iters=80, lam=0.97, target_kl=0.01, seed=0, hidden_sizes=(64, 64),
         activation="leaky_relu", fused=False, logger=None, logger_kwargs=None, graph=False, curriculum=False,
-        reset_each_epoch=True):
+        reset_each_epoch=True, update_graph=None):
     """ppo.py:107-346 for a batched env: every epoch = ``steps_per_epoch`` steps of EVERY environment of ``env``
     (rollout), GAE-lambda (finish_path), advantage normalisation over all ranks, then the PPO update.
     Hyper-parameter defaults are the reference's config.json.  ``logger_kwargs=dict(output_dir=..., exp_name=...)``
@@ -309,6 +396,8 @@ def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2,
     buf = TrajectoryBuffer(env.num_states, env.num_actions, steps_per_epoch, n, gamma, lam, device=dev,
                            max_ep_len=env.max_ep_len)
     upd = PPOUpdater(ac, clip_ratio, pi_lr, vf_lr, train_pi_iters, train_v_iters, target_kl)
+    if update_graph if update_graph is not None else graph:    # graph=True also replays the update from a CUDA graph
+        upd = _GraphUpdater(upd)
     config = dict(steps_per_epoch=steps_per_epoch, epochs=epochs, gamma=gamma, clip_ratio=clip_ratio, pi_lr=pi_lr,
                   vf_lr=vf_lr, train_pi_iters=train_pi_iters, train_v_iters=train_v_iters, lam=lam,
                   target_kl=target_kl, seed=seed)

@@ -128,6 +128,42 @@ def test_ppo_trains_the_shipped_architecture(cuda_device):
     assert hist[-1]["TotalEnvInteracts"] == 2 * 400 * 4
 
 
+@pytest.mark.parametrize("hidden", [(64, 64), (80, 80, 80)])
+def test_graph_update_equals_eager_update(cuda_device, hidden):
+    """PPOUpdater.update(graph=True): the 80 + 80 iterations, the device-side KL stop (ppo.py:268-271) and the closing loss
+    passes replayed from ONE CUDA graph leave the parameters, the Adam moments and the logger's numbers exactly where the
+    host-driven loop leaves them -- over several epochs (the step counts of the bias correction carry over)."""
+    import ml4ca_b200 as M
+    T, n = 4, 4096
+    obs, act, adv, ret = _batch(T, n, seed=17)
+    res = []
+    for use_graph in (False, True):
+        ac = M.ActorCritic(9, 7, hidden, "leaky_relu", device=cuda_device, seed=4)
+        buf = M.TrajectoryBuffer(9, 7, T, n, device=cuda_device)
+        upd = M.PPOUpdater(ac, train_pi_iters=12, train_v_iters=9, target_kl=0.004)
+        infos = []
+        for epoch in range(3):
+            buf.obs_buf.copy_(torch.as_tensor(obs)); buf.act_buf.copy_(torch.as_tensor(act))
+            buf.adv_buf.copy_(torch.as_tensor(adv) * (1.0 + 0.1 * epoch)); buf.ret_buf.copy_(torch.as_tensor(ret))
+            with torch.no_grad():
+                _, _, logp = ac.step(buf.obs_buf.permute(1, 0, 2).reshape(9, -1).contiguous(), deterministic=True)
+            # log-likelihood of the stored actions under the current policy = logp_old (ratio starts at 1)
+            fo = MO.forward(ac.parameters().cpu().numpy(), dict(obs_dim=9, act_dim=7, hidden=hidden[0], n_hidden=len(hidden)),
+                            _flatten(obs).T, "leaky_relu")
+            lp = MO.gaussian_likelihood(_flatten(act), fo["mu"].T, fo["log_std"]).astype(np.float32).reshape(T, n)
+            buf.logp_buf.copy_(torch.as_tensor(lp))
+            infos.append(upd.update(buf, graph=use_graph))
+        res.append((ac.parameters().clone(), upd.m1.clone(), upd.m2.clone(), infos, upd.t_pi, upd.t_v))
+    (pa, m1a, m2a, ia, tpa, tva), (pb, m1b, m2b, ib, tpb, tvb) = res
+    assert [i["StopIter"] for i in ia] == [i["StopIter"] for i in ib]
+    assert any(i["StopIter"] < 11 for i in ia)                      # the KL stop actually fired in some epoch
+    assert (tpa, tva) == (tpb, tvb)
+    assert torch.equal(pa, pb) and torch.equal(m1a, m1b) and torch.equal(m2a, m2b)
+    for a, b in zip(ia, ib):
+        for k in ("LossPi", "LossV", "KL", "Entropy", "ClipFrac", "DeltaLossPi", "DeltaLossV"):
+            assert abs(a[k] - b[k]) <= 1e-6 * max(1.0, abs(a[k])), (k, a[k], b[k])
+
+
 def test_adam_step_matches_tf1_formula(cuda_device):
     from ml4ca_b200 import _lib
     rng = np.random.default_rng(0)
