@@ -128,8 +128,9 @@ def test_ppo_trains_the_shipped_architecture(cuda_device):
     assert hist[-1]["TotalEnvInteracts"] == 2 * 400 * 4
 
 
+@pytest.mark.parametrize("target_kl,want_stop", [(1e-9, 1), (1.0, 11)])
 @pytest.mark.parametrize("hidden", [(64, 64), (80, 80, 80)])
-def test_graph_update_equals_eager_update(cuda_device, hidden):
+def test_graph_update_equals_eager_update(cuda_device, hidden, target_kl, want_stop):
     """PPOUpdater.update(graph=True): the pi / v iterations, the device-side KL stop (ppo.py:268-271) and the closing loss
     passes replayed from ONE CUDA graph leave the parameters, the Adam moments and the logger's numbers where the
     host-driven loop leaves them -- same stopping iterations, over several epochs (the step counts of the bias correction
@@ -141,7 +142,9 @@ def test_graph_update_equals_eager_update(cuda_device, hidden):
     for use_graph in (False, True):
         ac = M.ActorCritic(9, 7, hidden, "leaky_relu", device=cuda_device, seed=4)
         buf = M.TrajectoryBuffer(9, 7, T, n, device=cuda_device)
-        upd = M.PPOUpdater(ac, train_pi_iters=12, train_v_iters=9, target_kl=0.0002, pi_lr=1e-3)
+        # target 1e-9: approx-KL is 0 before the first step (logp_old is the current policy's) and > 0 after it, so the loop stops
+        # at iteration 1 whatever the rounding; target 1: it never stops
+        upd = M.PPOUpdater(ac, train_pi_iters=12, train_v_iters=9, target_kl=target_kl)
         infos = []
         for epoch in range(3):
             buf.obs_buf.copy_(torch.as_tensor(obs)); buf.act_buf.copy_(torch.as_tensor(act))
@@ -156,8 +159,7 @@ def test_graph_update_equals_eager_update(cuda_device, hidden):
             infos.append(upd.update(buf, graph=use_graph))
         res.append((ac.parameters().clone(), upd.m1.clone(), upd.m2.clone(), infos, upd.t_pi, upd.t_v))
     (pa, m1a, m2a, ia, tpa, tva), (pb, m1b, m2b, ib, tpb, tvb) = res
-    assert [i["StopIter"] for i in ia] == [i["StopIter"] for i in ib]
-    assert any(i["StopIter"] < 11 for i in ia)                      # the KL stop actually fired in some epoch
+    assert [i["StopIter"] for i in ia] == [i["StopIter"] for i in ib] == [want_stop] * 3
     assert (tpa, tva) == (tpb, tvb)
     # not bit-equal: the gradient kernels sum their per-CTA partials with atomicAdd, so two runs of either path differ in
     # the last bits; after 3 x (12 + 9) Adam steps the parameters agree to ~1e-6

@@ -30,9 +30,18 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     note = "not bound"
-    if args.bind:
-        import bench
-        note = bench.bind_to_gpu_cpus(local)
+    if args.bind:                       # (bench.py cannot be imported for this: it re-points file descriptor 1)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1} & set(os.sched_getaffinity(0))
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                note = "bound to %d CPUs local to GPU %d" % (len(cpus), local)
+        except Exception as e:  # noqa: BLE001
+            note = "not bound (%r)" % (e,)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.mb << 20

@@ -37,7 +37,7 @@ ac2, hist = M.ppo(env, steps_per_epoch=50, epochs=2, train_pi_iters=5, train_v_i
 p = ac2.parameters().clone()
 ref = p.clone(); dist.broadcast(ref, src=0)
 assert torch.equal(p, ref), "parameters diverged between ranks"
-print("rank %d: 2 PPO epochs over NCCL ok, parameters identical on all ranks; last %s" % (rank, {k: hist[-1][k] for k in ("KL", "LossV", "StopIter")}))
+print("rank %d: 2 PPO epochs over the collective ok, parameters identical on all ranks; last %s" % (rank, {k: hist[-1][k] for k in ("KL", "LossV", "StopIter")}))
 # the same with rollout AND update replayed from CUDA graphs (the NCCL all-reduce of the flat gradient is captured with them)
 import time
 env = M.RevoltFinal(M.StandInHull(), extended_state=True, cont_ang=True, num_envs=hi - lo, device=dev, seed=3,
@@ -49,6 +49,6 @@ ac3, hist3 = M.ppo(env, steps_per_epoch=50, epochs=5, train_pi_iters=5, train_v_
 p = ac3.parameters().clone()
 ref = p.clone(); dist.broadcast(ref, src=0)
 assert torch.equal(p, ref), "parameters diverged between ranks (graph update)"
-print("rank %d: 5 PPO epochs with graph-replayed update over NCCL ok, parameters identical; epoch %.2f ms; last %s" % (
+print("rank %d: 5 PPO epochs with graph-replayed update over the collective ok, parameters identical; epoch %.2f ms; last %s" % (
     rank, 1e3 * (marks[-1] - marks[-2]), {k: hist3[-1][k] for k in ("KL", "LossV", "StopIter")}))
 dist.destroy_process_group()
