@@ -95,8 +95,10 @@ class ActorCritic(object):
 
         class _Holder(object):
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+        holder = _Holder()
+        holder.owner = self          # the view keeps the policy (and with it the library-owned buffer) alive
         with torch.cuda.device(self.device):
-            return torch.as_tensor(_Holder(), device=self.device)
+            return torch.as_tensor(holder, device=self.device)
 
     def refresh(self):
         with torch.cuda.device(self.device):

@@ -169,7 +169,12 @@ static int launch_qp(int64_t n, const float* tau, float* prev, float* out, uint3
   int64_t per_thread = (n + (int64_t)kNumSMs * ML4CA_QP_MINBLOCKS * kQpThreads - 1) / ((int64_t)kNumSMs * ML4CA_QP_MINBLOCKS * kQpThreads);
   per_thread = per_thread < 1 ? 1 : (per_thread > kQpMaxPerThread ? kQpMaxPerThread : per_thread);
   const int64_t chunk = kQpThreads * per_thread;
-  const size_t smem = (size_t)kQpTableau * kQpThreads * sizeof(double) + (size_t)chunk * sizeof(int);
+  size_t smem = (size_t)kQpTableau * kQpThreads * sizeof(double) + (size_t)chunk * sizeof(int);
+  static const size_t pad = [] {     // tuning knob: ML4CA_QP_SMEM_PAD=<bytes> lowers the number of resident CTAs per SM
+    const char* e = getenv("ML4CA_QP_SMEM_PAD");
+    return e ? (size_t)atoll(e) : (size_t)0;
+  }();
+  smem += pad;
   ML4CA_CUDA(cudaFuncSetAttribute(qp_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
 #ifdef ML4CA_QP_CARVEOUT
   ML4CA_CUDA(cudaFuncSetAttribute(qp_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, ML4CA_QP_CARVEOUT));

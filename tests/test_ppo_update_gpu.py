@@ -166,7 +166,8 @@ def test_graph_update_equals_eager_update(cuda_device, hidden, target_kl, want_s
     # Not bit-equal: the gradient kernels sum per-CTA partials with atomicAdd, so two runs of EITHER path differ in the last
     # bits of the gradient, and Adam turns a gradient component at noise level into a step of +-lr whatever its size.  The
     # two paths must agree on all but a few such coordinates and move the parameters by the same vector overall.
-    p0 = M.ActorCritic(9, 7, hidden, "leaky_relu", device=cuda_device, seed=4).parameters().clone()
+    ac0 = M.ActorCritic(9, 7, hidden, "leaky_relu", device=cuda_device, seed=4)
+    p0 = ac0.parameters().clone()
     diff, moved = (pa - pb), (pa - p0)
     assert float((diff.abs() < 2e-5).float().mean()) > 0.97, float((diff.abs() < 2e-5).float().mean())
     assert float(diff.norm() / moved.norm()) < 0.05, float(diff.norm() / moved.norm())
