@@ -27,7 +27,7 @@
 
 #include "common.h"
 #include "ml4ca_constants.h"
-#include "qp_slsqp.cuh"
+#include "qp_group.cuh"
 
 namespace ml4ca {
 
@@ -184,6 +184,166 @@ static int launch_qp(int64_t n, const float* tau, float* prev, float* out, uint3
   return check_launch("qp_kernel");
 }
 
+// ---- the alternative mapping: one demand per group of 8 lanes (qp_group.cuh) -----------------------------------------------
+#ifndef ML4CA_QPG_MINBLOCKS
+#define ML4CA_QPG_MINBLOCKS 2
+#endif
+constexpr int kGrpThreads = 128;                 // 16 groups per CTA
+constexpr int kGrpPerCta = kGrpThreads / 8;
+
+template <int MODE>
+__device__ __forceinline__ void emit_group(const slsqp::DevB& b, int64_t n, int64_t env, const slsqp::GroupSolver<slsqp::DevB>& S,
+                                           const slsqp::Objective& obj, float* __restrict__ prev, float* __restrict__ out,
+                                           uint32_t* __restrict__ status) {
+  const bool ok = (S.mode == slsqp::kSuccess);
+  const unsigned bl = (__ballot_sync(b.mask, S.x <= S.lo + 1e-5) >> b.base) & 0xFFu;
+  const unsigned bu = (__ballot_sync(b.mask, S.x >= S.hi - 1e-5) >> b.base) & 0xFFu;
+  const unsigned amask = (bl & 0x1Fu) | ((bu & 0x1Fu) << 5) | ((bl >> 5) << 10) | ((bu >> 5) << 13);
+  float xv = (float)S.x;
+  if (!obj.raw && fabs(S.x) < ML4CA_QP_CLEAN_EPS) xv = 0.f;       // :232
+  const uint32_t st = (ok ? 1u : 0u) | (amask << 1) | (((uint32_t)S.mode & 15u) << 17) | ((uint32_t)S.iter << 24);
+  if (MODE == 0) {
+    out[(int64_t)b.lane * n + env] = xv;
+    if (b.lane == 0) status[env] = st;
+  } else {
+    // post-processing :267-320 (every lane computes the 7 outputs from the broadcast solution, lane i stores output i)
+    float x[5], pv[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      x[i] = __shfl_sync(b.mask, xv, b.base + i);
+      pv[i] = (float)b.bcast(S.prev, i);
+    }
+    float F[3], al[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) F[i] = ok ? x[i] : pv[i];
+    al[0] = map_to_pi(ok ? x[3] : pv[3]);
+    al[1] = map_to_pi(ok ? x[4] : pv[4]);
+    al[2] = map_to_pi((float)ML4CA_BOW_ANGLE_FIXED);
+    const float K[3] = {(float)ML4CA_K_STERN, (float)ML4CA_K_STERN, (float)ML4CA_K_BOW};
+    float np_[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float fk = F[i] / K[i];
+      np_[i] = copysignf(sqrtf(fabsf(fk)), fk);
+      if (fk == 0.f) np_[i] = 0.f;
+    }
+    const float bow = fminf(fmaxf(np_[2] * (float)ML4CA_BOW_THROTTLE_GAIN, -100.0f), 100.0f);
+    const float o7[8] = {np_[0], np_[1], np_[2], al[0], al[1], al[2], bow, 0.f};
+    const float p5[8] = {F[0], F[1], F[2], al[0], al[1], 0.f, 0.f, 0.f};
+    float ov = o7[0], pw = p5[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) ov = (b.lane == i) ? o7[i] : ov, pw = (b.lane == i) ? p5[i] : pw;
+    if (b.lane < 7) out[(int64_t)b.lane * n + env] = ov;
+    if (b.lane < 5) prev[(int64_t)b.lane * n + env] = pw;
+    if (b.lane == 0 && status != nullptr) status[env] = st;
+  }
+}
+
+__device__ __forceinline__ void load_group(const slsqp::DevB& b, int64_t n, int64_t env, const float* __restrict__ tau,
+                                           const float* __restrict__ prev, const slsqp::Objective& obj,
+                                           slsqp::GroupSolver<slsqp::DevB>& S) {
+  // lane i < 3 loads tau[i], lanes 3..7 load prev[i - 3]; every lane needs all eight
+  const double mine = (b.lane < 3) ? (double)tau[(int64_t)b.lane * n + env] : (double)prev[(int64_t)(b.lane - 3) * n + env];
+  double t3[3], p5[5];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) t3[i] = b.bcast(mine, i);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) p5[i] = b.bcast(mine, 3 + i);
+  S.set_problem(b, t3, p5, obj);
+  S.init(b);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kGrpThreads, ML4CA_QPG_MINBLOCKS) qp_group_kernel(int64_t n, const float* __restrict__ tau,
+                                                                                    float* __restrict__ prev, float* __restrict__ out,
+                                                                                    uint32_t* __restrict__ status,
+                                                                                    const slsqp::Objective obj, int per_group) {
+  extern __shared__ int hard[];               // [chunk]: demands deferred to phase 2
+  __shared__ int next_in_chunk, n_hard, next_hard;
+  if (threadIdx.x == 0) next_in_chunk = kGrpPerCta, n_hard = 0, next_hard = kGrpPerCta;   // first round taken statically
+  __syncthreads();
+  const int chunk = kGrpPerCta * per_group;
+  const int64_t chunk0 = (int64_t)blockIdx.x * chunk;
+  const int chunk_n = (int)((n - chunk0 < chunk) ? (n - chunk0) : chunk);
+  slsqp::DevB b;
+  b.lane = threadIdx.x & 7;
+  b.base = (threadIdx.x & 31) & ~7;
+  b.mask = 0xFFu << b.base;
+  const int group = threadIdx.x >> 3;
+  slsqp::GroupSolver<slsqp::DevB> S;
+  // ---- phase 1: every demand of the chunk, until it finishes or meets an inconsistent linearisation ----------------------
+  {
+    int local = group;
+    bool have = false;
+    while (true) {
+      if (!have) {
+        if (local >= chunk_n) break;
+        load_group(b, n, chunk0 + local, tau, prev, obj, S);
+        have = true;
+      }
+      if (S.iterate(b, false)) {
+        if (S.mode == slsqp::kDeferred) {
+          if (b.lane == 0) hard[atomicAdd(&n_hard, 1)] = local;
+        } else {
+          emit_group<MODE>(b, n, chunk0 + local, S, obj, prev, out, status);
+        }
+        have = false;
+        int nxt = 0;
+        if (b.lane == 0) nxt = atomicAdd(&next_in_chunk, 1);
+        local = __shfl_sync(b.mask, nxt, b.base);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: the deferred demands, restarted; every group may now run the augmented sub-problem -----------------------
+  {
+    const int nh = n_hard;
+    int slot = group, local = 0;
+    bool have = false;
+    while (true) {
+      if (!have) {
+        if (slot >= nh) break;
+        local = hard[slot];
+        load_group(b, n, chunk0 + local, tau, prev, obj, S);
+        have = true;
+      }
+      if (S.iterate(b, true)) {
+        emit_group<MODE>(b, n, chunk0 + local, S, obj, prev, out, status);
+        have = false;
+        int nxt = 0;
+        if (b.lane == 0) nxt = atomicAdd(&next_hard, 1);
+        slot = __shfl_sync(b.mask, nxt, b.base);
+      }
+    }
+  }
+}
+
+template <int MODE>
+static int launch_qp_group(int64_t n, const float* tau, float* prev, float* out, uint32_t* status, const slsqp::Objective& obj,
+                           cudaStream_t st) {
+  const int64_t slots = (int64_t)kNumSMs * ML4CA_QPG_MINBLOCKS * kGrpPerCta;       // resident groups
+  int64_t per_group = (n + slots - 1) / slots;
+  per_group = per_group < 1 ? 1 : (per_group > 256 ? 256 : per_group);
+  const int64_t chunk = kGrpPerCta * per_group;
+  const size_t smem = (size_t)chunk * sizeof(int);
+  const int64_t blocks = (n + chunk - 1) / chunk;
+  qp_group_kernel<MODE><<<(unsigned)blocks, kGrpThreads, smem, st>>>(n, tau, prev, out, status, obj, (int)per_group);
+  return check_launch("qp_group_kernel");
+}
+
+// ML4CA_QP_MAPPING=group selects the 8-lanes-per-demand kernel (qp_group.cuh).  Same results (tests/test_qp_gpu.py runs both);
+// measured on B200, 1 Mi demands: 82 ms against 51.5 ms for the one-thread-per-demand kernel -- its state is in registers
+// (no thread-local traffic to speak of, 23 of 32 lanes active) but it executes 17.5 G warp instructions instead of 10.8 G
+// (partial-mask shuffles and their convergence barriers, group-uniform algebra repeated in 8 lanes) out of 12 k instructions
+// of code with four independently diverging groups per warp: fetch-bound again (profiles/qp_r2.md).  Not the default.
+static bool qp_use_group() {
+  static const bool g = [] {
+    const char* e = getenv("ML4CA_QP_MAPPING");
+    return e != nullptr && e[0] == 'g';
+  }();
+  return g;
+}
+
 static int make_objective(const ml4ca_qp_options* opt, slsqp::Objective& o) {
   o = slsqp::default_objective();
   if (opt == nullptr) return ML4CA_OK;
@@ -223,12 +383,14 @@ int ml4ca_qp_solve_ex(int64_t n, const float* tau, const float* prev, const ml4c
   int rc = make_objective(opt, o);
   if (rc != ML4CA_OK) return rc;
   if (n == 0) return ML4CA_OK;
+  if (qp_use_group()) return launch_qp_group<0>(n, tau, const_cast<float*>(prev), x, status, o, static_cast<cudaStream_t>(stream));
   return launch_qp<0>(n, tau, const_cast<float*>(prev), x, status, o, static_cast<cudaStream_t>(stream));
 }
 
 int ml4ca_qp_allocate(int64_t n, const float* tau, float* prev, float* out, uint32_t* status, void* stream) {
   ML4CA_REQUIRE(n >= 0 && tau && prev && out, "bad arguments");
   if (n == 0) return ML4CA_OK;
+  if (qp_use_group()) return launch_qp_group<1>(n, tau, prev, out, status, slsqp::default_objective(), static_cast<cudaStream_t>(stream));
   return launch_qp<1>(n, tau, prev, out, status, slsqp::default_objective(), static_cast<cudaStream_t>(stream));
 }
 

@@ -137,6 +137,29 @@ def test_single_env_reference_call_shape(cuda_device):
         ta.solve_QP(np.zeros((3, 1)), weight_matrix=Q)
 
 
+def test_both_kernel_mappings_agree(cuda_device):
+    """One thread per demand (default) and one demand over 8 lanes (ML4CA_QP_MAPPING=group, csrc/qp_group.cuh) are the same
+    solver: equal flags and iteration counts, end points equal to fp32 output resolution."""
+    import subprocess
+    code = ("import numpy as np, torch, sys; sys.path.insert(0, %r); import ml4ca_b200 as M; "
+            "g = np.load(%r); ta = M.QPTA(num_envs=4096); ta.previous_thruster_state = g['prev']; "
+            "x, ok = ta.solve_QP(torch.as_tensor(g['tau'], dtype=torch.float32, device='cuda'), raw=True); "
+            "np.savez(sys.argv[1], x=x.cpu().numpy(), st=ta.last_status.cpu().numpy())")
+    outs = []
+    for mapping in ("thread", "group"):
+        path = "/tmp/qp_mapping_%s.npz" % mapping
+        env = dict(os.environ, ML4CA_QP_MAPPING=mapping)
+        subprocess.run([sys.executable, "-c", code % (ROOT, os.path.join(ROOT, "tests", "golden", "qp_config1.npz")), path],
+                       check=True, env=env, cwd=ROOT)
+        outs.append(np.load(path))
+    a, b = outs
+    sa, sb = a['st'].astype(np.uint32), b['st'].astype(np.uint32)
+    np.testing.assert_array_equal(sa & 1, sb & 1)
+    same = ((sa & 1) == 1) & ((sa >> 24) == (sb >> 24))
+    assert same.sum() >= 0.995 * (sa & 1).sum()
+    np.testing.assert_allclose(b['x'][:, same], a['x'][:, same], rtol=0, atol=2e-6)
+
+
 def test_full_size_batch_is_the_tiled_small_one(cuda_device):
     """BASELINE's bench size (1 Mi demands): 256 copies of the 4096-demand golden batch must give 256 identical result
     blocks -- chunking, work fetching and indexing do not depend on the batch size."""

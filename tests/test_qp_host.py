@@ -55,6 +55,20 @@ def test_float64_path_reproduces_the_reference_row_by_row(harness, tmp_path):
     assert same_iter >= 0.98, same_iter                                # stops at the iteration the reference stops at
 
 
+def test_lane_distributed_formulation_is_the_same_solver(harness, tmp_path):
+    """csrc/qp_group.cuh (one demand over 8 lanes, the alternative kernel mapping) on its host backend: same flags, same
+    iteration counts, same end points as the scalar formulation (sums are re-associated: 1e-9)."""
+    g = golden("qp_config1.npz")
+    xa, ma, ia, ka = run(harness, "double", g['tau'], g['prev'], str(tmp_path))
+    xb, mb, ib, kb = run(harness, "group", g['tau'], g['prev'], str(tmp_path))
+    np.testing.assert_array_equal(ma == 0, mb == 0)
+    same = (ma == 0) & (ia == ib)
+    assert same.sum() >= 0.995 * (ma == 0).sum()
+    np.testing.assert_allclose(xb[:, same], xa[:, same], rtol=0, atol=1e-7)
+    cls, dist = qp_parity.classify(g, xb, mb == 0, kb)
+    assert int((cls == 'FLAG').sum()) == 0 and int((cls == 'X').sum()) == 0
+
+
 def test_float32_cannot_follow_the_path(harness, tmp_path):
     """Why the kernel computes in float64: the reference's stopping tests compare |f - f0| with 1e-6, below the
     fp32 resolution of f ~ 10..200; an fp32 path overruns them."""
