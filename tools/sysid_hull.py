@@ -50,6 +50,15 @@ def lag(x, t, T):
     return y
 
 
+# --wrench-lag: the lag acts on the generalised force instead of on the thrust / azimuth commands -- the form the env kernel
+# implements (ml4ca_env_cfg.hull_model = 1: three extra state rows instead of six, no sin / cos inside the sub-steps)
+WRENCH_LAG = '--wrench-lag' in sys.argv
+
+
+def lagged_wrench(n, a, t, T):
+    return lag(wrench(n, a), t, T) if WRENCH_LAG else wrench(lag(n, t, T), lag(a, t, T))
+
+
 def body_rates(t, eta):
     h = t[1] - t[0]
     sm = lambda x, d: savgol_filter(x, 41, 3, deriv=d, delta=h)
@@ -80,7 +89,7 @@ def main():
         rows = {0: [], 1: [], 2: []}; rhs = {0: [], 1: [], 2: []}
         for m, (t, eta, n, a) in runs.items():
             nu, dnu = body_rates(t, eta)
-            tau = wrench(lag(n, t, Tlag), lag(a, t, Tlag))
+            tau = lagged_wrench(n, a, t, Tlag)
             u, v, r = nu
             sl = slice(60, -60)
             # surge:  m11 du - m22 v r + Xu u + Xuu |u| u = tau_x   (m22 taken from the sway fit: iterate twice)
@@ -106,7 +115,7 @@ def main():
         errs = []
         for m, (t, eta, n, a) in runs.items():
             nu, _ = body_rates(t, eta)
-            tau = wrench(lag(n, t, Tlag), lag(a, t, Tlag))
+            tau = lagged_wrench(n, a, t, Tlag)
             h = t[1] - t[0]; W = int(10 / h)
             for s in range(100, len(t) - W - 100, W):
                 sim = simulate(par, eta[:, s], nu[:, s], tau[:, s:s + W], h)
@@ -145,7 +154,7 @@ def fit_simulation_error(window_s=10.0, constrained=False):
         taus = []
         for (e, v0, n, a, pre) in segs:
             tl = np.arange(n.shape[1]) * h
-            tau = wrench(lag(n, tl, Tl), lag(a, tl, Tl))[:, pre:pre + W]
+            tau = lagged_wrench(n, a, tl, Tl)[:, pre:pre + W]
             taus.append(tau)
         tau = np.stack(taus, 2)          # [3, W, nwin]
         N, E, psi = eta0.copy(); u, v, r = nu0.copy()
