@@ -55,12 +55,15 @@ typedef struct ml4ca_env_cfg {
                              step and the returned obs is the first obs of its next episode */
   int32_t reset_acts;     /* Revolt(reset_acts=True), customEnv.py:179-188: every reset draws the previous thrust
                              as scale_and_clip(N(0, 0.1)^3) instead of [0, 0, 0] (:190); default 0 */
-  int32_t reserved1;
+  int32_t hull_model;     /* stand-in hull parameter set (DECLARED, ml4ca_constants.h): 0 = round-1 constants, 1 = the
+                             constants fitted to the reference's recorded box tests (tools/sysid_hull.py) */
   float ss_bounds[6];     /* termination bounds real_ss_bounds (customEnv.py:26,337,361,386) */
   float sim_dt;           /* 0.01 s */
   float step_dt;          /* dt used by the action-derivative penalty = 0.01 * 20 (customEnv.py:81,311,317) */
   float reset_fraction;   /* fraction used by auto_reset (0.8, ppo.py:286,320) */
-  float reserved2;
+  float actuator_lag_s;   /* > 0: the thruster wrench follows its command through a first-order lag of this time constant,
+                             advanced every simulator sub-step (three more state rows; ml4ca_rollout_step refuses it).
+                             0 (default): commanded thrust / azimuth act instantly */
   uint64_t seed;          /* Philox key */
   int64_t env_id_offset;  /* global id of local env 0: RNG streams do not depend on how envs shard over GPUs */
 } ml4ca_env_cfg;

@@ -20,9 +20,9 @@ class EnvCfg(ctypes.Structure):
     _fields_ = [
         ("kind", ctypes.c_int32), ("cont_ang", ctypes.c_int32), ("extended_state", ctypes.c_int32),
         ("n_substeps", ctypes.c_int32), ("max_ep_len", ctypes.c_int32), ("auto_reset", ctypes.c_int32),
-        ("reset_acts", ctypes.c_int32), ("reserved1", ctypes.c_int32),
+        ("reset_acts", ctypes.c_int32), ("hull_model", ctypes.c_int32),
         ("ss_bounds", ctypes.c_float * 6), ("sim_dt", ctypes.c_float), ("step_dt", ctypes.c_float),
-        ("reset_fraction", ctypes.c_float), ("reserved2", ctypes.c_float),
+        ("reset_fraction", ctypes.c_float), ("actuator_lag_s", ctypes.c_float),
         ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_int64),
     ]
 

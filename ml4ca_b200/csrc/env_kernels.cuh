@@ -40,6 +40,7 @@ struct EnvParams {
   float* obs_tail;     // [3, n] tail (prev_thrust / 100) of the last returned observation; fused rollout only
   float* cut_obs;      // [obs_dim, n] caller-owned, nullable (ml4ca_env_set_cut_obs): the observation an env returned at its
                        // episode-length cut, saved before the in-kernel restart replaces it (ppo.py:311 evaluates V on it)
+  float* tau_act;      // [3, n] lagged thruster wrench (N, N, Nm); read and written only when cfg.actuator_lag_s > 0
   int32_t* ep_len;     // [n] episode word: episode counter << 16 | steps in this episode (env_math.cuh)
   int64_t n;
   float bounds[6];
@@ -153,11 +154,13 @@ __device__ __forceinline__ void st_flags(uint8_t* __restrict__ row, int64_t i, c
 }
 
 // ---- K3 ------------------------------------------------------------------------------------------------------------
-template <int KIND, bool CONT, bool EXT, int VEC>
+// LAG = true (one env per thread only): the wrench lag of cfg.actuator_lag_s, three more state rows in and out.
+template <int KIND, bool CONT, bool EXT, int VEC, bool LAG = false>
 __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : (VEC == 2 ? ML4CA_ENV_MIN_BLOCKS2 : 1)) env_step_kernel(const EnvParams p, const float* __restrict__ action,
                                                        float* __restrict__ obs, float* __restrict__ rew,
                                                        uint8_t* __restrict__ done) {
   using T = EnvTraits<KIND, CONT>;
+  static_assert(!LAG || VEC == 1, "the lagged integrator is scalar");
   const int64_t n = p.n, ios = p.io_stride;
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (i0 >= p.count) return;
@@ -186,6 +189,11 @@ __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : (VEC ==
     }
   }
   ld_irow<VEC>(p.ep_len, i0, ep);
+  float tact[3][VEC];
+  if constexpr (LAG) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ld_row<VEC>(p.tau_act + (int64_t)c * n, i0, tact[c]);
+  }
 
   float o[9][VEC], rw[VEC];
   uint32_t flags[VEC];
@@ -227,7 +235,10 @@ __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : (VEC ==
   }
   // ---- phase B: dTwin.step(n_steps), :124 ---------------------------------------------------------------------------
   if (p.n_sub > 0) {
-    if constexpr (VEC == 2) {                                          // two envs per thread: packed FP32 pipe
+    if constexpr (LAG) {
+      integrate_hull_lag(eta[0][0], eta[1][0], eta[2][0], nu[0][0], nu[1][0], nu[2][0], wx[0], wy[0], wn[0], tact[0][0],
+                         tact[1][0], tact[2][0], p.n_sub, p.hull);
+    } else if constexpr (VEC == 2) {                                   // two envs per thread: packed FP32 pipe
       float2 N = make_float2(eta[0][0], eta[0][1]), E = make_float2(eta[1][0], eta[1][1]),
              psi = make_float2(eta[2][0], eta[2][1]), u = make_float2(nu[0][0], nu[0][1]),
              v = make_float2(nu[1][0], nu[1][1]), r = make_float2(nu[2][0], nu[2][1]);
@@ -280,6 +291,7 @@ __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : (VEC ==
       sample_reset(p.seed, p.env_off + i0 + j, ep[j], p.reset_scale, eta[0][j], eta[1][j], eta[2][j], nu[0][j],
                    nu[1][j], nu[2][j]);
       ang[0][j] = T::DEF_BOW, ang[1][j] = T::DEF_PORT, ang[2][j] = T::DEF_STAR;
+      if constexpr (LAG) tact[0][j] = tact[1][j] = tact[2][j] = 0.f;
       float t0[3] = {0.f, 0.f, 0.f};                                   // customEnv.py:190
       if (p.reset_acts) sample_reset_thrust(p.seed, p.env_off + i0 + j, ep[j], t0);   // :179-188 (old episode word)
       ep[j] = next_episode_word(ep[j]);
@@ -300,6 +312,10 @@ __global__ void __launch_bounds__(256, VEC == 1 ? ML4CA_ENV_MIN_BLOCKS : (VEC ==
     if (is_state) st_row<VEC>(p.angles + (int64_t)c * n, i0, ang[c]);
   }
   st_irow<VEC>(p.ep_len, i0, ep);
+  if constexpr (LAG) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st_row<VEC>(p.tau_act + (int64_t)c * n, i0, tact[c]);
+  }
 #pragma unroll
   for (int c = 0; c < (EXT ? 9 : 6); ++c) st_row<VEC>(obs + (int64_t)c * ios, i0, o[c]);
   st_row<VEC>(rew, i0, rw);
@@ -332,6 +348,7 @@ __global__ void __launch_bounds__(256) env_reset_kernel(const EnvParams p, const
   if (p.reset_acts) sample_reset_thrust(p.seed, p.env_off + i, epi, t0);               // :179-188
   p.prev_thrust[i] = t0[0], p.prev_thrust[n + i] = t0[1], p.prev_thrust[2 * n + i] = t0[2];
   p.angles[i] = T::DEF_BOW, p.angles[n + i] = T::DEF_PORT, p.angles[2 * n + i] = T::DEF_STAR;  // :173-177,192
+  p.tau_act[i] = 0.f, p.tau_act[n + i] = 0.f, p.tau_act[2 * n + i] = 0.f;
   p.obs_tail[i] = div100(t0[0]), p.obs_tail[n + i] = div100(t0[1]), p.obs_tail[2 * n + i] = div100(t0[2]);
   p.ep_len[i] = next_episode_word(epi);
   if (obs != nullptr) {

@@ -225,26 +225,35 @@ struct HullConsts {
   float k_vr, k_ur, k_uv;     // Coriolis couplings times h / m
   float one_xu, xuu, one_yv, yvv, one_nr, nrr;  // 1 - h Xu/m11, h Xuu/m11, ...
   float rot_c2, rot_s1, rot_s3;  // -h^2/2, h, -h^3/6: small-angle rotation kernel in terms of r
+  float lag_k;                // h / (T + h): gain of the wrench lag per sub-step (1 = no lag)
 };
 
-inline HullConsts hull_consts(float h) {
+// `model`: ml4ca_env_cfg.hull_model (0 = default constants, 1 = the box-test fit, ml4ca_constants.h); `lag_s`:
+// ml4ca_env_cfg.actuator_lag_s.
+inline HullConsts hull_consts(float h, int model = 0, float lag_s = 0.f) {
+  const bool fit = model == 1;
+  const double m11 = fit ? ML4CA_H1_M11 : ML4CA_M11, m22 = fit ? ML4CA_H1_M22 : ML4CA_M22, m33 = fit ? ML4CA_H1_M33 : ML4CA_M33;
+  const double xu = fit ? ML4CA_H1_XU : ML4CA_XU, xuu = fit ? ML4CA_H1_XUU : ML4CA_XUU;
+  const double yv = fit ? ML4CA_H1_YV : ML4CA_YV, yvv = fit ? ML4CA_H1_YVV : ML4CA_YVV;
+  const double nr = fit ? ML4CA_H1_NR : ML4CA_NR, nrr = fit ? ML4CA_H1_NRR : ML4CA_NRR;
   HullConsts k;
   k.h = h;
-  k.hm1 = (float)((double)h / ML4CA_M11);
-  k.hm2 = (float)((double)h / ML4CA_M22);
-  k.hm3 = (float)((double)h / ML4CA_M33);
-  k.k_vr = (float)((double)h * ML4CA_M22 / ML4CA_M11);
-  k.k_ur = (float)((double)h * ML4CA_M11 / ML4CA_M22);
-  k.k_uv = (float)((double)h * (ML4CA_M22 - ML4CA_M11) / ML4CA_M33);
-  k.one_xu = (float)(1.0 - (double)h * ML4CA_XU / ML4CA_M11);
-  k.xuu = (float)((double)h * ML4CA_XUU / ML4CA_M11);
-  k.one_yv = (float)(1.0 - (double)h * ML4CA_YV / ML4CA_M22);
-  k.yvv = (float)((double)h * ML4CA_YVV / ML4CA_M22);
-  k.one_nr = (float)(1.0 - (double)h * ML4CA_NR / ML4CA_M33);
-  k.nrr = (float)((double)h * ML4CA_NRR / ML4CA_M33);
+  k.hm1 = (float)((double)h / m11);
+  k.hm2 = (float)((double)h / m22);
+  k.hm3 = (float)((double)h / m33);
+  k.k_vr = (float)((double)h * m22 / m11);
+  k.k_ur = (float)((double)h * m11 / m22);
+  k.k_uv = (float)((double)h * (m22 - m11) / m33);
+  k.one_xu = (float)(1.0 - (double)h * xu / m11);
+  k.xuu = (float)((double)h * xuu / m11);
+  k.one_yv = (float)(1.0 - (double)h * yv / m22);
+  k.yvv = (float)((double)h * yvv / m22);
+  k.one_nr = (float)(1.0 - (double)h * nr / m33);
+  k.nrr = (float)((double)h * nrr / m33);
   k.rot_c2 = (float)(-0.5 * (double)h * h);
   k.rot_s1 = h;
   k.rot_s3 = (float)(-(double)h * h * h / 6.0);
+  k.lag_k = lag_s > 0.f ? (float)((double)h / ((double)lag_s + (double)h)) : 1.0f;
   return k;
 }
 
@@ -269,6 +278,42 @@ __device__ __forceinline__ void integrate_hull(float& N, float& E, float& psi, f
     const float un = fmaf(fmaf(-k.xuu, fabsf(u), k.one_xu), u, fmaf(k.k_vr, vr, ax));
     const float vn = fmaf(fmaf(-k.yvv, fabsf(v), k.one_yv), v, fmaf(-k.k_ur, ur, ay));
     const float rn = fmaf(fmaf(-k.nrr, fabsf(r), k.one_nr), r, fmaf(-k.k_uv, uv, an));
+    u = un;
+    v = vn;
+    r = rn;
+    sN = fmaf(-s, v, fmaf(c, u, sN));
+    sE = fmaf(c, v, fmaf(s, u, sE));
+    sr += r;
+    const float r2 = r * r;
+    const float cd = fmaf(k.rot_c2, r2, 1.0f);
+    const float sd = r * k.rot_s1;
+    const float cn = fmaf(-s, sd, c * cd);
+    s = fmaf(c, sd, s * cd);
+    c = cn;
+  }
+  N = fmaf(k.h, sN, N);
+  E = fmaf(k.h, sE, E);
+  psi = fmaf(k.h, sr, psi);
+}
+
+// integrate_hull with a first-order lag of the thruster wrench (ml4ca_env_cfg.actuator_lag_s > 0; oracle/vessel.py):
+// tau_act is a state of the env; every sub-step first moves it towards the command by lag_k, then advances the hull with it.
+// Nine more FP32 instructions per sub-step than integrate_hull.
+__device__ __forceinline__ void integrate_hull_lag(float& N, float& E, float& psi, float& u, float& v, float& r,
+                                                   float tx, float ty, float tn, float& ta_x, float& ta_y, float& ta_n,
+                                                   int n_sub, const HullConsts& k) {
+  float s, c;
+  sincos_heading(psi, s, c);
+  float sN = 0.f, sE = 0.f, sr = 0.f;
+#pragma unroll 5
+  for (int i = 0; i < n_sub; ++i) {
+    ta_x = fmaf(k.lag_k, tx - ta_x, ta_x);
+    ta_y = fmaf(k.lag_k, ty - ta_y, ta_y);
+    ta_n = fmaf(k.lag_k, tn - ta_n, ta_n);
+    const float vr = v * r, ur = u * r, uv = u * v;
+    const float un = fmaf(fmaf(-k.xuu, fabsf(u), k.one_xu), u, fmaf(k.k_vr, vr, k.hm1 * ta_x));
+    const float vn = fmaf(fmaf(-k.yvv, fabsf(v), k.one_yv), v, fmaf(-k.k_ur, ur, k.hm2 * ta_y));
+    const float rn = fmaf(fmaf(-k.nrr, fabsf(r), k.one_nr), r, fmaf(-k.k_uv, uv, k.hm3 * ta_n));
     u = un;
     v = vn;
     r = rn;

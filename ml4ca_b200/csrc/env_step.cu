@@ -62,6 +62,8 @@ static int validate_cfg(const ml4ca_env_cfg* c) {
                 "RevoltSimple has no azimuth bound for the extended-state penalty (customEnv.py:319,339)");
   ML4CA_REQUIRE(c->n_substeps >= 0 && c->max_ep_len > 0 && c->max_ep_len <= 65535,
                 "n_substeps >= 0 and 0 < max_ep_len <= 65535 required");
+  ML4CA_REQUIRE(c->hull_model == 0 || c->hull_model == 1, "hull_model must be 0 (default constants) or 1 (box-test fit)");
+  ML4CA_REQUIRE(c->actuator_lag_s >= 0.f && c->actuator_lag_s <= 60.f, "actuator_lag_s must lie in [0, 60] s");
   return ML4CA_OK;
 }
 
@@ -88,6 +90,7 @@ static int launch_step(const ml4ca_env* e, int64_t first, int64_t count, int64_t
                        float* obs, float* rew, uint8_t* done, cudaStream_t st) {
   EnvParams p = e->p;
   p.eta += first, p.nu += first, p.ref += first, p.prev_thrust += first, p.angles += first, p.obs_tail += first;
+  p.tau_act += first;
   p.ep_len += first;
   if (p.cut_obs != nullptr) p.cut_obs += first;
   p.env_off += first;
@@ -185,10 +188,10 @@ int ml4ca_env_create(const ml4ca_env_cfg* cfg, int64_t n_env, int32_t device, ml
   e->n = n_env;
   e->device = device;
   e->tail_valid = true;
-  // one slab: 18 fp32 rows + 1 int32 row (the episode words), each row padded to a 16-byte multiple so that every row start is
+  // one slab: 21 fp32 rows + 1 int32 row (the episode words), each row padded to a 16-byte multiple so that every row start is
   // float4-aligned whenever n % 4 == 0 (rows are indexed with stride n, so the padding only sits at the end).
   const size_t row = (size_t)n_env * sizeof(float);
-  const size_t bytes = 19 * row + 256;
+  const size_t bytes = 22 * row + 256;
   cudaError_t ce = cudaMalloc(&e->slab, bytes);
   if (ce != cudaSuccess) {
     delete e;
@@ -208,14 +211,15 @@ int ml4ca_env_create(const ml4ca_env_cfg* cfg, int64_t n_env, int32_t device, ml
   p.prev_thrust = f + 9 * n_env;
   p.angles = f + 12 * n_env;
   p.obs_tail = f + 15 * n_env;
-  p.ep_len = reinterpret_cast<int32_t*>(f + 18 * n_env);
+  p.tau_act = f + 18 * n_env;
+  p.ep_len = reinterpret_cast<int32_t*>(f + 21 * n_env);
   p.cut_obs = nullptr;
   p.n = n_env;
   for (int i = 0; i < 6; ++i) p.bounds[i] = cfg->ss_bounds[i];
   make_reset_scale(*cfg, cfg->reset_fraction, p.reset_scale);
   p.inv_step_dt = 1.0f / cfg->step_dt;
   p.pad1 = 0.f;
-  p.hull = hull_consts(cfg->sim_dt);
+  p.hull = hull_consts(cfg->sim_dt, cfg->hull_model, cfg->actuator_lag_s);
   p.n_sub = cfg->n_substeps;
   p.max_ep_len = cfg->max_ep_len;
   p.auto_reset = cfg->auto_reset;

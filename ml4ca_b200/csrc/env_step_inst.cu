@@ -42,6 +42,11 @@ template <int KIND, bool CONT, bool EXT>
 static int launch_step_vec(const ml4ca_env* e, const EnvParams& p, const float* action, float* obs, float* rew,
                            uint8_t* done, cudaStream_t st) {
   const int64_t n = p.count;
+  if (e->cfg.actuator_lag_s > 0.f) {   // lagged wrench: the scalar kernel with three more state rows
+    const int64_t blocks = (n + 255) / 256;
+    env_step_kernel<KIND, CONT, EXT, 1, true><<<(unsigned)blocks, 256, 0, st>>>(p, action, obs, rew, done);
+    return check_launch("env_step_kernel<lag>");
+  }
   const bool vec4 = (p.n % 4 == 0) && (n % 4 == 0) && (p.io_stride % 4 == 0) && aligned16(p.eta) && aligned16(action) &&
                     aligned16(obs) && aligned16(rew) && ((reinterpret_cast<uintptr_t>(done) & 3u) == 0);
   static const int threads = [] {   // tuning knob: ML4CA_ENV_THREADS=64|128|256

@@ -51,6 +51,19 @@
 #define ML4CA_NR (60.0)
 #define ML4CA_NRR (90.3)    //                   60*0.52 + 90.3*0.2704 = 55.6 Nm
 #define ML4CA_SIM_DT (0.01) // s, one simulator sub-step (customEnv.py:79-81)
+// Second DECLARED parameter set (ml4ca_env_cfg.hull_model = 1): output-error fit of the same equations to the reference's
+// recorded Cybersea box tests (tools/sysid_hull.py --constrained --wrench-lag; results/all_plots/box_test/), with the
+// quadratic coefficients tied to the same top speeds as above, plus a first-order lag of the thruster wrench.
+#define ML4CA_H1_M11 (271.0)
+#define ML4CA_H1_M22 (316.0)
+#define ML4CA_H1_M33 (320.0)
+#define ML4CA_H1_XU (12.3)
+#define ML4CA_H1_XUU (12.13)  //                   12.3*1.4 + 12.13*1.96 = 41.0 N
+#define ML4CA_H1_YV (0.0)
+#define ML4CA_H1_YVV (555.6)  //                   555.6*0.09 = 50.0 N
+#define ML4CA_H1_NR (106.0)
+#define ML4CA_H1_NRR (1.78)   //                   106*0.52 + 1.78*0.2704 = 55.6 Nm
+#define ML4CA_H1_LAG_S (0.92) // s, fitted time constant of the wrench lag (ml4ca_env_cfg.actuator_lag_s)
 
 // ---- env (RevoltFinal, extended state, continuous angles) ---------------------------------------------------
 #define ML4CA_N_SUBSTEPS 20

@@ -743,6 +743,7 @@ int ml4ca_rollout_step(ml4ca_env* env, ml4ca_policy* p, uint64_t seed, uint32_t 
   ML4CA_REQUIRE(env->cfg.kind == ML4CA_ENV_FINAL && env->cfg.cont_ang && env->cfg.extended_state,
                 "the fused rollout is built for RevoltFinal(extended_state=True, cont_ang=True)");
   ML4CA_REQUIRE(p->d.obs == 9 && p->d.act == 7, "the fused rollout needs a 9 -> 7 policy");
+  ML4CA_REQUIRE(env->cfg.actuator_lag_s == 0.f, "the fused rollout has no actuator lag: use ml4ca_policy_forward + ml4ca_env_step");
   ML4CA_REQUIRE(env->device == p->device, "env and policy live on different devices");
   ML4CA_REQUIRE(env->tail_valid, "the fused rollout keeps the tail of the last returned observation in the env state; "
                                  "after ml4ca_env_step calls, reset the env before using ml4ca_rollout_step");

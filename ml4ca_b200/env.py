@@ -29,11 +29,21 @@ class StandInHull(object):
 
     frozen=True is a null simulator (the hull state only changes through reset), which isolates the
     wrapper arithmetic exactly like stepping the reference with a no-op twin.
+
+    hull_model picks the DECLARED parameter set of the stand-in equations (ml4ca_constants.h): 0 = the default constants,
+    1 = the constants fitted to the reference's recorded Cybersea box tests (tools/sysid_hull.py), which come with a
+    first-order lag of the thruster wrench (actuator_lag_s, default 0.92 s for model 1 and none for model 0).
     """
 
-    def __init__(self, frozen=False, n_substeps=None):
+    FITTED_LAG_S = 0.92         # ML4CA_H1_LAG_S
+
+    def __init__(self, frozen=False, n_substeps=None, hull_model=0, actuator_lag_s=None):
         self.frozen = bool(frozen)
         self.n_substeps = n_substeps
+        self.hull_model = int(hull_model)
+        if actuator_lag_s is None:
+            actuator_lag_s = self.FITTED_LAG_S if self.hull_model == 1 else 0.0
+        self.actuator_lag_s = float(actuator_lag_s)
 
 
 class Box(object):
@@ -167,6 +177,8 @@ class Revolt(object):
                                                     ctypes.byref(cfg)), "ml4ca_env_cfg_default")
         n_sub = self.n_steps if digitwin.n_substeps is None else int(digitwin.n_substeps)
         cfg.n_substeps = 0 if digitwin.frozen else n_sub
+        cfg.hull_model = int(getattr(digitwin, "hull_model", 0))
+        cfg.actuator_lag_s = float(getattr(digitwin, "actuator_lag_s", 0.0))
         cfg.max_ep_len = self.max_ep_len
         cfg.auto_reset = int(bool(auto_reset))
         cfg.reset_acts = int(bool(reset_acts))            # customEnv.py:179-188

@@ -29,6 +29,12 @@ XU, XUU = 10.0, 13.8
 YV, YVV = 100.0, 222.0
 NR, NRR = 60.0, 90.3
 SIM_DT = 0.01
+# hull_model -> (m11, m22, m33, Xu, Xuu, Yv, Yvv, Nr, Nrr); model 1 = tools/sysid_hull.py --constrained --wrench-lag
+HULL_MODELS = {
+    0: dict(m11=M11, m22=M22, m33=M33, Xu=XU, Xuu=XUU, Yv=YV, Yvv=YVV, Nr=NR, Nrr=NRR),
+    1: dict(m11=271.0, m22=316.0, m33=320.0, Xu=12.3, Xuu=12.13, Yv=0.0, Yvv=555.6, Nr=106.0, Nrr=1.78),
+}
+H1_LAG_S = 0.92
 
 # env (customEnv.py:26,79-83,386-399)
 N_SUBSTEPS = 20

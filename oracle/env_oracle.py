@@ -22,9 +22,11 @@ class EnvSpec(object):
     """Static description of one reference env class (customEnv.py:22-90,327-399)."""
 
     def __init__(self, kind='final', cont_ang=True, extended_state=True, n_substeps=C.N_SUBSTEPS,
-                 max_ep_len=800, testing=False, realtime=False):
+                 max_ep_len=800, testing=False, realtime=False, hull_model=0, actuator_lag_s=0.0):
         assert kind in KINDS
         self.kind = kind
+        self.hull = C.HULL_MODELS[int(hull_model)]          # DECLARED stand-in parameter set (vessel.py)
+        self.actuator_lag_s = float(actuator_lag_s)
         self.cont_ang = bool(cont_ang) and kind == 'final'
         self.extended_state = bool(extended_state)
         # customEnv.py:79-83
@@ -190,6 +192,7 @@ def new_state(spec, n, dt=np.float64):
         'ref': np.zeros((3, n), dtype=dt), 'prev_thrust': np.zeros((3, n), dtype=dt),
         'angles': np.repeat(da, n, axis=1).astype(dt),
         'ep_len': np.zeros(n, dtype=np.int32), 'episode': np.zeros(n, dtype=np.int32),
+        'tau_act': np.zeros((3, n), dtype=np.float64),      # lagged thruster wrench (vessel.py), used when actuator_lag_s > 0
     }
 
 
@@ -245,6 +248,7 @@ def reset(spec, state, mask=None, seed=0, env_id_offset=0, fraction=0.8, eta=Non
     else:
         state['prev_thrust'][:, m] = 0
     state['angles'][:, m] = np.asarray(spec.default_angles, dtype=dt)[:, None]
+    state['tau_act'][:, m] = 0
     state['ep_len'][m] = 0
     state['episode'][m] += 1
     return observe(spec, state['eta'], state['nu'], state['ref'], state['prev_thrust'], dt)
@@ -265,7 +269,11 @@ def step(spec, state, action, dt=np.float64, integrate=True):
             state['angles'][idx - 3] = act[spec.amap[idx]]
     if integrate and spec.n_substeps > 0:                              # :124
         tau = vessel.thruster_wrench(thrust, state['angles'])
-        eta, nu = vessel.integrate(state['eta'], state['nu'], tau, spec.n_substeps)
+        if spec.actuator_lag_s > 0:
+            eta, nu, state['tau_act'] = vessel.integrate(state['eta'], state['nu'], tau, spec.n_substeps, params=spec.hull,
+                                                         tau_act=state['tau_act'], lag_s=spec.actuator_lag_s)
+        else:
+            eta, nu = vessel.integrate(state['eta'], state['nu'], tau, spec.n_substeps, params=spec.hull)
         state['eta'], state['nu'] = eta.astype(dt), nu.astype(dt)
     obs = observe(spec, state['eta'], state['nu'], state['ref'], state['prev_thrust'], dt)   # :125
     old_scaled = obs[6:9] if spec.extended_state else None

@@ -19,7 +19,13 @@ integrated with the semi-implicit Euler scheme (h = 10 ms, customEnv.py:79-81)
 
     nu+ = nu + h nu_dot(nu) ;  N+,E+ = N,E + h R(psi) nu+ ;  psi+ = psi + h r+
 
-Commanded thrust/azimuth act instantly and stay constant over the sub-steps of one env step.
+Commanded thrust/azimuth act instantly and stay constant over the sub-steps of one env step -- unless an
+actuator lag T > 0 is declared (ml4ca_env_cfg.actuator_lag_s): the wrench then follows its command through
+
+    tau_act+ = tau_act + h / (T + h) (tau_cmd - tau_act)          (implicit Euler of  T d tau_act/dt = tau_cmd - tau_act)
+
+advanced at the start of every sub-step, and tau_act is a state of the env (zero after a reset).
+``params`` selects the DECLARED parameter set (constants.HULL_MODELS; 0 = default).
 """
 import numpy as np
 
@@ -47,15 +53,24 @@ def thruster_wrench(n_pct, alpha):
     return np.stack([tx, ty, tn])
 
 
-def integrate(eta, nu, tau, n_sub, h=C.SIM_DT):
-    """n_sub semi-implicit Euler sub-steps.  eta, nu, tau: float64 [3, ...].  Returns (eta, nu)."""
+def integrate(eta, nu, tau, n_sub, h=C.SIM_DT, params=None, tau_act=None, lag_s=0.0):
+    """n_sub semi-implicit Euler sub-steps.  eta, nu, tau: float64 [3, ...].  Returns (eta, nu), or (eta, nu, tau_act)
+    when a lagged wrench state ``tau_act`` [3, ...] is passed."""
+    p = C.HULL_MODELS[0] if params is None else params
+    m11, m22, m33 = p['m11'], p['m22'], p['m33']
     N, E, psi = (np.array(x, dtype=np.float64) for x in eta)
     u, v, r = (np.array(x, dtype=np.float64) for x in nu)
-    tx, ty, tn = (np.asarray(x, dtype=np.float64) for x in tau)
+    cmd = np.stack([np.asarray(x, dtype=np.float64) for x in tau])
+    lagged = tau_act is not None
+    act = np.array(tau_act, dtype=np.float64) if lagged else cmd
+    k = h / (lag_s + h) if lag_s > 0 else 1.0
     for _ in range(int(n_sub)):
-        du = (tx + C.M22 * v * r - (C.XU + C.XUU * np.abs(u)) * u) / C.M11
-        dv = (ty - C.M11 * u * r - (C.YV + C.YVV * np.abs(v)) * v) / C.M22
-        dr = (tn - (C.M22 - C.M11) * u * v - (C.NR + C.NRR * np.abs(r)) * r) / C.M33
+        if lagged:
+            act = act + k * (cmd - act)
+        tx, ty, tn = act
+        du = (tx + m22 * v * r - (p['Xu'] + p['Xuu'] * np.abs(u)) * u) / m11
+        dv = (ty - m11 * u * r - (p['Yv'] + p['Yvv'] * np.abs(v)) * v) / m22
+        dr = (tn - (m22 - m11) * u * v - (p['Nr'] + p['Nrr'] * np.abs(r)) * r) / m33
         u = u + h * du
         v = v + h * dv
         r = r + h * dr
@@ -63,6 +78,8 @@ def integrate(eta, nu, tau, n_sub, h=C.SIM_DT):
         N = N + h * (c * u - s * v)
         E = E + h * (s * u + c * v)
         psi = psi + h * r
+    if lagged:
+        return np.stack([N, E, psi]), np.stack([u, v, r]), act
     return np.stack([N, E, psi]), np.stack([u, v, r])
 
 

@@ -346,8 +346,36 @@ def gen_reset_acts(B=64, T=3, seed=31):
             'obs': np.transpose(np.array(rec['obs']), (1, 2, 0)), 'rew': np.array(rec['rew']).T}
 
 
+def gen_hull_replay(window_s=10.0, pre_s=5.0, every=2):
+    """Recorded Cybersea box tests of the reference (results/all_plots/box_test/bagfile__*.csv: observer pose at 20 Hz and
+    the thruster commands of four controllers), cut into open-loop replay windows: the recorded pose of the window, the
+    body velocity at its start (Savitzky-Golay rates of the pose, tools/sysid_hull.py) and the COMMANDED thruster wrench
+    (reference thruster model on the recorded commands) from pre_s before the window, so that an actuator lag can settle."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    argv, sys.argv = sys.argv, [sys.argv[0]]
+    import sysid_hull as S
+    sys.argv = argv
+    eta_w, nu0, tau_w, src = [], [], [], []
+    for k, m in enumerate(('RL', 'QP', 'pseudo', 'RLintegral')):
+        t, eta, n, a = S.load(m)
+        h = t[1] - t[0]
+        W, P = int(round(window_s / h)), int(round(pre_s / h))
+        nu, _ = S.body_rates(t, eta)
+        tau = S.wrench(n, a)
+        for s in list(range(100, len(t) - W - 100, W))[::every]:
+            eta_w.append(eta[:, s:s + W]); nu0.append(nu[:, s]); tau_w.append(tau[:, s - P:s + W]); src.append(k)
+    return {'eta': np.array(eta_w, dtype=np.float32), 'nu0': np.array(nu0, dtype=np.float32),
+            'tau_cmd': np.array(tau_w, dtype=np.float32), 'run': np.array(src, dtype=np.int8),
+            'h': np.float64(0.05), 'pre': np.int32(int(round(pre_s / 0.05)))}
+
+
 def main():
     assert ref_loader.available(), "reference checkout not found"
+    if "--only-hull-replay" in sys.argv:
+        out = gen_hull_replay()
+        np.savez_compressed(os.path.join(HERE, 'hull_replay.npz'), **out)
+        print('wrote hull_replay.npz  windows %d' % out['eta'].shape[0])
+        return
     if "--only-reset-acts" in sys.argv:
         np.savez_compressed(os.path.join(HERE, 'resetacts_final.npz'), **gen_reset_acts())
         print('wrote resetacts_final.npz')

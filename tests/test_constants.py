@@ -36,6 +36,10 @@ def test_header_matches_oracle():
     assert (h["ML4CA_M11"], h["ML4CA_M22"], h["ML4CA_M33"]) == (C.M11, C.M22, C.M33)
     assert (h["ML4CA_XU"], h["ML4CA_XUU"], h["ML4CA_YV"], h["ML4CA_YVV"], h["ML4CA_NR"], h["ML4CA_NRR"]) == \
         (C.XU, C.XUU, C.YV, C.YVV, C.NR, C.NRR)
+    h1 = C.HULL_MODELS[1]
+    assert [h["ML4CA_H1_" + k.upper()] for k in ("m11", "m22", "m33", "Xu", "Xuu", "Yv", "Yvv", "Nr", "Nrr")] == \
+        [h1[k] for k in ("m11", "m22", "m33", "Xu", "Xuu", "Yv", "Yvv", "Nr", "Nrr")]
+    assert h["ML4CA_H1_LAG_S"] == C.H1_LAG_S
     assert h["ML4CA_SIM_DT"] == C.SIM_DT and h["ML4CA_N_SUBSTEPS"] == C.N_SUBSTEPS
     assert h["ML4CA_MAX_EP_LEN"] == C.MAX_EP_LEN
     assert (h["ML4CA_BOUND_POS"], h["ML4CA_BOUND_POS"], h["ML4CA_BOUND_YAW"], h["ML4CA_BOUND_U"], h["ML4CA_BOUND_V"],
@@ -56,8 +60,9 @@ def test_header_matches_oracle():
 def test_hull_calibration_matches_reference_top_speeds():
     """customEnv.py:13-18 ('with thrust losses', full): +1.4 m/s, 0.30 m/s, 0.52 rad/s at full thrust."""
     fx = 2 * C.F_MAX[0]
-    assert abs(C.XU * 1.4 + C.XUU * 1.4 ** 2 - fx) < 0.1
     fy = 2 * C.F_MAX[0] + C.F_MAX[2]
-    assert abs(C.YV * 0.30 + C.YVV * 0.30 ** 2 - fy) < 0.1
     mz = 2 * C.F_MAX[0] * abs(C.LX[0]) + C.F_MAX[2] * C.LX[2]
-    assert abs(C.NR * 0.52 + C.NRR * 0.52 ** 2 - mz) < 0.2
+    for model, p in C.HULL_MODELS.items():          # both declared parameter sets keep the stated top speeds
+        assert abs(p["Xu"] * 1.4 + p["Xuu"] * 1.4 ** 2 - fx) < 0.1, model
+        assert abs(p["Yv"] * 0.30 + p["Yvv"] * 0.30 ** 2 - fy) < 0.1, model
+        assert abs(p["Nr"] * 0.52 + p["Nrr"] * 0.52 ** 2 - mz) < 0.2, model

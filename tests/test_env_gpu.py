@@ -23,9 +23,9 @@ ENV_FILES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "
 CLS = {'full': 'Revolt', 'simple': 'RevoltSimple', 'limited': 'RevoltLimited', 'final': 'RevoltFinal'}
 
 
-def make_env(kind, cont_ang, ext, n, frozen=False, **kw):
+def make_env(kind, cont_ang, ext, n, frozen=False, hull_kw=None, **kw):
     import ml4ca_b200.env as E
-    hull = E.StandInHull(frozen=frozen)
+    hull = E.StandInHull(frozen=frozen, **(hull_kw or {}))
     if kind == 'full':
         return E.Revolt(digitwin=hull, extended_state=ext, num_envs=n, **kw)
     if kind == 'final':
@@ -125,6 +125,72 @@ def test_single_step_hull_vs_float64(cuda_device, n):
         np.testing.assert_allclose(r.cpu().numpy().reshape(n), r64, rtol=0, atol=1e-4)
         # keep both sides on the same trajectory: continue the oracle from the kernel's state
         st['eta'], st['nu'] = sg['eta'].cpu().numpy().astype(np.float64), sg['nu'].cpu().numpy().astype(np.float64)
+
+
+@pytest.mark.parametrize("hull_model,lag", [(1, None), (1, 0.0), (0, 0.5)])
+@pytest.mark.parametrize("n", [257, 4096])
+def test_second_hull_model_and_actuator_lag_vs_float64(cuda_device, n, hull_model, lag):
+    """ml4ca_env_cfg.hull_model / actuator_lag_s: the box-test parameter set and the first-order wrench lag against the float64
+    integration of the same stated equations (oracle/vessel.py).  The lagged wrench is a state: it carries over env steps and an
+    in-kernel restart zeroes it (steps 4.. follow a cut of every env at step 3)."""
+    rng = np.random.default_rng(n + hull_model)
+    lag_s = (0.92 if hull_model == 1 else 0.0) if lag is None else lag
+    spec = EO.EnvSpec('final', True, True, max_ep_len=6, hull_model=hull_model, actuator_lag_s=lag_s)
+    assert spec.max_ep_len == 3
+    env = make_env('final', True, True, n, hull_kw=dict(hull_model=hull_model, actuator_lag_s=lag), max_ep_len=6, auto_reset=True,
+                   seed=5)
+    assert abs(env._cfg.actuator_lag_s - lag_s) < 1e-7 and env._cfg.hull_model == hull_model
+    eta0 = rng.uniform(-1, 1, (3, n)) * np.array([[5.0], [5.0], [0.5]])
+    nu0 = rng.uniform(-1, 1, (3, n)) * np.array([[0.8], [0.15], [0.3]])
+    eta0, nu0 = eta0.astype(np.float32).astype(np.float64), nu0.astype(np.float32).astype(np.float64)
+    st = EO.new_state(spec, n)
+    EO.reset(spec, st, eta=eta0, nu=nu0)
+    z = 0 * eta0[0]
+    env.reset(**{'Hull.PosNED': eta0[:2], 'Hull.PosAttitude': np.stack([z, z, eta0[2]]),
+                 'Hull.VelocityNu': np.stack([nu0[0], nu0[1], z, z, z, nu0[2]])})
+    a = rng.uniform(-1.0, 1.0, (7, n)).astype(np.float32)          # held command: the lag shows as a ramp of the wrench
+    for t in range(5):
+        if t == 2:
+            a = rng.uniform(-1.0, 1.0, (7, n)).astype(np.float32)
+        o64, r64, d64, info = EO.step(spec, st, a.astype(np.float64))
+        o, r, d, inf = env.step(torch.as_tensor(a, device=cuda_device))
+        sg = env.get_state()
+        eta, nu = sg['eta'].cpu().numpy().astype(np.float64), sg['nu'].cpu().numpy().astype(np.float64)
+        flags = inf['flags'].cpu().numpy()
+        restarted = flags != 0                                       # left its bounds, or (t == 2) hit the episode-length cut
+        if t == 2:
+            assert info['truncated'].all() and (flags & 2).all()
+        else:
+            assert restarted.mean() < 0.1
+        keep = ~restarted
+        np.testing.assert_allclose(r.cpu().numpy().reshape(n)[~d64], r64[~d64], rtol=0, atol=1e-4)
+        np.testing.assert_allclose(eta[:, keep], st['eta'][:, keep], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(nu[:, keep], st['nu'][:, keep], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(o.cpu().numpy().reshape(9, n)[:, keep], o64[:, keep], rtol=0, atol=2e-5)
+        st['eta'], st['nu'] = st['eta'].copy(), st['nu'].copy()
+        st['eta'][:, keep], st['nu'][:, keep] = eta[:, keep], nu[:, keep]
+        if restarted.any():                                          # the kernel's restart state; tau_act back to zero
+            EO.reset(spec, st, mask=restarted, eta=eta, nu=nu)
+    if lag_s > 0:
+        # the lag is not a no-op: the same commands without it end somewhere else
+        spec0 = EO.EnvSpec('final', True, True, max_ep_len=6, hull_model=hull_model, actuator_lag_s=0.0)
+        s0 = EO.new_state(spec0, n)
+        EO.reset(spec0, s0, eta=eta0, nu=nu0)
+        s1 = EO.new_state(spec, n)
+        EO.reset(spec, s1, eta=eta0, nu=nu0)
+        EO.step(spec0, s0, a.astype(np.float64)), EO.step(spec, s1, a.astype(np.float64))
+        assert np.abs(s0['nu'] - s1['nu']).max() > 1e-3
+
+
+def test_fused_rollout_refuses_the_actuator_lag(cuda_device):
+    import ml4ca_b200 as M
+    env = make_env('final', True, True, 64, hull_kw=dict(hull_model=1), auto_reset=True)
+    ac = M.ActorCritic(9, 7, (64, 64), "leaky_relu", device=cuda_device, seed=0)
+    buf = M.TrajectoryBuffer(9, 7, 2, 64, device=cuda_device, max_ep_len=env.max_ep_len)
+    env.reset()
+    with pytest.raises(RuntimeError, match="actuator lag"):
+        M.rollout(env, ac, buf, fused=True)
+    M.rollout(env, ac, buf, fused=False)
 
 
 def test_reset_sampling_is_bit_identical_to_oracle(cuda_device):

@@ -139,7 +139,7 @@ def test_graph_update_equals_eager_update(cuda_device, hidden, target_kl, want_s
     T, n = 4, 4096
     obs, act, adv, ret = _batch(T, n, seed=17)
     res = []
-    for use_graph in (False, True):
+    for use_graph in (False, True, False):
         ac = M.ActorCritic(9, 7, hidden, "leaky_relu", device=cuda_device, seed=4)
         buf = M.TrajectoryBuffer(9, 7, T, n, device=cuda_device)
         # target 1e-9: approx-KL is 0 before the first step (logp_old is the current policy's) and > 0 after it, so the loop stops
@@ -158,19 +158,22 @@ def test_graph_update_equals_eager_update(cuda_device, hidden, target_kl, want_s
             buf.logp_buf.copy_(torch.as_tensor(lp))
             infos.append(upd.update(buf, graph=use_graph))
         res.append((ac.parameters().clone(), upd.m1.clone(), upd.m2.clone(), infos, upd.t_pi, upd.t_v))
-    (pa, m1a, m2a, ia, tpa, tva), (pb, m1b, m2b, ib, tpb, tvb) = res
+    (pa, m1a, m2a, ia, tpa, tva), (pb, m1b, m2b, ib, tpb, tvb), (pc, _, _, ic, _, _) = res
     assert [i["StopIter"] for i in ia] == [i["StopIter"] for i in ib]
     # (the tensor-core forward differs from the float64 logp_old by ~1e-3, which already exceeds 1.5e-9 at iteration 0)
     assert all(i["StopIter"] <= want_stop for i in ia) if want_stop == 1 else all(i["StopIter"] == want_stop for i in ia)
     assert (tpa, tva) == (tpb, tvb)
     # Not bit-equal: the gradient kernels sum per-CTA partials with atomicAdd, so two runs of EITHER path differ in the last
-    # bits of the gradient, and Adam turns a gradient component at noise level into a step of +-lr whatever its size.  The
-    # two paths must agree on all but a few such coordinates and move the parameters by the same vector overall.
+    # bits of the gradient, and Adam turns a gradient component at noise level into a step of +-lr whatever its size
+    # (profiles/ppo_graph_noise_r2.txt: eager vs eager ends 2e-3..7e-3 of the travelled distance apart, graph vs eager the same).
+    # The graph must therefore land as close to the host-driven loop as a second host-driven run does.
     ac0 = M.ActorCritic(9, 7, hidden, "leaky_relu", device=cuda_device, seed=4)
     p0 = ac0.parameters().clone()
-    diff, moved = (pa - pb), (pa - p0)
-    assert float((diff.abs() < 2e-5).float().mean()) > 0.97, float((diff.abs() < 2e-5).float().mean())
-    assert float(diff.norm() / moved.norm()) < 0.05, float(diff.norm() / moved.norm())
+    moved = float((pa - p0).norm())
+    floor = float((pa - pc).norm()) / moved
+    dist = float((pa - pb).norm()) / moved
+    assert floor < 0.03 and dist < 0.03, (floor, dist)
+    assert dist <= 3.0 * floor + 2e-3, (floor, dist)
     for a, b in zip(ia, ib):
         for k in ("LossPi", "LossV", "KL", "Entropy", "ClipFrac", "DeltaLossPi", "DeltaLossV"):
             assert abs(a[k] - b[k]) <= 2e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])
