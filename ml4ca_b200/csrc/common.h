@@ -40,4 +40,17 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 constexpr int kNumSMs = 148;  // B200
 
+#ifdef __CUDACC__
+// Sample s of a time-major [T, ., n] trajectory buffer -> (time step t, env i).  The update kernels tile the flat sample
+// index, so a tile may straddle time steps: no padding when n is small (the reference's own batch is 4 envs x 400 steps).
+__device__ __forceinline__ void split_sample(int64_t s, int64_t n, int64_t& t, int64_t& i) {
+  if ((uint64_t)s < 0x80000000ull && (uint64_t)n < 0x80000000ull) {
+    const uint32_t q = (uint32_t)s / (uint32_t)n;
+    t = q, i = (int64_t)((uint32_t)s - q * (uint32_t)n);
+  } else {
+    t = s / n, i = s - t * n;
+  }
+}
+#endif
+
 }  // namespace ml4ca

@@ -172,19 +172,22 @@ __global__ void __launch_bounds__(256, 1) ppo_grad_kernel(const Args A) {
   double st[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 
   const int64_t n = A.n;
-  const int64_t tiles_per_t = (n + TS - 1) / TS;
-  const int64_t num_tiles = tiles_per_t * A.T;
+  const int64_t total = n * (int64_t)A.T;       // tiles run over the flat sample index (common.h: split_sample)
+  const int64_t num_tiles = (total + TS - 1) / TS;
   const int rows_in = obs + (NET == 0 ? A.act + 2 : 1);   // obs rows, then (pi) act rows, adv, logp_old | (v) ret
   constexpr int kLoads = (XR + OP + 2) * TS / 256;         // 11 >= rows_in * 128 / 256
   float pre[kLoads];
 
   auto fetch = [&](int64_t tile) {
-    const int64_t t = tile / tiles_per_t, i0 = (tile % tiles_per_t) * TS;
+    const int64_t smp = tile * TS + (tid & 127);   // the column of every load of this thread (256 % 128 == 0)
+    const bool live = smp < total;
+    int64_t t = 0, i = 0;
+    if (live) split_sample(smp, n, t, i);
 #pragma unroll
     for (int m = 0; m < kLoads; ++m) {
-      const int idx = tid + 256 * m, row = idx >> 7, col = idx & 127;
+      const int idx = tid + 256 * m, row = idx >> 7;
       float v = 0.f;
-      if (row < rows_in && i0 + col < n) {
+      if (row < rows_in && live) {
         const float* base;     // rows a mode does not use have a NULL base and read as zero
         int64_t off;
         if (row < obs) base = A.obs_buf, off = ((int64_t)t * obs + row) * n;
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(256, 1) ppo_grad_kernel(const Args A) {
         else if (row < obs + A.act) base = A.act_buf, off = ((int64_t)t * A.act + (row - obs)) * n;
         else if (row == obs + A.act) base = A.adv, off = (int64_t)t * n;
         else base = A.logp_old, off = (int64_t)t * n;
-        if (base != nullptr) v = __ldg(base + off + i0 + col);
+        if (base != nullptr) v = __ldg(base + off + i);
       }
       pre[m] = v;
     }
@@ -215,8 +218,7 @@ __global__ void __launch_bounds__(256, 1) ppo_grad_kernel(const Args A) {
   __syncthreads();
 
   for (; tile < num_tiles; tile += gridDim.x) {
-    const int64_t i0 = (tile % tiles_per_t) * TS;
-    const int valid = (int)((n - i0) < TS ? (n - i0) : TS);
+    const int valid = (int)((total - tile * TS) < TS ? (total - tile * TS) : TS);
     stash();
     __syncthreads();
     if (tile + gridDim.x < num_tiles) fetch(tile + gridDim.x);   // next tile's rows travel while this one computes
@@ -266,8 +268,9 @@ __global__ void __launch_bounds__(256, 1) ppo_grad_kernel(const Args A) {
     __syncthreads();
     if (A.mu_out != nullptr) {   // forward only (uniform branch): store the means, next tile
       if (tid < TS && tid < valid) {
-        const int64_t t = tile / tiles_per_t;
-        for (int a = 0; a < nout; ++a) A.mu_out[((int64_t)t * nout + a) * n + i0 + tid] = S.out[a][tid];
+        int64_t t, i;
+        split_sample(tile * TS + tid, n, t, i);
+        for (int a = 0; a < nout; ++a) A.mu_out[((int64_t)t * nout + a) * n + i] = S.out[a][tid];
       }
       __syncthreads();           // the next tile overwrites x0 / out
       continue;
@@ -651,7 +654,7 @@ static ppogen::Args generic_args(ml4ca_policy* p, const ml4ca_policy_cfg& cfg, i
 }
 
 static int ppo_launch_fp32(const ppo::Args& a, int activation, int net, cudaStream_t st) {
-  const int64_t tiles = ((a.n + ppo::TS - 1) / ppo::TS) * a.T;
+  const int64_t tiles = (a.n * (int64_t)a.T + ppo::TS - 1) / ppo::TS;
   if (tiles == 0) return ML4CA_OK;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   const size_t smem = sizeof(ppo::Smem);
@@ -724,7 +727,7 @@ int ml4ca_ppo_grad_ex(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const 
   a.clip = clip_ratio;
   a.grad = grad, a.stats = stats;
   a.ctl = reinterpret_cast<const int32_t*>(ctl), a.iter = iter;
-  const int64_t tiles = ((n + ppo::TS - 1) / ppo::TS) * T;
+  const int64_t tiles = (n * (int64_t)T + ppo::TS - 1) / ppo::TS;
   if (tiles == 0) return ML4CA_OK;
   // Default: the tcgen05 kernel (fp16 operands, fp32 TMEM accumulation).  ML4CA_PPO_FP32=1 selects the fp32
   // CUDA-core kernel (gradients to 1e-5 instead of 1e-3).

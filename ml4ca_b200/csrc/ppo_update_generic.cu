@@ -87,12 +87,13 @@ __global__ void __launch_bounds__(NW * 32, 1) ppo_grad_generic_kernel(const Args
   __syncthreads();
 
   const int64_t n = A.n;
-  const int64_t tiles_per_t = (n + TS - 1) / TS;
-  const int64_t num_tiles = tiles_per_t * A.T;
+  const int64_t total = n * (int64_t)A.T;       // tiles run over the flat sample index (common.h: split_sample)
+  const int64_t num_tiles = (total + TS - 1) / TS;
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int64_t t = tile / tiles_per_t, i0 = (tile % tiles_per_t) * TS;
-    const int valid = (int)((n - i0) < TS ? (n - i0) : TS);
-    const bool live = lane < valid;
+    const int64_t smp = tile * TS + lane;
+    const bool live = smp < total;
+    int64_t t = 0, i = 0;                       // lane = sample
+    if (live) split_sample(smp, n, t, i);
     // ---- rows of this tile -> shared memory (warp w loads rows w, w + 8, ...) ---------------------------------------------
     const int rows_in = obs + (NET == 0 ? A.act + 2 : 1);
     for (int row = warp; row < rows_in; row += NW) {
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ppo_grad_generic_kernel(const Args
       else if (row < obs + A.act) base = A.act_buf, off = ((int64_t)t * A.act + (row - obs)) * n, dst = actb + (size_t)(row - obs) * RS;
       else if (row == obs + A.act) base = A.adv, off = (int64_t)t * n, dst = aux;
       else base = A.logp_old, off = (int64_t)t * n, dst = aux + RS;
-      dst[lane] = (base != nullptr && live) ? __ldg(base + off + i0 + lane) : 0.f;
+      dst[lane] = (base != nullptr && live) ? __ldg(base + off + i) : 0.f;
     }
     __syncthreads();
     // ---- forward -----------------------------------------------------------------------------------------------------------
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ppo_grad_generic_kernel(const Args
     __syncthreads();
     if (A.mu_out != nullptr) {           // forward only (uniform branch): store the means, next tile
       for (int a = warp; a < nout; a += NW)
-        if (live) A.mu_out[((int64_t)t * nout + a) * n + i0 + lane] = out[(size_t)a * RS + lane];
+        if (live) A.mu_out[((int64_t)t * nout + a) * n + i] = out[(size_t)a * RS + lane];
       __syncthreads();
       continue;
     }
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ppo_grad_generic_kernel(const Args
 using namespace ml4ca;
 
 int ml4ca_ppo_grad_generic_launch(const ppogen::Args& a, int activation, int net, cudaStream_t st) {
-  const int64_t tiles = ((a.n + ppogen::TS - 1) / ppogen::TS) * a.T;
+  const int64_t tiles = (a.n * (int64_t)a.T + ppogen::TS - 1) / ppogen::TS;
   if (tiles == 0) return ML4CA_OK;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   const size_t smem = sizeof(float) * ppogen::smem_floats(a.obs, a.hidden, a.n_hidden, a.net_params);

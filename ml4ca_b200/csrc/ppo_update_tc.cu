@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
   };
 
   const int64_t n = A.n;
-  const int64_t tiles_per_t = (n + TS - 1) / TS;
-  const int64_t num_tiles = tiles_per_t * A.T;
+  const int64_t total = n * (int64_t)A.T;       // tiles run over the flat sample index (common.h: split_sample)
+  const int64_t num_tiles = (total + TS - 1) / TS;
   float dls[8];
 #pragma unroll
   for (int a = 0; a < 8; ++a) dls[a] = 0.f;
@@ -227,8 +227,10 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
   constexpr int kPreObs = S97 ? 9 : 12;        // observation rows fetched one tile ahead (wider inputs load the rest in place)
   float pf_o[kPreObs], pf_a[8], pf_adv = 0.f, pf_lpo = 0.f, pf_ret = 0.f;
   auto fetch = [&](int64_t tl) {
-    const int64_t t = tl / tiles_per_t, i = (tl % tiles_per_t) * TS + row;
-    const bool live = tl < num_tiles && i < n;
+    const int64_t smp = tl * TS + row;
+    const bool live = smp < total;
+    int64_t t = 0, i = 0;
+    if (live) split_sample(smp, n, t, i);
 #pragma unroll
     for (int c = 0; c < kPreObs; ++c) pf_o[c] = (c < obs && live) ? __ldg(A.obs_buf + ((int64_t)t * obs + c) * n + i) : 0.f;
 #pragma unroll
@@ -246,8 +248,10 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
   };
   bool first_tile = true;
   for (int64_t tile = (int64_t)blockIdx.x * G + g; tile < num_tiles; tile += (int64_t)gridDim.x * G) {
-    const int64_t t = tile / tiles_per_t, i = (tile % tiles_per_t) * TS + row;
-    const bool live = i < n;
+    const int64_t smp = tile * TS + row;
+    const bool live = smp < total;
+    int64_t t = 0, i = 0;
+    if (live) split_sample(smp, n, t, i);
     // ---- inputs: thread = sample.  Requested one tile ahead (below, after the first hand-over), so their HBM latency is
     // off the serial chain of the group; only the first tile loads in place.
     if (first_tile) {
@@ -526,7 +530,7 @@ int ml4ca_ppo_grad_tc_launch(const ppotc::Args& args, int activation, int net, v
   int rc = check_launch("ppo pack_kernel");
   if (rc != ML4CA_OK) return rc;
   a.blob = b;
-  const int64_t tiles = ((a.n + ppotc::TS - 1) / ppotc::TS) * a.T;
+  const int64_t tiles = (a.n * (int64_t)a.T + ppotc::TS - 1) / ppotc::TS;
   const int64_t want = (tiles + ppotc::G - 1) / ppotc::G;
   const int grid = (int)(want < kNumSMs ? want : kNumSMs);
   const bool s97 = a.obs == 9 && a.act == 7;

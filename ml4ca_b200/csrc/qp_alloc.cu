@@ -27,6 +27,7 @@
 
 #include "common.h"
 #include "ml4ca_constants.h"
+#define ML4CA_QP_TABLEAU_STRIDE 64   // = kQpThreads: the pivoting tableau is strided by the CTA size (qp_slsqp.cuh)
 #include "qp_group.cuh"
 
 namespace ml4ca {
@@ -35,6 +36,7 @@ namespace ml4ca {
 #define ML4CA_QP_MINBLOCKS 4           // CTAs per SM the register allocation must allow
 #endif
 constexpr int kQpThreads = 64;         // per CTA
+static_assert(kQpThreads == ML4CA_QP_TABLEAU_STRIDE, "tableau stride");
 constexpr int kQpMaxPerThread = 64;    // demands per thread in a CTA's chunk (upper limit; the host sizes the chunk)
 constexpr int kQpTableau = 45;         // packed lower triangle of the 9 x 9 pivoting tableau
 

@@ -310,21 +310,44 @@ ML4CA_ROLLED
   for (int j = 0; j < n; ++j) row[j] = (real)S[sidx(k, j) * gs];
 }
 
-// sweep (dir = +1: index k enters) or reverse sweep (dir = -1: k leaves); row = row k of S before the sweep
-template <typename real, typename greal>
-ML4CA_HD_CALL void tableau_sweep(greal* __restrict__ S, int gs, int n, int k, real dir, const real* row) {
-  const real inv = (real)1 / row[k];
-  int e = 0;
-ML4CA_ROLLED
-  for (int i = 0; i < n; ++i) {
-    const real ri = row[i] * inv;
-ML4CA_ROLLED
-    for (int j = 0; j <= i; ++j, ++e) {
-      real v;
-      if (i == k) v = (j == k) ? -inv : dir * row[j] * inv;
-      else if (j == k) v = dir * ri;
-      else v = (real)S[e * gs] - ri * row[j];
-      S[e * gs] = (greal)v;
+// sweep (dir = +1: index k enters) or reverse sweep (dir = -1: k leaves) of the leading n x n block, n <= NMAX.
+// This routine is where the solver spends its instructions (58 % of the kernel's in the rolled, branching form it had first:
+// profiles/qp_r2.md), so it is the one place written for the instruction count: row k is read into registers, every other
+// element gets the generic update S_ij -= S_ik S_kj / S_kk from a fully unrolled, branch-free loop nest (constant offsets into
+// the packed storage: load, DFMA, store per element), and row / column k, whose generic update is meaningless, are written
+// afterwards.  Same arithmetic, element for element, as the textbook form.
+template <typename real, typename greal, int NMAX>
+ML4CA_HD_CALL void tableau_sweep(greal* __restrict__ S, int gs_arg, int n, int k, real dir) {
+#if defined(ML4CA_QP_TABLEAU_STRIDE)
+  constexpr int gs = ML4CA_QP_TABLEAU_STRIDE;   // the device build knows its CTA size: element offsets become immediates
+  (void)gs_arg;
+#else
+  const int gs = gs_arg;
+#endif
+  real row[NMAX];
+  const int kk = k * (k + 1) / 2;
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    const int e = (j <= k) ? kk + j : j * (j + 1) / 2 + k;
+    row[j] = (j < n) ? (real)S[e * gs] : (real)0;
+  }
+  const real inv = (real)1 / (real)S[(kk + k) * gs];
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    if (i < n) {
+      const real ri = row[i] * inv;
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        const int e = i * (i + 1) / 2 + j;
+        S[e * gs] = (greal)((real)S[e * gs] - ri * row[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    if (j < n) {
+      const int e = (j <= k) ? kk + j : j * (j + 1) / 2 + k;
+      S[e * gs] = (greal)((j == k) ? -inv : dir * row[j] * inv);
     }
   }
 }
@@ -341,8 +364,7 @@ ML4CA_ROLLED
     for (int e = 0; e < ne; ++e) S[e * gs] = (greal)Q.H[e];
 ML4CA_ROLLED
     for (int k = 0; k < nv; ++k) {
-      tableau_row<real, greal>(S, gs, nv, k, row);
-      tableau_sweep<real, greal>(S, gs, nv, k, (real)1, row);
+      tableau_sweep<real, greal, 6>(S, gs, nv, k, (real)1);
     }
 ML4CA_ROLLED
     for (int e = 0; e < ne; ++e) S[e * gs] = -S[e * gs];
@@ -450,14 +472,13 @@ ML4CA_ROLLED
     }
     Q.lam[bs] += st;
     if (t2 <= t1) {
-      tableau_sweep<real, greal>(S, gs, nc, bs, (real)1, row);
+      tableau_sweep<real, greal, 9>(S, gs, nc, bs, (real)1);
       p[bs] = (sig > (real)0) ? Q.hi[bs] : Q.lo[bs];   // exactly on its bound
       in_act |= 1u << bs;
       n_act += 1;
       bs = -1;
     } else {
-      tableau_row<real, greal>(S, gs, nc, drop, row);
-      tableau_sweep<real, greal>(S, gs, nc, drop, (real)-1, row);
+      tableau_sweep<real, greal, 9>(S, gs, nc, drop, (real)-1);
       in_act &= ~(1u << drop);
       n_act -= 1;
       Q.lam[drop] = (real)0;
