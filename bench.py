@@ -644,7 +644,7 @@ def run_b200(args, rank, local_rank, world):
             del qp, tau_t
         except Exception as e:  # noqa: BLE001
             extra["qp_allocate"] = {"error": repr(e)}
-        # K4: actor/critic 64x64 forward (configs[3]) stand-alone, and fused with the env step
+        # K4: actor/critic 64x64 forward (configs[3]) stand-alone, and the rollout step built on it (policy kernel + env kernel)
         try:
             m = 1 << 23
             ac = M.ActorCritic(9, 7, (64, 64), "leaky_relu", device=dev, seed=3)
@@ -667,16 +667,15 @@ def run_b200(args, rank, local_rank, world):
             buf = M.TrajectoryBuffer(9, 7, 32, m, device=dev)     # 32 steps per call: the per-window bootstrap forward (ppo.py:311) is 1 / 32 of a policy pass
             state = {"t": 0}
 
-            def roll(fused):
-                M.rollout(env2, ac, buf, seed=3, start_step=state["t"], fused=fused)
+            def roll():
+                M.rollout(env2, ac, buf, seed=3, start_step=state["t"])
                 state["t"] += buf.max_size
-            for fused in (False, True):
-                env2.reset(fraction=0.8)
-                t = timed(lambda: roll(fused), 3, warm=1) / buf.max_size
-                extra["rollout_fused" if fused else "rollout_two_kernel"] = {
-                    "workload": "configs[3]: policy forward + env step + trajectory record, 8 Mi envs/GPU, training mode",
-                    "value": m / t, "unit": "env-steps/s", "ms_per_step": t * 1e3,
-                    "achieved_GBs": ROLLOUT_TRAIN_BYTES * m / t / 1e9}
+            t = timed(roll, 3, warm=1) / buf.max_size
+            extra["rollout_two_kernel"] = {
+                "workload": "configs[3]: policy forward + env step + trajectory record, 8 Mi envs/GPU, training mode "
+                            "(one policy kernel + one env kernel per step; fused arrangements measured slower: profiles/rollout_r2.md)",
+                "value": m / t, "unit": "env-steps/s", "ms_per_step": t * 1e3,
+                "achieved_GBs": ROLLOUT_TRAIN_BYTES * m / t / 1e9}
             # K5: GAE-lambda over the [T, n] buffer
             Tg = 64
             mg = 1 << 21
@@ -776,7 +775,7 @@ def run_b200(args, rank, local_rank, world):
         pick("pinv_pid", ("value", "unit", "us_per_launch"))
         pick("pinv_pid_16Mi", ("value", "unit", "ms_per_launch", "hbm_frac"))
         pick("policy_forward", ("value", "unit", "ms_per_launch", "achieved_TFLOPs"))
-        for k in ("rollout_two_kernel", "rollout_fused"):
+        for k in ("rollout_two_kernel",):
             pick(k, ("value", "unit", "ms_per_step", "achieved_GBs"))
             if k in kernels:
                 kernels[k]["hbm_frac"] = kernels[k]["achieved_GBs"] / peak_gbs

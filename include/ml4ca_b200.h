@@ -62,7 +62,7 @@ typedef struct ml4ca_env_cfg {
   float step_dt;          /* dt used by the action-derivative penalty = 0.01 * 20 (customEnv.py:81,311,317) */
   float reset_fraction;   /* fraction used by auto_reset (0.8, ppo.py:286,320) */
   float actuator_lag_s;   /* > 0: the thruster wrench follows its command through a first-order lag of this time constant,
-                             advanced every simulator sub-step (three more state rows; ml4ca_rollout_step refuses it).
+                             advanced every simulator sub-step (three more state rows).
                              0 (default): commanded thrust / azimuth act instantly */
   uint64_t seed;          /* Philox key */
   int64_t env_id_offset;  /* global id of local env 0: RNG streams do not depend on how envs shard over GPUs */
@@ -89,7 +89,7 @@ ML4CA_API int ml4ca_env_reset_to(ml4ca_env* env, const uint8_t* mask, const floa
 /* Side buffer for the value bootstrap at the episode-length cut (ppo.py:303-311: `last_val = 0 if d else v(o)` on the
  * observation o2 that env.step returned).  With auto_reset the in-kernel restart replaces that observation in the step's
  * output; cut_obs [obs_dim, n] (caller-owned device memory, NULL = off) receives it instead, for the envs whose flag byte
- * is exactly ML4CA_DONE_TRUNCATED; other columns are left untouched.  Used by ml4ca_env_step and ml4ca_rollout_step. */
+ * is exactly ML4CA_DONE_TRUNCATED; other columns are left untouched. */
 ML4CA_API int ml4ca_env_set_cut_obs(ml4ca_env* env, float* cut_obs);
 /* The `fraction` every later in-kernel restart samples with (curriculum learning, ppo.py:286,319-322: the reference passes
  * it to each env.reset).  Launch parameter: CUDA graphs captured earlier keep the value they were captured with. */
@@ -107,7 +107,7 @@ ML4CA_API int ml4ca_env_step(ml4ca_env* env, const float* action, float* obs, fl
 ML4CA_API int ml4ca_env_step_host(ml4ca_env* env, const float* action_host, float* obs_host, float* rew_host,
                                   uint8_t* done_host, void* stream);
 /* Revolt.state() / state_extended() (customEnv.py:196-205) of the current state: obs [obs_dim, n].  With the extended
- * state this needs the previous-thrust tail, which the library keeps after reset and ml4ca_rollout_step only. */
+ * state this needs the previous-thrust tail, which the library keeps after reset only. */
 ML4CA_API int ml4ca_env_observe(ml4ca_env* env, float* obs, void* stream);
 /* Copies of the SoA state (any pointer may be NULL): eta [3,n], nu [3,n], prev_thrust [3,n] (env order bow, port,
  * star), angles [3,n] (current_angles, customEnv.py:71), ep_len [n].  Also EF.get_NED_pos (errorFrame.py:19). */
@@ -192,17 +192,10 @@ ML4CA_API int ml4ca_policy_forward(ml4ca_policy* p, int64_t n, const float* obs,
                                    float* mu, void* stream);
 
 /* CUDA-graph support for launch-bound rollouts (no reference counterpart: the reference steps one env per sess.run).  With a
- * device-resident counter set, every later ml4ca_policy_forward / ml4ca_rollout_step uses step + *step_dev as the Philox
+ * device-resident counter set, every later ml4ca_policy_forward uses step + *step_dev as the Philox
  * step: a captured graph of T rollout steps (step arguments 0 .. T-1) is replayed epoch after epoch with fresh noise by
  * writing the epoch's first step number into the counter.  NULL restores the plain step argument. */
 ML4CA_API int ml4ca_policy_set_step_counter(ml4ca_policy* p, const uint32_t* step_dev);
-/* One fused rollout step = ppo.py:291-293 (`sess.run(get_action_ops)` then `env.step(a)`) for every environment of
- * `env` (RevoltFinal, extended state, continuous angles; 9 -> 7 policy): observation from the state in HBM -> tcgen05
- * MLP -> sampled action -> env step, in ONE kernel.  Trajectory records of this time step (each nullable):
- * obs [9, n] = the observation the policy saw, act [7, n], rew [n], val [n], logp [n], done [n] flags. */
-ML4CA_API int ml4ca_rollout_step(ml4ca_env* env, ml4ca_policy* p, uint64_t seed, uint32_t step, int32_t deterministic,
-                                 float* obs, float* act, float* rew, float* val, float* logp, uint8_t* done, void* stream);
-
 /* TrajectoryBuffer.finish_path for every environment (ppo.py:65-91; core.discount_cumsum core.py:48-63):
  * rew [T, n], val [T + 1, n] (row T = bootstrap values at the buffer end, ppo.py:311), done [T, n] flag bytes
  * (nullable) -> adv [T, n], ret [T, n].  boot [ceil(T / boot_window), n] (nullable): `last_val = v(o)` of ppo.py:311 at

@@ -75,8 +75,6 @@ _SIGNATURES = {
     "ml4ca_policy_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_f32p, ctypes.c_uint64, ctypes.c_uint32,
                                             ctypes.c_int32, ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_stream]),
     "ml4ca_policy_set_step_counter": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
-    "ml4ca_rollout_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32,
-                                          c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_stream]),
     "ml4ca_gae": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_u8p, c_f32p, ctypes.c_int32, ctypes.c_float, ctypes.c_float,
                                  c_f32p, c_f32p, c_stream]),
     "ml4ca_stats": (ctypes.c_int, [ctypes.c_int64, c_f32p, ctypes.c_void_p, c_stream]),

@@ -37,7 +37,7 @@ struct EnvParams {
   float* ref;          // [3, n]
   float* prev_thrust;  // [3, n]
   float* angles;       // [3, n] bow, port, star
-  float* obs_tail;     // [3, n] tail (prev_thrust / 100) of the last returned observation; fused rollout only
+  float* obs_tail;     // [3, n] tail (prev_thrust / 100) of the observation a reset returned (ml4ca_env_observe)
   float* cut_obs;      // [obs_dim, n] caller-owned, nullable (ml4ca_env_set_cut_obs): the observation an env returned at its
                        // episode-length cut, saved before the in-kernel restart replaces it (ppo.py:311 evaluates V on it)
   float* tau_act;      // [3, n] lagged thruster wrench (N, N, Nm); read and written only when cfg.actuator_lag_s > 0
@@ -79,7 +79,7 @@ struct ml4ca_env {
   int32_t device;
   void* slab;
   ml4ca::HostPipe* pipe = nullptr;
-  bool tail_valid;     // obs_tail rows describe the last returned observation (reset / fused steps keep it so)
+  bool tail_valid;     // obs_tail rows describe the last returned observation (true after a reset, false after a step)
   ml4ca::EnvParams p;
 };
 

@@ -195,26 +195,14 @@ struct PolicyGroups {
   static constexpr int THREADS = 4 * G * 32;
 };
 
-struct RolloutOut {   // trajectory slice of one time step (any pointer may be NULL = not recorded)
-  float* obs;    // [9, n]
-  float* act;    // [7, n]
-  float* rew;    // [n]
-  float* val;    // [n]
-  float* logp;   // [n]
-  uint8_t* done; // [n]
-};
-
-// FUSE = false: obs [obs_dim, n] -> act [act_dim, n] (sampled or deterministic), val [n], logp [n], mu (nullable).
-// FUSE = true : one fused rollout step of RevoltFinal(extended_state, cont_ang): observation from the env state in
-//               HBM -> policy -> sampled action -> env step (env_math.cuh) -> new state, reward, done; the observation
-//               and the action never round-trip through HBM except as trajectory records.
-//               S97 = the 9 -> 7 network of RevoltFinal(extended_state, cont_ang) with both dims known at compile time (no
-//               predicated row loads / stores); other shapes take the generic instantiation.
-template <int H, int NL, int ACTIVATION, bool FUSE, bool S97>
+// obs [obs_dim, n] -> act [act_dim, n] (sampled or deterministic), val [n], logp [n], mu (nullable).
+// S97 = the 9 -> 7 network of RevoltFinal(extended_state, cont_ang) with both dims known at compile time (no predicated row
+// loads / stores); other shapes take the generic instantiation.
+template <int H, int NL, int ACTIVATION, bool S97>
 __global__ void __launch_bounds__(PolicyGroups<H>::THREADS, 1)
 policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, uint64_t seed, uint32_t step,
               int deterministic, int64_t env_off, float* __restrict__ act_out, float* __restrict__ val_out,
-              float* __restrict__ logp_out, float* __restrict__ mu_out, const EnvParams ep, const RolloutOut ro) {
+              float* __restrict__ logp_out, float* __restrict__ mu_out) {
   using namespace tc05;
   constexpr int G = PolicyGroups<H>::G;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -355,7 +343,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
     __half* a0 = reinterpret_cast<__half*>(smem + a0_off(g));
     uint8_t* actb = smem + act_off(g);
     uint32_t dphase = 0;
-    constexpr int kPre = FUSE ? 1 : (S97 ? 9 : 12);   // observation rows fetched one tile ahead (wider inputs load the rest in place)
+    constexpr int kPre = S97 ? 9 : 12;   // observation rows fetched one tile ahead (wider inputs load the rest in place)
     float onext[kPre];
 #pragma unroll
     for (int c = 0; c < kPre; ++c) onext[c] = 0.f;
@@ -365,39 +353,13 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
       const int64_t tile = r * tiles_per_round + (int64_t)blockIdx.x * G + g;
       const int64_t env = tile * 128 + row;
       const bool live = env < n;
-      // ---- observation: from the caller's buffer, or computed from the env state -------------------------------
+      // ---- observation rows of this tile: requested during the previous tile (below, after its first hand-over), so their
+      // HBM latency is off the chain; only the first round loads in place
       float o[16];
-      // env state kept in registers across the MLP (fused mode)
-      float eN = 0.f, eE = 0.f, ePsi = 0.f, eu = 0.f, ev = 0.f, er = 0.f, rN = 0.f, rE = 0.f, rPsi = 0.f;
-      float pth[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < 16; ++c) o[c] = 0.f;
-      if constexpr (FUSE) {
-        if (live) {
-          eN = ep.eta[env], eE = ep.eta[ep.n + env], ePsi = ep.eta[2 * ep.n + env];
-          eu = ep.nu[env], ev = ep.nu[ep.n + env], er = ep.nu[2 * ep.n + env];
-          rN = ep.ref[env], rE = ep.ref[ep.n + env], rPsi = ep.ref[2 * ep.n + env];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) pth[c] = ep.prev_thrust[(int64_t)c * ep.n + env];
-          error_frame(eN, eE, ePsi, rN, rE, rPsi, o[0], o[1], o[2]);                // state_extended(), customEnv.py:196-205
-          o[3] = eu, o[4] = ev, o[5] = er;
-          // The observation the reference's agent acts on is the one returned by the PREVIOUS step, whose tail is the
-          // thrust before that step (state_extended() runs before prev_thrust is updated, customEnv.py:125-126).
-#pragma unroll
-          for (int c = 0; c < 3; ++c) o[6 + c] = ep.obs_tail[(int64_t)c * ep.n + env];
-          if (ro.obs != nullptr) {
-#pragma unroll
-            for (int c = 0; c < 9; ++c) ro.obs[(int64_t)c * n + env] = o[c];
-          }
-        }
-      } else {
-        // rows of this tile were requested during the previous tile (below, after its first hand-over), so their HBM
-        // latency is off the chain; only the first round loads in place
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          if (c < kPre) o[c] = (r == 0) ? ((c < OBS && live) ? __ldg(obs + (int64_t)c * n + env) : 0.f) : onext[c];
-          else o[c] = (c < OBS && live) ? __ldg(obs + (int64_t)c * n + env) : 0.f;
-        }
+      for (int c = 0; c < 16; ++c) {
+        if (c < kPre) o[c] = (r == 0) ? ((c < OBS && live) ? __ldg(obs + (int64_t)c * n + env) : 0.f) : onext[c];
+        else o[c] = (c < OBS && live) ? __ldg(obs + (int64_t)c * n + env) : 0.f;
       }
       {
 #pragma unroll
@@ -411,7 +373,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
       }
       ML4CA_TRACE(1);
       hand_over(g, row, 0);
-      if constexpr (!FUSE) {
+      {
         // next tile's observation rows: issued AFTER the hand-over (its MEMBAR would otherwise wait for these loads)
         const int64_t env2 = env + tiles_per_round * 128;
         const bool live2 = (r + 1 < rounds) && env2 < n;
@@ -454,7 +416,7 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
         hand_over(g, row, s + 1);
         ML4CA_TRACE(8 + s);
       }
-      // ---- output layer: mu, v -> sample, log-likelihood (-> env step) ---------------------------------------------
+      // ---- output layer: mu, v -> sample, log-likelihood ------------------------------------------------------------
       // The noise and the log-likelihood depend on neither network (logp_pi is a function of eps and log_std only): they
       // are drawn while the output chain runs on the tensor core, before the wait.
       float eps[kMaxAct];
@@ -506,74 +468,14 @@ policy_kernel(const PolicyParams pp, int64_t n, const float* __restrict__ obs, u
           pi[a] = 0.f;
           if (a < ACT) pi[a] = fmaf(eps[a], consts[a], out[a]);                  // mu + eps * exp(log_std), core.py:85
         }
-        if constexpr (!FUSE) {
 #pragma unroll
-          for (int a = 0; a < kMaxAct; ++a)
-            if (a < ACT) {
-              act_out[(int64_t)a * n + env] = pi[a];
-              if (mu_out != nullptr) mu_out[(int64_t)a * n + env] = out[a];
-            }
-          val_out[env] = vv;
-          logp_out[env] = logp;
-        } else {
-          // ---- env step: customEnv.py:92-133 on the sampled action (RevoltFinal, extended state, cont. angles) ----
-          using T = EnvTraits<ML4CA_ENV_FINAL, true>;
-          float a7[7], cmd[5];
-          int sat[5];
-#pragma unroll
-          for (int a = 0; a < 7; ++a) a7[a] = pi[a];
-          float sp, cp, ss, cs;
-          transform_action_final_cont(a7, cmd, sat, sp, cp, ss, cs);
-          float a_port = ep.angles[ep.n + env], a_star = ep.angles[2 * ep.n + env];
-          const float pa_port = a_port, pa_star = a_star;
-          a_port = cmd[3], a_star = cmd[4];
-          int32_t epl = ep.ep_len[env];
-          if (ep.n_sub > 0) {
-            float tx, ty, tn;
-            thruster_wrench_sc(cmd[0], cmd[1], cmd[2], 1.f, 0.f, sp, cp, ss, cs, tx, ty, tn);
-            integrate_hull(eN, eE, ePsi, eu, ev, er, tx, ty, tn, ep.n_sub, ep.hull);
+        for (int a = 0; a < kMaxAct; ++a)
+          if (a < ACT) {
+            act_out[(int64_t)a * n + env] = pi[a];
+            if (mu_out != nullptr) mu_out[(int64_t)a * n + env] = out[a];
           }
-          float xb, yb, pb;
-          error_frame(eN, eE, ePsi, rN, rE, rPsi, xb, yb, pb);
-          const float thrust[3] = {cmd[0], cmd[1], cmd[2]};
-          const float rew = reward_fn<true>(xb, yb, pb, eu, ev, er, thrust, pth, 0.f, a_port - pa_port, a_star - pa_star,
-                                            ep.inv_step_dt, 1.0f / T::ANG_BOUND);
-          const bool term = is_terminal(xb, yb, pb, eu, ev, er, ep.bounds);
-          epl += 1;
-          const bool trunc = (int32_t)((uint32_t)epl & kEpLenMask) >= ep.max_ep_len;
-          const uint32_t flags = (term ? ML4CA_DONE_TERMINAL : 0u) | (trunc ? ML4CA_DONE_TRUNCATED : 0u);
-          float npt[3] = {thrust[0], thrust[1], thrust[2]};
-          if (ep.auto_reset && flags != 0u) {
-            if (flags == ML4CA_DONE_TRUNCATED && ep.cut_obs != nullptr) {   // o2 of ppo.py:293 at the cut (ppo.py:311)
-              const float co[9] = {xb, yb, pb, eu, ev, er, div100(pth[0]), div100(pth[1]), div100(pth[2])};
-#pragma unroll
-              for (int c = 0; c < 9; ++c) ep.cut_obs[(int64_t)c * ep.n + env] = co[c];
-            }
-            sample_reset(ep.seed, ep.env_off + env, epl, ep.reset_scale, eN, eE, ePsi, eu, ev, er);
-            npt[0] = npt[1] = npt[2] = 0.f;
-            if (ep.reset_acts) sample_reset_thrust(ep.seed, ep.env_off + env, epl, npt);   // customEnv.py:179-188
-            epl = next_episode_word(epl);
-            a_port = T::DEF_PORT, a_star = T::DEF_STAR;
-          }
-          ep.eta[env] = eN, ep.eta[ep.n + env] = eE, ep.eta[2 * ep.n + env] = ePsi;
-          ep.nu[env] = eu, ep.nu[ep.n + env] = ev, ep.nu[2 * ep.n + env] = er;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            ep.prev_thrust[(int64_t)c * ep.n + env] = npt[c];
-            // tail of the observation this step returns: previous thrust / 100 (0 after a re-sample, :190)
-            ep.obs_tail[(int64_t)c * ep.n + env] = div100((ep.auto_reset && flags != 0u) ? npt[c] : pth[c]);
-          }
-          ep.angles[ep.n + env] = a_port, ep.angles[2 * ep.n + env] = a_star;
-          ep.ep_len[env] = epl;
-          if (ro.act != nullptr) {
-#pragma unroll
-            for (int a = 0; a < 7; ++a) ro.act[(int64_t)a * n + env] = pi[a];
-          }
-          if (ro.rew != nullptr) ro.rew[env] = rew;
-          if (ro.val != nullptr) ro.val[env] = vv;
-          if (ro.logp != nullptr) ro.logp[env] = logp;
-          if (ro.done != nullptr) ro.done[env] = (uint8_t)flags;
-        }
+        val_out[env] = vv;
+        logp_out[env] = logp;
       }
       ML4CA_TRACE(7);
     }
@@ -601,10 +503,10 @@ static int repack(ml4ca_policy* p, cudaStream_t st) {
   return check_launch("pack_weights_kernel");
 }
 
-template <int H, int NL, bool FUSE>
+template <int H, int NL>
 static int launch_policy(const ml4ca_policy* p, const PolicyParams& pp, int64_t n, const float* obs, uint64_t seed,
                          uint32_t step, int det, int64_t env_off, float* act, float* val, float* logp, float* mu,
-                         const EnvParams& ep, const RolloutOut& ro, cudaStream_t st) {
+                         cudaStream_t st) {
   constexpr int G = PolicyGroups<H>::G;
   const PolicySmem L(p->d, G);
   const int64_t tiles = (n + 127) / 128;
@@ -613,13 +515,11 @@ static int launch_policy(const ml4ca_policy* p, const PolicyParams& pp, int64_t 
   const bool s97 = p->d.obs == 9 && p->d.act == 7;
 #define ML4CA_POLICY_LAUNCH(ACTV, S97V)                                                                                   \
   do {                                                                                                                    \
-    auto k = policy_kernel<H, NL, ACTV, FUSE, S97V>;                                                                      \
+    auto k = policy_kernel<H, NL, ACTV, S97V>;                                                                           \
     ML4CA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));                            \
-    k<<<grid, PolicyGroups<H>::THREADS, L.total, st>>>(pp, n, obs, seed, step, det, env_off, act, val, logp, mu, ep, ro); \
+    k<<<grid, PolicyGroups<H>::THREADS, L.total, st>>>(pp, n, obs, seed, step, det, env_off, act, val, logp, mu);         \
   } while (0)
-  if constexpr (FUSE) {            // the fused rollout only exists for the 9 -> 7 network (checked by the caller)
-    if (p->d.activation == 1) ML4CA_POLICY_LAUNCH(1, true); else ML4CA_POLICY_LAUNCH(0, true);
-  } else if (s97) {
+  if (s97) {
     if (p->d.activation == 1) ML4CA_POLICY_LAUNCH(1, true); else ML4CA_POLICY_LAUNCH(0, true);
   } else {
     if (p->d.activation == 1) ML4CA_POLICY_LAUNCH(1, false); else ML4CA_POLICY_LAUNCH(0, false);
@@ -628,19 +528,17 @@ static int launch_policy(const ml4ca_policy* p, const PolicyParams& pp, int64_t 
   return check_launch("policy_kernel");
 }
 
-template <bool FUSE>
 static int dispatch_policy(const ml4ca_policy* p, int64_t n, const float* obs, uint64_t seed, uint32_t step, int det,
-                           int64_t env_off, float* act, float* val, float* logp, float* mu, const EnvParams& ep,
-                           const RolloutOut& ro, cudaStream_t st) {
+                           int64_t env_off, float* act, float* val, float* logp, float* mu, cudaStream_t st) {
   PolicyParams pp;
   pp.blob = p->blob;
   pp.params = p->params;
   pp.log_std_off = p->d.n_params_net(p->d.act);
   pp.d = p->d;
   pp.step_dev = p->step_dev;
-  if (p->d.H == 64 && p->d.NL == 2) return launch_policy<64, 2, FUSE>(p, pp, n, obs, seed, step, det, env_off, act, val, logp, mu, ep, ro, st);
-  if (p->d.H == 64 && p->d.NL == 3) return launch_policy<64, 3, FUSE>(p, pp, n, obs, seed, step, det, env_off, act, val, logp, mu, ep, ro, st);
-  return launch_policy<80, 3, FUSE>(p, pp, n, obs, seed, step, det, env_off, act, val, logp, mu, ep, ro, st);
+  if (p->d.H == 64 && p->d.NL == 2) return launch_policy<64, 2>(p, pp, n, obs, seed, step, det, env_off, act, val, logp, mu, st);
+  if (p->d.H == 64 && p->d.NL == 3) return launch_policy<64, 3>(p, pp, n, obs, seed, step, det, env_off, act, val, logp, mu, st);
+  return launch_policy<80, 3>(p, pp, n, obs, seed, step, det, env_off, act, val, logp, mu, st);
 }
 
 }  // namespace ml4ca
@@ -731,25 +629,7 @@ int ml4ca_policy_forward(ml4ca_policy* p, int64_t n, const float* obs, uint64_t 
                          int64_t env_id_offset, float* act, float* val, float* logp, float* mu, void* stream) {
   ML4CA_REQUIRE(p != nullptr && obs && act && val && logp, "policy, obs, act, val and logp are required");
   if (n <= 0) return n == 0 ? ML4CA_OK : ML4CA_ERR_INVALID;
-  EnvParams ep = {};
-  RolloutOut ro = {};
-  return dispatch_policy<false>(p, n, obs, seed, step, deterministic, env_id_offset, act, val, logp, mu, ep, ro,
-                                static_cast<cudaStream_t>(stream));
-}
-
-int ml4ca_rollout_step(ml4ca_env* env, ml4ca_policy* p, uint64_t seed, uint32_t step, int32_t deterministic, float* obs,
-                       float* act, float* rew, float* val, float* logp, uint8_t* done, void* stream) {
-  ML4CA_REQUIRE(env != nullptr && p != nullptr, "env and policy are required");
-  ML4CA_REQUIRE(env->cfg.kind == ML4CA_ENV_FINAL && env->cfg.cont_ang && env->cfg.extended_state,
-                "the fused rollout is built for RevoltFinal(extended_state=True, cont_ang=True)");
-  ML4CA_REQUIRE(p->d.obs == 9 && p->d.act == 7, "the fused rollout needs a 9 -> 7 policy");
-  ML4CA_REQUIRE(env->cfg.actuator_lag_s == 0.f, "the fused rollout has no actuator lag: use ml4ca_policy_forward + ml4ca_env_step");
-  ML4CA_REQUIRE(env->device == p->device, "env and policy live on different devices");
-  ML4CA_REQUIRE(env->tail_valid, "the fused rollout keeps the tail of the last returned observation in the env state; "
-                                 "after ml4ca_env_step calls, reset the env before using ml4ca_rollout_step");
-  RolloutOut ro = {obs, act, rew, val, logp, done};
-  return dispatch_policy<true>(p, env->n, nullptr, seed, step, deterministic, env->cfg.env_id_offset, nullptr, nullptr,
-                               nullptr, nullptr, env->p, ro, static_cast<cudaStream_t>(stream));
+  return dispatch_policy(p, n, obs, seed, step, deterministic, env_id_offset, act, val, logp, mu, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

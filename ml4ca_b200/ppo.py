@@ -75,8 +75,8 @@ class TrajectoryBuffer(object):
         return [self.obs_buf, self.act_buf, self.adv_buf, self.ret_buf, self.logp_buf]
 
 
-def _rollout_launches(env, ac, buf, seed, start_step, deterministic, fused):
-    """The 2T (or T) kernel launches of one rollout on the current stream; nothing else (capturable)."""
+def _rollout_launches(env, ac, buf, seed, start_step, deterministic):
+    """The 2T kernel launches of one rollout on the current stream; nothing else (capturable)."""
     L = _lib.lib()
     T, n = buf.max_size, env.num_envs
     stream = _lib.current_stream()
@@ -90,14 +90,6 @@ def _rollout_launches(env, ac, buf, seed, start_step, deterministic, fused):
                                               env._cfg.env_id_offset, _lib.ptr(buf._scratch[0]), _lib.ptr(buf.boot_buf[t // W]),
                                               _lib.ptr(buf._scratch[1]), None, stream), "ml4ca_policy_forward")
 
-    if fused:
-        for t in range(T):
-            _lib.check(L.ml4ca_rollout_step(env._handle, ac._handle, seed & 0xFFFFFFFFFFFFFFFF, start_step + t,
-                                            int(bool(deterministic)), _lib.ptr(buf.obs_buf[t]), _lib.ptr(buf.act_buf[t]),
-                                            _lib.ptr(buf.rew_buf[t]), _lib.ptr(buf.val_buf[t]), _lib.ptr(buf.logp_buf[t]),
-                                            _lib.ptr(buf.done_buf[t]), stream), "ml4ca_rollout_step")
-            bootstrap_window(t)
-        return
     rows = buf._obs_rows     # row t = observation acted on at step t; the env kernel writes row t + 1 directly (no per-step copy)
     for t in range(T):
         _lib.check(L.ml4ca_policy_forward(ac._handle, n, _lib.ptr(rows[t]), seed & 0xFFFFFFFFFFFFFFFF, start_step + t,
@@ -108,11 +100,11 @@ def _rollout_launches(env, ac, buf, seed, start_step, deterministic, fused):
         bootstrap_window(t)
 
 
-def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, fused=False, graph=False):
+def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, graph=False):
     """Fill ``buf`` with T = buf.max_size steps of every environment (ppo.py:290-302 batched).
 
-    fused=False: policy kernel then env-step kernel per time step (the faster arrangement on B200, see DESIGN.md);
-    fused=True: the single fused kernel (ml4ca_rollout_step), which keeps observation and action out of HBM.
+    One policy kernel and one env-step kernel per time step; the env kernel writes the next observation row of the buffer
+    directly.  (A single fused kernel was built in three arrangements and measured slower every time: profiles/rollout_r2.md.)
     graph=True: the T steps are captured once into a CUDA graph (per env / policy / buffer) and replayed on later calls --
     for small and medium batches the rollout is launch-bound (2T launches through ctypes); the Philox step number then comes
     from a device counter (ml4ca_policy_set_step_counter) that is set to ``start_step`` before every replay, so a graph
@@ -120,7 +112,7 @@ def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, fused=False
     The env must have auto_reset=True (finished episodes restart in-kernel) and must have been reset: both are checked.
     The observations returned at episode-length cuts go to ``buf.cut_obs`` and their values to ``buf.boot_buf``
     (ppo.py:311), window by window.
-    Returns the observation after the last step (for the bootstrap value); None on the fused path.
+    Returns the observation after the last step (for the bootstrap value).
     """
     T = buf.max_size
     if not env._cfg.auto_reset:
@@ -134,18 +126,17 @@ def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, fused=False
                                    device=buf.device)
         buf.__dict__.pop("_rollout_graphs", None)                     # captured graphs hold the old rows
     _lib.check(_lib.lib().ml4ca_env_set_cut_obs(env._handle, _lib.ptr(buf.cut_obs)), "ml4ca_env_set_cut_obs")
-    if not fused:
-        buf._obs_rows[0].copy_(env._obs)   # observation returned by the last reset() / step()
+    buf._obs_rows[0].copy_(env._obs)   # observation returned by the last reset() / step()
     if not graph:
-        _rollout_launches(env, ac, buf, seed, start_step, deterministic, fused)
+        _rollout_launches(env, ac, buf, seed, start_step, deterministic)
     else:
         cache = buf.__dict__.setdefault("_rollout_graphs", {})
         # launch parameters are baked into a captured graph: the restart fraction (curriculum) is part of the key
-        key = (id(env), id(ac), int(seed), bool(deterministic), bool(fused), float(env._cfg.reset_fraction))
+        key = (id(env), id(ac), int(seed), bool(deterministic), float(env._cfg.reset_fraction))
         entry = cache.get(key)
         if entry is None:                  # first call: eager, and remember that the next one may capture
             cache[key] = {"graph": None, "counter": torch.zeros(1, dtype=torch.int32, device=buf.device)}
-            _rollout_launches(env, ac, buf, seed, start_step, deterministic, fused)
+            _rollout_launches(env, ac, buf, seed, start_step, deterministic)
         else:
             L = _lib.lib()
             if entry["graph"] is None:
@@ -154,7 +145,7 @@ def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, fused=False
                     torch.cuda.synchronize(buf.device)
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, capture_error_mode="relaxed"):
-                        _rollout_launches(env, ac, buf, seed, 0, deterministic, fused)     # step = counter + t
+                        _rollout_launches(env, ac, buf, seed, 0, deterministic)     # step = counter + t
                 finally:
                     _lib.check(L.ml4ca_policy_set_step_counter(ac._handle, None))
                 entry["graph"] = g
@@ -162,8 +153,6 @@ def rollout(env, ac, buf, seed=0, start_step=0, deterministic=False, fused=False
             entry["counter"].fill_(v - (1 << 32) if v >= (1 << 31) else v)
             entry["graph"].replay()
     _lib.check(_lib.lib().ml4ca_env_set_cut_obs(env._handle, None))   # the launches (or the graph) hold the pointer
-    if fused:
-        return None
     env._obs = buf._obs_rows[T].clone()
     return env._obs
 
@@ -376,7 +365,7 @@ PPO_COLUMNS = ('LossPi', 'LossV', 'DeltaLossPi', 'DeltaLossV', 'Entropy', 'KL', 
 
 def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2, pi_lr=3e-4, vf_lr=1e-3,
         train_pi_iters=80, train_v_iters=80, lam=0.97, target_kl=0.01, seed=0, hidden_sizes=(64, 64),
-        activation="leaky_relu", fused=False, logger=None, logger_kwargs=None, graph=False, curriculum=False,
+        activation="leaky_relu", logger=None, logger_kwargs=None, graph=False, curriculum=False,
         reset_each_epoch=True, update_graph=None):
     """ppo.py:107-346 for a batched env: every epoch = ``steps_per_epoch`` steps of EVERY environment of ``env``
     (rollout), GAE-lambda (finish_path), advantage normalisation over all ranks, then the PPO update.
@@ -401,11 +390,11 @@ def ppo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, clip_ratio=0.2,
     config = dict(steps_per_epoch=steps_per_epoch, epochs=epochs, gamma=gamma, clip_ratio=clip_ratio, pi_lr=pi_lr,
                   vf_lr=vf_lr, train_pi_iters=train_pi_iters, train_v_iters=train_v_iters, lam=lam,
                   target_kl=target_kl, seed=seed)
-    return run_epochs(env, ac, buf, upd, steps_per_epoch, epochs, seed, fused, logger, logger_kwargs, config, PPO_COLUMNS,
+    return run_epochs(env, ac, buf, upd, steps_per_epoch, epochs, seed, logger, logger_kwargs, config, PPO_COLUMNS,
                       log_std_column=True, graph=graph, curriculum=curriculum, reset_each_epoch=reset_each_epoch)
 
 
-def run_epochs(env, ac, buf, upd, steps_per_epoch, epochs, seed, fused, logger, logger_kwargs, config, columns,
+def run_epochs(env, ac, buf, upd, steps_per_epoch, epochs, seed, logger, logger_kwargs, config, columns,
                log_std_column=False, graph=False, curriculum=False, reset_each_epoch=True):
     """The epoch loop shared by ppo() (ppo.py:283-346) and trpo() (trpo.py:327-384): rollout of every environment,
     bootstrap + GAE-lambda (cuts inside the buffer bootstrap with V of the observation returned at the cut, the buffer
@@ -432,10 +421,8 @@ def run_epochs(env, ac, buf, upd, steps_per_epoch, epochs, seed, fused, logger, 
     for epoch in range(epochs):
         fraction = min(3.0 * epoch / epochs, 0.8) if curriculum else 0.8   # ppo.py:319
         env.set_reset_fraction(fraction)                              # what the restarts inside this epoch sample with
-        o_last = rollout(env, ac, buf, seed=seed, start_step=step, fused=fused, graph=graph)
+        o_last = rollout(env, ac, buf, seed=seed, start_step=step, graph=graph)
         step += steps_per_epoch
-        if o_last is None:                        # fused path: the observation is rebuilt from the env state
-            o_last = env.observe()
         _, v_last, _ = ac.step(o_last, deterministic=True, step=step)
         buf.finish_path(last_val=v_last)          # ppo.py:311 for the envs still running at the epoch end
         with torch.cuda.device(dev):

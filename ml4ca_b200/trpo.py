@@ -216,7 +216,7 @@ class _InfoRecordingUpdater(object):
 
 def trpo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, target_kl=0.01, vf_lr=1e-3, train_v_iters=80,
          damping_coeff=0.1, cg_iters=10, backtrack_iters=10, backtrack_coeff=0.8, lam=0.97, seed=0, algo='trpo',
-         hidden_sizes=(64, 64), activation="leaky_relu", fused=False, logger=None, logger_kwargs=None, graph=False,
+         hidden_sizes=(64, 64), activation="leaky_relu", logger=None, logger_kwargs=None, graph=False,
          kernel='fp32'):
     """trpo.py:95-384 for a batched env (hyper-parameter defaults: trpo.py:95-99, train.py:86-90).  Every epoch =
     ``steps_per_epoch`` steps of EVERY environment, GAE-lambda, the TRPO (or NPG) policy step, ``train_v_iters`` value
@@ -234,5 +234,5 @@ def trpo(env, ac=None, steps_per_epoch=400, epochs=1, gamma=0.99, target_kl=0.01
     config = dict(steps_per_epoch=steps_per_epoch, epochs=epochs, gamma=gamma, target_kl=target_kl, vf_lr=vf_lr,
                   train_v_iters=train_v_iters, damping_coeff=damping_coeff, cg_iters=cg_iters,
                   backtrack_iters=backtrack_iters, backtrack_coeff=backtrack_coeff, lam=lam, seed=seed, algo=algo)
-    return run_epochs(env, ac, buf, _InfoRecordingUpdater(upd), steps_per_epoch, epochs, seed, fused, logger, logger_kwargs,
+    return run_epochs(env, ac, buf, _InfoRecordingUpdater(upd), steps_per_epoch, epochs, seed, logger, logger_kwargs,
                       config, TRPO_COLUMNS if algo == 'trpo' else NPG_COLUMNS, graph=graph)

@@ -91,8 +91,7 @@ def _reference_order_gae(rew, val, flags, boot_at, last_val, gamma, lam):
     return adv, ret
 
 
-@pytest.mark.parametrize("fused", [False, True])
-def test_value_bootstrap_at_the_episode_length_cut(cuda_device, fused):
+def test_value_bootstrap_at_the_episode_length_cut(cuda_device):
     """ppo.py:303-311: a trajectory cut by max_ep_len bootstraps with v(o) of the observation env.step RETURNED at the cut.
     With in-kernel restarts that observation is saved to a side buffer (ml4ca_env_set_cut_obs):
       (a) it equals, bit for bit, what an env WITHOUT auto-reset returns at that step;
@@ -110,7 +109,7 @@ def test_value_bootstrap_at_the_episode_length_cut(cuda_device, fused):
     envA, envB = mk(True), mk(False)
     envA.reset(); oB = envB.reset()
     buf = M.TrajectoryBuffer(9, 7, L, n, gamma=0.99, lam=0.97, device=cuda_device)
-    M.rollout(envA, ac, buf, seed=3, fused=fused)
+    M.rollout(envA, ac, buf, seed=3)
     assert buf.boot_window == L and buf.boot_buf.shape == (1, n)
     alive = torch.ones(n, dtype=torch.bool, device=cuda_device)
     for t in range(L):
@@ -127,9 +126,7 @@ def test_value_bootstrap_at_the_episode_length_cut(cuda_device, fused):
     env = mk(True)
     env.reset()
     buf = M.TrajectoryBuffer(9, 7, T, n, gamma=0.99, lam=0.97, device=cuda_device, max_ep_len=env.max_ep_len)
-    o_last = M.rollout(env, ac, buf, seed=3, fused=fused)
-    if o_last is None:
-        o_last = env.observe()
+    o_last = M.rollout(env, ac, buf, seed=3)
     v_last = ac.step(o_last, deterministic=True)[1]
     buf.finish_path(last_val=v_last)
     flags = buf.done_buf.cpu().numpy()

@@ -33,47 +33,3 @@ for _ in range(10): ac.step(obs, out=out)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 print('policy forward 8Mi obs: %.3f ms -> %.2f G obs/s, %.1f TFLOP/s' % (ms, n / ms / 1e6, n * 19712 / ms / 1e9))
-
-# ---- fused rollout step vs (policy forward -> env step) as separate kernels -------------------------------------
-import ctypes
-from ml4ca_b200 import _lib
-from ml4ca_b200.env import RevoltFinal, StandInHull
-n = 100000
-envA = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=n, seed=5, auto_reset=True, max_ep_len=60)
-envB = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=n, seed=5, auto_reset=True, max_ep_len=60)
-oA = envA.reset(); oB = envB.reset()
-ac.seed = 99
-dev = torch.device('cuda')
-T = 8
-for t in range(T):
-    # separate
-    pi, v, logp = ac.step(oA, step=t)
-    oA2, rA, dA, infoA = envA.step(pi)
-    # fused
-    obs_f = torch.empty(9, n, device=dev); act_f = torch.empty(7, n, device=dev); rew_f = torch.empty(n, device=dev)
-    val_f = torch.empty(n, device=dev); logp_f = torch.empty(n, device=dev); done_f = torch.empty(n, dtype=torch.uint8, device=dev)
-    _lib.check(_lib.lib().ml4ca_rollout_step(envB._handle, ac._handle, 99, t, 0, _lib.ptr(obs_f), _lib.ptr(act_f), _lib.ptr(rew_f),
-                                             _lib.ptr(val_f), _lib.ptr(logp_f), _lib.ptr(done_f), _lib.current_stream()))
-    torch.cuda.synchronize()
-    print('t', t, 'obs', float((obs_f - oA).abs().max()), 'act', float((act_f - pi).abs().max()), 'val', float((val_f - v).abs().max()),
-          'logp', float((logp_f - logp).abs().max()), 'rew', float((rew_f - rA).abs().max()), 'done eq', bool((done_f == infoA['flags']).all()),
-          'n done', int((done_f != 0).sum()))
-    oA = oA2
-sA, sB = envA.get_state(), envB.get_state()
-print('state diff', {k: float((sA[k].float() - sB[k].float()).abs().max()) for k in sA})
-# fused throughput, 16 Mi envs, training-mode records
-n = 1 << 24
-env = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=n, seed=2, auto_reset=True)
-env.reset()
-bufs = [torch.empty(9, n, device=dev), torch.empty(7, n, device=dev), torch.empty(n, device=dev), torch.empty(n, device=dev), torch.empty(n, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)]
-def fused(t, rec=True):
-    ptrs = [_lib.ptr(b) if rec else None for b in bufs]
-    if not rec: ptrs[2] = _lib.ptr(bufs[2]); ptrs[5] = _lib.ptr(bufs[5])
-    _lib.check(_lib.lib().ml4ca_rollout_step(env._handle, ac._handle, 7, t, 0, *ptrs, _lib.current_stream()))
-for rec in (True, False):
-    for t in range(3): fused(t, rec)
-    e0.record()
-    for t in range(20): fused(t, rec)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 20
-    print('fused rollout step 16Mi envs (%s): %.3f ms -> %.2f G env-steps/s' % ('training records' if rec else 'inference', ms, n / ms / 1e6))
