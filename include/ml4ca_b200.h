@@ -284,6 +284,34 @@ ML4CA_API int ml4ca_ppo_grad_ex(ml4ca_policy* p, int32_t net, int64_t n, int32_t
 ML4CA_API int ml4ca_adam_step_dev(int64_t m, float* params, const float* grad, float* m1, float* m2, float lr, float beta1,
                                   float beta2, float eps, float grad_scale, int32_t net, int32_t iter, const float* stats_tail,
                                   float count, float kl_limit, ml4ca_ppo_ctl* ctl, void* stream);
+/* ---- Gradient exchange over NVLink peer memory, fused with the Adam step (ranks = GPUs of one node) --------------------------
+ * Replaces MpiAdamOptimizer.compute_gradients / apply_gradients (spinup/utils/mpi_tf.py:45-80: Allreduce(SUM) of the flat
+ * gradient, division by the number of processes, Adam, parameter Bcast).  Every rank creates a comm (one device slab: flag
+ * words + two halves of max_floats), exports its 64-byte cudaIpcMemHandle_t, the caller gathers the handles of all ranks (any
+ * transport) and connects.  No reference counterpart for the plumbing: the reference is MPI on CPUs. */
+typedef struct ml4ca_peer_comm ml4ca_peer_comm;
+ML4CA_API int ml4ca_peer_comm_create(int32_t rank, int32_t world, int64_t max_floats, int32_t device, ml4ca_peer_comm** out);
+ML4CA_API int ml4ca_peer_comm_export(const ml4ca_peer_comm* c, uint8_t* handle64);
+/* handles [world][64] in rank order (the own entry is ignored). */
+ML4CA_API int ml4ca_peer_comm_connect(ml4ca_peer_comm* c, const uint8_t* handles);
+/* The same for ranks that share an address space (several comms in one process: threads as ranks, the single-GPU test of
+ * the protocol): slabs [world] = the device pointers ml4ca_peer_comm_slab returned for every rank. */
+ML4CA_API int ml4ca_peer_comm_slab(const ml4ca_peer_comm* c, void** slab);
+ML4CA_API int ml4ca_peer_comm_connect_ptrs(ml4ca_peer_comm* c, void* const* slabs);
+ML4CA_API int ml4ca_peer_comm_destroy(ml4ca_peer_comm* c);
+/* steps completed and waits given up (a peer did not publish within 5 s: results of that step are invalid). */
+ML4CA_API int ml4ca_peer_comm_status(ml4ca_peer_comm* c, int32_t* steps, int32_t* timeouts);
+/* In-place sum over ranks of buf [n] (device), one kernel: publish -> wait -> sum in rank order (bit-identical on every rank).
+ * tail_src (nullable, device, double): buf[tail_off + q], q < n_tail, is taken from (float)tail_src[q] (the statistics sums of
+ * ml4ca_ppo_grad).  ctl / iter: skipped like ml4ca_ppo_grad_ex.  Every rank must issue the same sequence of calls. */
+ML4CA_API int ml4ca_peer_allreduce(ml4ca_peer_comm* c, float* buf, int64_t n, const double* tail_src, int64_t tail_off,
+                                   int32_t n_tail, const ml4ca_ppo_ctl* ctl, int32_t iter, void* stream);
+/* ml4ca_peer_allreduce of the flat gradient buf [n] (statistics tail of 5 at tail_off) + ml4ca_adam_step_dev on the slice
+ * [lo, hi) in the same kernel.  params, m1, m2: bases of the FULL flat vectors (indexed like buf). */
+ML4CA_API int ml4ca_adam_step_peer(ml4ca_peer_comm* c, float* buf, int64_t n, const double* tail_src, int64_t tail_off, int64_t lo,
+                                   int64_t hi, float* params, float* m1, float* m2, float lr, float beta1, float beta2, float eps,
+                                   float grad_scale, int32_t net, int32_t iter, float count, float kl_limit, ml4ca_ppo_ctl* ctl,
+                                   void* stream);
 /* ml4ca_ppo_grad runs on the tensor cores by default (tcgen05, fp16 operands, fp32 accumulation: gradients to ~1e-3 of
  * the largest component).  enable = 1 selects the fp32 CUDA-core kernel (1e-5), 0 the tensor-core one, -1 only
  * queries; returns the previous setting.  Initial value: environment variable ML4CA_PPO_FP32. */

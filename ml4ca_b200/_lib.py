@@ -97,6 +97,19 @@ _SIGNATURES = {
     "ml4ca_adam_step_dev": (ctypes.c_int, [ctypes.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_float, ctypes.c_float,
                                            ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int32, ctypes.c_int32,
                                            c_f32p, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, c_stream]),
+    "ml4ca_peer_comm_create": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
+    "ml4ca_peer_comm_export": (ctypes.c_int, [ctypes.c_void_p, c_u8p]),
+    "ml4ca_peer_comm_connect": (ctypes.c_int, [ctypes.c_void_p, c_u8p]),
+    "ml4ca_peer_comm_slab": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "ml4ca_peer_comm_connect_ptrs": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "ml4ca_peer_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "ml4ca_peer_comm_status": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    "ml4ca_peer_allreduce": (ctypes.c_int, [ctypes.c_void_p, c_f32p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                                            ctypes.c_void_p, ctypes.c_int32, c_stream]),
+    "ml4ca_adam_step_peer": (ctypes.c_int, [ctypes.c_void_p, c_f32p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                            ctypes.c_int64, c_f32p, c_f32p, c_f32p, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                            ctypes.c_float, ctypes.c_float, ctypes.c_int32, ctypes.c_int32, ctypes.c_float,
+                                            ctypes.c_float, ctypes.c_void_p, c_stream]),
     "ml4ca_ppo_use_fp32": (ctypes.c_int, [ctypes.c_int]),
     "ml4ca_trpo_use_tensor_cores": (ctypes.c_int, [ctypes.c_int]),
     "ml4ca_trpo_policy_mu": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_stream]),

@@ -41,6 +41,16 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 constexpr int kNumSMs = 148;  // B200
 
 #ifdef __CUDACC__
+// TF-1 Adam on one parameter (tf.train.AdamOptimizer, mpi_tf.py:45):  m <- b1 m + (1 - b1) g;  v <- b2 v + (1 - b2) g^2;
+// p <- p - lr_t m / (sqrt(v) + eps).  Roundings are spelled out so that every kernel that applies the step (adam_kernel,
+// adam_dev_kernel, peer_adam_kernel) produces the same bits whatever the compiler contracts around it.
+__device__ __forceinline__ void adam_update(float& p, float& m1, float& m2, float g, float lr_t, float b1, float b2, float eps) {
+  const float a = __fmaf_rn(b1, m1, __fmul_rn(1.0f - b1, g));
+  const float v = __fmaf_rn(b2, m2, __fmul_rn(__fmul_rn(1.0f - b2, g), g));
+  m1 = a, m2 = v;
+  p = __fsub_rn(p, __fdiv_rn(__fmul_rn(lr_t, a), __fadd_rn(__fsqrt_rn(v), eps)));
+}
+
 // Sample s of a time-major [T, ., n] trajectory buffer -> (time step t, env i).  The update kernels tile the flat sample
 // index, so a tile may straddle time steps: no padding when n is small (the reference's own batch is 4 envs x 400 steps).
 __device__ __forceinline__ void split_sample(int64_t s, int64_t n, int64_t& t, int64_t& i) {

@@ -497,11 +497,7 @@ __global__ void __launch_bounds__(256) adam_kernel(int64_t m, float* __restrict_
                                                    float b2, float eps, float gscale) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  const float g = grad[i] * gscale;
-  const float a = b1 * m1[i] + (1.0f - b1) * g;
-  const float v = b2 * m2[i] + (1.0f - b2) * g * g;
-  m1[i] = a, m2[i] = v;
-  p[i] -= lr_t * a / (sqrtf(v) + eps);
+  adam_update(p[i], m1[i], m2[i], __fmul_rn(grad[i], gscale), lr_t, b1, b2, eps);
 }
 
 // Adam step of one optimizer inside the update graph: step count and early stop come from the control block.
@@ -521,11 +517,7 @@ __global__ void __launch_bounds__(256) adam_dev_kernel(int64_t m, float* __restr
   const float lr_t = lr_t_s;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < m) {
-    const float g = grad[i] * gscale;
-    const float a = b1 * m1[i] + (1.0f - b1) * g;
-    const float v = b2 * m2[i] + (1.0f - b2) * g * g;
-    m1[i] = a, m2[i] = v;
-    p[i] -= lr_t * a / (sqrtf(v) + eps);
+    adam_update(p[i], m1[i], m2[i], __fmul_rn(grad[i], gscale), lr_t, b1, b2, eps);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (iter == 0) {

@@ -82,6 +82,66 @@ def sync_all_params(flat_params, root=0):
     return flat_params
 
 
+class PeerComm(object):
+    """The gradient exchange of MpiAdamOptimizer (mpi_tf.py:45-80) over NVLink peer memory: ml4ca_peer_allreduce /
+    ml4ca_adam_step_peer (csrc/peer_comm.cu) sum a small flat buffer over the GPUs of one node inside ONE kernel that also
+    applies the Adam step -- no NCCL call, no separate scale / copy kernels.  ``PeerComm.create`` returns None (callers keep
+    the NCCL all-reduce) when there is a single rank, the backend is not NCCL, ML4CA_PEER_COMM=0, or any rank fails to map its
+    peers' memory (ranks on different nodes, no peer access): the decision is taken collectively."""
+
+    def __init__(self, handle, device):
+        self._handle, self.device = handle, device
+
+    @classmethod
+    def create(cls, max_floats, device):
+        import ctypes, os
+        from . import _lib
+        if not _on() or dist.get_backend() != "nccl" or os.environ.get("ML4CA_PEER_COMM", "1") == "0":
+            return None
+        if num_procs() > 16:
+            return None
+        device = torch.device(device)
+        L, h, ok = _lib.lib(), ctypes.c_void_p(), 1
+        mine = torch.zeros(64, dtype=torch.uint8)
+        with torch.cuda.device(device):
+            if L.ml4ca_peer_comm_create(proc_id(), num_procs(), int(max_floats), device.index, ctypes.byref(h)) != 0:
+                ok, h = 0, None
+            elif L.ml4ca_peer_comm_export(h, mine.data_ptr()) != 0:
+                ok = 0
+            every = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(num_procs())]
+            dist.all_gather(every, mine.to(device))
+            if ok and L.ml4ca_peer_comm_connect(h, torch.cat(every).cpu().contiguous().data_ptr()) != 0:
+                ok = 0
+            agree = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)       # also the barrier: every slab is mapped before anyone uses it
+            if int(agree.item()) == 0:
+                if h is not None:
+                    L.ml4ca_peer_comm_destroy(h)
+                if proc_id() == 0:
+                    import sys
+                    print("ml4ca_b200: peer-memory gradient exchange unavailable (%s); using NCCL"
+                          % _lib.lib().ml4ca_last_error().decode("utf-8", "replace"), file=sys.stderr)
+                return None
+        return cls(h, device)
+
+    def status(self):
+        """(steps completed, waits given up).  A non-zero second number means a peer did not answer within 5 s."""
+        import ctypes
+        from . import _lib
+        a, b = ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(_lib.lib().ml4ca_peer_comm_status(self._handle, ctypes.byref(a), ctypes.byref(b)), "ml4ca_peer_comm_status")
+        return a.value, b.value
+
+    def close(self):
+        if self._handle is not None:
+            from . import _lib
+            if dist.is_initialized():
+                torch.cuda.synchronize(self.device)
+                dist.barrier()                                  # nobody unmaps a slab a peer's kernel may still read
+            _lib.lib().ml4ca_peer_comm_destroy(self._handle)
+            self._handle = None
+
+
 def statistics_from_sums(sums3):
     """[sum, sum of squares, count] (already reduced over ranks) -> (mean, std), population std like
     mpi_statistics_scalar (:85-89: sqrt(sum((x - mean)^2) / n))."""

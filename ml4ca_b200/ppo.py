@@ -180,6 +180,10 @@ class PPOUpdater(object):
         self._stats2 = torch.zeros(8, dtype=torch.float64, device=dev)
         self._host = [torch.zeros(5, dtype=torch.float32).pin_memory() for _ in range(2)]
         self._events = [torch.cuda.Event() for _ in range(2)]
+        # ranks = GPUs of one node: the all-reduce of the flat gradient runs over NVLink peer memory inside the kernel that
+        # applies the Adam step (csrc/peer_comm.cu); None = single rank or peers not mappable -> NCCL all-reduce
+        from . import mpi_tools
+        self.peer = mpi_tools.PeerComm.create(P + 8, dev)
 
     # -- one gradient pass: returns the rank-summed statistics as a list of 5 floats and the global sample count ------
     def _slot(self, slot):
@@ -198,14 +202,26 @@ class PPOUpdater(object):
                                         _lib.ptr(stats), _lib.current_stream()), "ml4ca_ppo_grad")
         from . import mpi_tools
         P = ac.num_params
-        flat[P:P + 5].copy_(stats[:5])
-        mpi_tools.allreduce_sum_(flat)
+        self._exchange(flat, stats)
         count = float(T) * float(n) * mpi_tools.num_procs()   # equal shards (mpi_tools.shard_bounds differ by <= 1 env)
         if read == 'async':
             self._host[slot].copy_(flat[P:P + 5], non_blocking=True)
             self._events[slot].record()
             return None, count
         return (flat[P:P + 5].tolist() if read else None), count
+
+    def _exchange(self, flat, stats, ctl=None, it=0):
+        """Sum of the flat gradient (+ the five statistics, moved into its tail) over the ranks, in place."""
+        from . import mpi_tools
+        P = self.ac.num_params
+        if self.peer is not None:
+            with torch.cuda.device(self.ac.device):
+                _lib.check(_lib.lib().ml4ca_peer_allreduce(self.peer._handle, _lib.ptr(flat), P + 8, _lib.ptr(stats), P, 5,
+                                                           None if ctl is None else _lib.ptr(ctl), int(it), _lib.current_stream()),
+                           "ml4ca_peer_allreduce")
+        else:
+            flat[P:P + 5].copy_(stats[:5])
+            mpi_tools.allreduce_sum_(flat)
 
     def _read(self, slot):
         self._events[slot].synchronize()
@@ -262,12 +278,12 @@ class PPOUpdater(object):
         flat, stats, params = self.flat, self.stats, ac.parameters()
         kl_limit = 1.5 * self.target_kl
 
-        def one_pass(net, it, use_ctl):
+        def one_pass(net, it, use_ctl, exchange=True):
             _lib.check(L.ml4ca_ppo_grad_ex(ac._handle, net, int(n), int(T), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(adv), _lib.ptr(ret),
                                            _lib.ptr(logp), self.clip_ratio, _lib.ptr(flat), _lib.ptr(stats),
                                            _lib.ptr(ctl) if use_ctl else None, it, _lib.current_stream()), "ml4ca_ppo_grad_ex")
-            flat[P:P + 5].copy_(stats[:5])
-            mpi_tools.allreduce_sum_(flat)
+            if exchange:
+                self._exchange(flat, stats, ctl if use_ctl else None, it)
 
         def launches():
             st = _lib.current_stream()
@@ -275,6 +291,12 @@ class PPOUpdater(object):
             for net, iters, lr, limit in ((0, self.train_pi_iters, self.pi_lr, kl_limit), (1, self.train_v_iters, self.vf_lr, 0.0)):
                 lo, hi = (0, self.n_pi) if net == 0 else (self.n_pi, P)
                 for it in range(iters):
+                    if self.peer is not None:      # exchange + Adam + early-stop test in one kernel over NVLink peer memory
+                        one_pass(net, it, net == 0, exchange=False)
+                        _lib.check(L.ml4ca_adam_step_peer(self.peer._handle, _lib.ptr(flat), P + 8, _lib.ptr(stats), P, lo, hi,
+                                                          _lib.ptr(params), _lib.ptr(self.m1), _lib.ptr(self.m2), lr, 0.9, 0.999, 1e-8,
+                                                          1.0 / count, net, it, count, limit, _lib.ptr(ctl), st), "ml4ca_adam_step_peer")
+                        continue
                     one_pass(net, it, net == 0)
                     _lib.check(L.ml4ca_adam_step_dev(hi - lo, _lib.ptr(params[lo:hi]), _lib.ptr(flat[lo:hi]), _lib.ptr(self.m1[lo:hi]),
                                                      _lib.ptr(self.m2[lo:hi]), lr, 0.9, 0.999, 1e-8, 1.0 / count, net, it,
