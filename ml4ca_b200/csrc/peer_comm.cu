@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerArgs a) {
     lr_t_s = (float)((double)a.lr * sqrt(1.0 - pow((double)a.b2, (double)t)) / (1.0 - pow((double)a.b1, (double)t)));
   }
   // ---- B: wait for every rank's step number in the local flag words -----------------------------------------------------
-  if ((int)threadIdx.x < a.world) {
+  // (after a first timeout the exchange is dead: later steps do not wait again, the caller sees it in ml4ca_peer_comm_status)
+  if ((int)threadIdx.x < a.world && *reinterpret_cast<volatile uint32_t*>(&hdr->timeouts) == 0u) {
     long long t0 = 0;
     for (uint32_t polls = 0; (int32_t)(ld_acquire_sys(&hdr->flags[threadIdx.x]) - target) < 0; ++polls) {
       if (polls < 256) continue;            // the common case: the peer is a few microseconds behind

@@ -471,14 +471,15 @@ ML4CA_ROLLED
       else p[c] -= st * row[c];
     }
     Q.lam[bs] += st;
-    if (t2 <= t1) {
-      tableau_sweep<real, greal, 9>(S, gs, nc, bs, (real)1);
+    // one call site for both directions: lanes that add and lanes that drop run the sweep together
+    const bool add = (t2 <= t1);
+    tableau_sweep<real, greal, 9>(S, gs, nc, add ? bs : drop, add ? (real)1 : (real)-1);
+    if (add) {
       p[bs] = (sig > (real)0) ? Q.hi[bs] : Q.lo[bs];   // exactly on its bound
       in_act |= 1u << bs;
       n_act += 1;
       bs = -1;
     } else {
-      tableau_sweep<real, greal, 9>(S, gs, nc, drop, (real)-1);
       in_act &= ~(1u << drop);
       n_act -= 1;
       Q.lam[drop] = (real)0;

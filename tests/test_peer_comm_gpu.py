@@ -120,3 +120,25 @@ def test_arguments_are_checked(cuda_device):
     buf = torch.zeros(32, device=cuda_device)
     assert L.ml4ca_peer_allreduce(h, _lib.ptr(buf), 16, None, 0, 0, None, 0, None) != 0   # not connected
     _lib.check(L.ml4ca_peer_comm_destroy(h))
+
+
+def test_a_silent_peer_times_out_instead_of_hanging(cuda_device):
+    """Only rank 0 of two launches its exchange: the kernel gives up after ~5 s, counts the timeout and returns; later steps do
+    not wait again."""
+    import time
+    from ml4ca_b200 import _lib
+    L = _lib.lib()
+    comms = _make(2, 64, cuda_device)
+    buf = torch.ones(64, device=cuda_device)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _lib.check(L.ml4ca_peer_allreduce(comms[0], _lib.ptr(buf), 64, None, 0, 0, None, 0, None))
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    assert 1.0 < t1 - t0 < 20.0
+    assert _status(comms[0]) == (1, 1)
+    _lib.check(L.ml4ca_peer_allreduce(comms[0], _lib.ptr(buf), 64, None, 0, 0, None, 0, None))
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t1 < 1.0 and _status(comms[0]) == (2, 1)
+    for h in comms:
+        _lib.check(L.ml4ca_peer_comm_destroy(h))
