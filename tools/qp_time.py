@@ -27,4 +27,5 @@ for i in range(6):
     ok_rate = float(ok.float().mean())
 print(os.path.basename(os.environ.get("ML4CA_LIB", "libml4ca_b200.so")), os.environ.get("ML4CA_QP_THREADS", "-"),
       "ms %.3f (min of %s)" % (min(times[1:]), ["%.2f" % t for t in times]), "M alloc/s %.1f" % (m / min(times[1:]) / 1e3),
-      "success %.4f" % ok_rate, "checksum %.6f" % float(x.double().abs().mean()))
+      "success %.4f" % ok_rate, "checksum %.6f" % float(x.double().abs().mean()),
+      "sha %s" % __import__("hashlib").sha256(x.cpu().numpy().tobytes()).hexdigest()[:12])
