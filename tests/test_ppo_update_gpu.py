@@ -173,7 +173,9 @@ def test_graph_update_equals_eager_update(cuda_device, hidden, target_kl, want_s
     floor = float((pa - pc).norm()) / moved
     dist = float((pa - pb).norm()) / moved
     assert floor < 0.03 and dist < 0.03, (floor, dist)
-    assert dist <= 3.0 * floor + 2e-3, (floor, dist)
+    # the noise level itself scatters between pairs of runs (80^3 in that record: 2.6e-3 .. 6.8e-3), so one measured floor is
+    # no sharp bound for another pair: three floors or the largest recorded level, whichever is larger
+    assert dist <= max(3.0 * floor, 8e-3), (floor, dist)
     for a, b in zip(ia, ib):
         for k in ("LossPi", "LossV", "KL", "Entropy", "ClipFrac", "DeltaLossPi", "DeltaLossV"):
             assert abs(a[k] - b[k]) <= 2e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])

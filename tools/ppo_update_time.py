@@ -1,5 +1,6 @@
 """Device time of one graph-replayed PPO update (80 + 80 iterations) under torchrun: the gradient exchange over NVLink peer memory
-(default) against NCCL (ML4CA_PEER_COMM=0), at the bench batch (16 Ki envs x 400 steps per rank) and the reference's (4 x 400)."""
+(default) against NCCL (ML4CA_PEER_COMM=0), at the bench batch (16 Ki envs x 400 steps per rank) and the reference's (4 x 400).
+HIDDEN=80,80,80 times the reference's own network (generic fp32 gradient kernel) instead of the 64 x 64 of the bench config."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
@@ -12,7 +13,8 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 for n in [int(x) for x in os.environ.get("ENVS", "16384,4").split(",")]:
     T = 400
-    ac = M.ActorCritic(9, 7, (64, 64), "leaky_relu", device=dev, seed=4)
+    hidden = tuple(int(x) for x in os.environ.get("HIDDEN", "64,64").split(","))
+    ac = M.ActorCritic(9, 7, hidden, "leaky_relu", device=dev, seed=4)
     buf = M.TrajectoryBuffer(9, 7, T, n, device=dev)
     g = torch.Generator(device=dev); g.manual_seed(7 + rank)
     buf.obs_buf.normal_(generator=g); buf.adv_buf.normal_(generator=g); buf.ret_buf.normal_(generator=g)
@@ -33,8 +35,9 @@ for n in [int(x) for x in os.environ.get("ENVS", "16384,4").split(",")]:
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     if rank == 0:
-        print("%d rank(s), exchange %s, %5d envs x 400: update %.3f ms = %.1f us per iteration%s" % (
-            world, "none" if world == 1 else ("peer" if upd.peer is not None else "NCCL"), n, ms, ms / 160 * 1e3,
+        print("%d rank(s), hidden %s, exchange %s, %5d envs x 400: update %.3f ms = %.1f us per iteration = %.1f M sample-passes/s%s" % (
+            world, hidden, "none" if world == 1 else ("peer" if upd.peer is not None else "NCCL"), n, ms, ms / 160 * 1e3,
+            162 * n * T / ms / 1e3,
             "" if upd.peer is None else "  peer status %s" % (upd.peer.status(),)))
 if world > 1:
     dist.destroy_process_group()
