@@ -715,6 +715,29 @@ def run_b200(args, rank, local_rank, world):
             del env3, ac3
         except Exception as e:  # noqa: BLE001
             extra["ppo_train"] = {"error": repr(e)}
+        # the same training loop with the reference's OWN default network (train.py:30-32: 80 x 80 x 80, every shipped checkpoint but
+        # one): tcgen05 forward, generic fp32 gradient kernel (csrc/ppo_update_generic.cu); 2 Ki envs/GPU keep the leg short
+        try:
+            ne, Tp = 1 << 11, 400
+            env4 = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=ne, device=dev, seed=6,
+                               auto_reset=True, env_id_offset=rank * ne)
+            ac4 = M.ActorCritic(9, 7, (80, 80, 80), "leaky_relu", device=dev, seed=6)
+            marks = []
+
+            def mark4(info):
+                torch.cuda.synchronize()
+                marks.append(time.perf_counter())
+            _, hist = M.ppo(env4, ac4, steps_per_epoch=Tp, epochs=4, seed=6, graph=True, logger=mark4)
+            dt = max_over_ranks(sorted(b - a for a, b in zip(marks[1:-1], marks[2:]))[0])
+            hist = hist[2:]
+            passes = sum(h["StopIter"] + 1 + 80 + 2 for h in hist) / float(len(hist))
+            extra["ppo_train_80x3"] = {"workload": "PPO epoch with the reference's default 80 x 80 x 80 network, 2 Ki envs/GPU x 400 steps "
+                                                   "(generic fp32 gradient kernel)",
+                                       "value": ne * world * Tp / dt, "unit": "env-steps/s incl. update", "s_per_epoch": dt,
+                                       "gradient_passes_per_epoch": passes, "sample_passes_per_s": passes * ne * world * Tp / dt}
+            del env4, ac4
+        except Exception as e:  # noqa: BLE001
+            extra["ppo_train_80x3"] = {"error": repr(e)}
         # the same epoch with the TRPO update (train.py --algo trpo): CG on the Fisher-vector product + line search + 80 v steps;
         # once with every policy pass on the fp32 kernel (parity mode, default) and once with the CG passes on tcgen05
         for leg, kern in (("trpo_train", "fp32"), ("trpo_train_tc", "tensor_core")):
@@ -780,8 +803,8 @@ def run_b200(args, rank, local_rank, world):
             if k in kernels:
                 kernels[k]["hbm_frac"] = kernels[k]["achieved_GBs"] / peak_gbs
         pick("gae", ("value", "unit", "ms_per_launch", "hbm_frac"))
-        for k in ("ppo_train", "trpo_train", "trpo_train_tc"):
-            pick(k, ("value", "unit", "s_per_epoch"))
+        for k in ("ppo_train", "ppo_train_80x3", "trpo_train", "trpo_train_tc"):
+            pick(k, ("value", "unit", "s_per_epoch", "sample_passes_per_s"))
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -149,34 +149,64 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_generic_kernel(const Args A) {
   const int64_t n = A.n;
   const int64_t total = n * (int64_t)A.T;       // tiles run over the flat sample index (common.h: split_sample)
   const int64_t num_tiles = (total + TS - 1) / TS;
-  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    // ---- rows of this tile -> shared memory (warp w loads rows w, w + 8, ...; a lane two samples) ---------------------------
-    int64_t t2[2], i2[2];
-    bool live2[2];
+  // The rows of a tile (observation, action / return, advantage, old log-likelihood) are fetched ONE TILE AHEAD into registers
+  // (warp w: rows w, w + 8, ...; a lane two samples, coalesced) and written to shared memory when the previous tile has
+  // finished with them: their HBM latency is off the tile's chain.
+  const int rows_in = obs + (NET == 0 ? A.act + 2 : 1);
+  constexpr int RPW = 4;                        // rows per warp: obs <= 16, act <= 8, + 2
+  int64_t tN[2] = {0, 0}, iN[2] = {0, 0};
+  bool liveN[2] = {false, false};
+  float pre[RPW][2];
+  auto row_slot = [&](int row, float*& dst) {   // where row `row` of a tile lives in shared memory
+    if (row < obs) dst = act0 + (size_t)row * RS;
+    else if (NET == 1) dst = aux;
+    else if (row < obs + A.act) dst = actb + (size_t)(row - obs) * RS;
+    else if (row == obs + A.act) dst = aux;
+    else dst = aux + RS;
+  };
+  auto prefetch = [&](int64_t tile) {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int64_t smp = tile * TS + q * 32 + lane;
-      live2[q] = smp < total;
-      t2[q] = 0, i2[q] = 0;
-      if (live2[q]) split_sample(smp, n, t2[q], i2[q]);
+      liveN[q] = smp < total;
+      tN[q] = 0, iN[q] = 0;
+      if (liveN[q]) split_sample(smp, n, tN[q], iN[q]);
     }
-    const int rows_in = obs + (NET == 0 ? A.act + 2 : 1);
-    for (int row = warp; row < rows_in; row += NW) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int row = warp + NW * r;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const int64_t t = t2[q], i = i2[q];
-        const float* base;
-        int64_t off;
+        const int64_t t = tN[q], i = iN[q];
+        const float* base = nullptr;
+        int64_t off = 0;
+        if (row < obs) base = A.obs_buf, off = ((int64_t)t * obs + row) * n;
+        else if (row >= rows_in) base = nullptr;
+        else if (NET == 1) base = A.ret, off = (int64_t)t * n;
+        else if (row < obs + A.act) base = A.act_buf, off = ((int64_t)t * A.act + (row - obs)) * n;
+        else if (row == obs + A.act) base = A.adv, off = (int64_t)t * n;
+        else base = A.logp_old, off = (int64_t)t * n;
+        pre[r][q] = (base != nullptr && liveN[q]) ? __ldg(base + off + i) : 0.f;
+      }
+    }
+  };
+  if ((int64_t)blockIdx.x < num_tiles) prefetch(blockIdx.x);
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int64_t t2[2], i2[2];
+    bool live2[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) t2[q] = tN[q], i2[q] = iN[q], live2[q] = liveN[q];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int row = warp + NW * r;
+      if (row < rows_in) {
         float* dst;
-        if (row < obs) base = A.obs_buf, off = ((int64_t)t * obs + row) * n, dst = act0 + (size_t)row * RS;
-        else if (NET == 1) base = A.ret, off = (int64_t)t * n, dst = aux;
-        else if (row < obs + A.act) base = A.act_buf, off = ((int64_t)t * A.act + (row - obs)) * n, dst = actb + (size_t)(row - obs) * RS;
-        else if (row == obs + A.act) base = A.adv, off = (int64_t)t * n, dst = aux;
-        else base = A.logp_old, off = (int64_t)t * n, dst = aux + RS;
-        dst[q * 32 + lane] = (base != nullptr && live2[q]) ? __ldg(base + off + i) : 0.f;
+        row_slot(row, dst);
+        dst[lane] = pre[r][0], dst[32 + lane] = pre[r][1];
       }
     }
     __syncthreads();
+    if (tile + gridDim.x < num_tiles) prefetch(tile + gridDim.x);
     // ---- forward -----------------------------------------------------------------------------------------------------------
 #pragma unroll 1
     for (int l = 0; l < NL; ++l) {
