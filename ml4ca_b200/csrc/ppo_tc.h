@@ -12,7 +12,9 @@ struct Args {
   const float* params;     // flat fp32 master parameters
   const __half* blob;      // packed fp16 operands of this net (filled by the launcher)
   int obs, act, nout;      // nout = act (pi) or 1 (v)
-  int off_w1, off_b1, off_w2, off_b2, off_wo, off_bo, off_ls;
+  int hidden, n_hidden;    // H and NL: 64 x 64, 64^3, 80 x 80, 80^3
+  int off_w[4], off_b[4];  // flat offsets: [0] layer 1 (obs -> H), [l - 1] hidden layer l, [NL] output layer
+  int off_ls;
   int64_t n;
   int T;
   const float *obs_buf, *act_buf, *adv, *logp_old, *ret;
@@ -27,10 +29,12 @@ struct Args {
   int iter;
 };
 
-constexpr int kBlobHalves = 64 * 16 + 64 * 80 + 16 * 80 + 64 * 16 + 64 * 64;
+constexpr int kBlobHalves = 80 * 16 + 2 * 80 * 96 + 16 * 96 + 80 * 16 + 2 * 80 * 80;   // the largest shape (80^3)
 
 }  // namespace ppotc
 }  // namespace ml4ca
 
+// Shapes the tensor-core kernel is built for (obs / act dims other than 9 / 7 only with 64 x 64).
+bool ml4ca_ppo_tc_supports(int hidden, int n_hidden, int obs, int act);
 // Packs the operands into `blob` (>= kBlobHalves halves of device scratch) and launches the kernel.
 int ml4ca_ppo_grad_tc_launch(const ml4ca::ppotc::Args& args, int activation, int net, void* blob, cudaStream_t st);

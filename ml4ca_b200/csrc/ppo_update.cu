@@ -581,8 +581,9 @@ static int tc_blob(int32_t device, __half** out) {
 static ppotc::Args tc_args(const ppo::Args& a) {
   ppotc::Args t = {};
   t.params = a.params, t.obs = a.obs, t.act = a.act, t.nout = a.nout;
-  t.off_w1 = a.off_w1, t.off_b1 = a.off_b1, t.off_w2 = a.off_w2, t.off_b2 = a.off_b2, t.off_wo = a.off_wo;
-  t.off_bo = a.off_bo, t.off_ls = a.off_ls;
+  t.hidden = 64, t.n_hidden = 2;
+  t.off_w[0] = a.off_w1, t.off_b[0] = a.off_b1, t.off_w[1] = a.off_w2, t.off_b[1] = a.off_b2, t.off_w[2] = a.off_wo;
+  t.off_b[2] = a.off_bo, t.off_ls = a.off_ls;
   t.n = a.n, t.T = a.T;
   t.obs_buf = a.obs_buf, t.act_buf = a.act_buf, t.adv = a.adv, t.logp_old = a.logp_old, t.ret = a.ret;
   t.clip = a.clip, t.loss_mode = a.loss_mode, t.kl_ls_old = a.kl_ls_old, t.mu_out = a.mu_out;
@@ -643,6 +644,24 @@ static ppogen::Args generic_args(ml4ca_policy* p, const ml4ca_policy_cfg& cfg, i
   g.off_ls = net_size(Ad);
   g.n = n, g.T = T;
   return g;
+}
+
+// Argument block of the tensor-core kernel for one net of a policy whose shape is not the 64 x 64 of ppo::Args
+// (80^3, 64^3, 80 x 80: ml4ca_ppo_tc_supports).
+static ppotc::Args tc_deep_args(ml4ca_policy* p, const ml4ca_policy_cfg& cfg, int32_t net, int64_t n, int32_t T) {
+  const int H = cfg.hidden, O = cfg.obs_dim, Ad = cfg.act_dim, NL = cfg.n_hidden;
+  auto net_size = [&](int outw) { return O * H + H + (NL - 1) * (H * H + H) + H * outw + outw; };
+  ppotc::Args t = {};
+  t.params = ml4ca_policy_params(p);
+  t.obs = O, t.act = Ad, t.nout = net == 0 ? Ad : 1;
+  t.hidden = H, t.n_hidden = NL;
+  const int base = net == 0 ? 0 : net_size(Ad) + Ad;
+  t.off_w[0] = base, t.off_b[0] = base + O * H;
+  for (int l = 1; l < NL; ++l) t.off_w[l] = t.off_b[l - 1] + H, t.off_b[l] = t.off_w[l] + H * H;
+  t.off_w[NL] = t.off_b[NL - 1] + H, t.off_b[NL] = t.off_w[NL] + H * t.nout;
+  t.off_ls = net_size(Ad);
+  t.n = n, t.T = T;
+  return t;
 }
 
 static int ppo_launch_fp32(const ppo::Args& a, int activation, int net, cudaStream_t st) {
@@ -708,7 +727,19 @@ int ml4ca_ppo_grad_ex(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ML4CA_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)ml4ca_policy_num_params(&cfg), st));
   ML4CA_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 8, st));
-  if (a.params == nullptr) {     // 64^3 / 80^3 ...: generic fp32 kernel
+  if (a.params == nullptr && !g_use_fp32 && ml4ca_ppo_tc_supports(cfg.hidden, cfg.n_hidden, cfg.obs_dim, cfg.act_dim)) {
+    // the reference's own shapes (80^3, 64^3) on the tensor cores, like the 64 x 64 config
+    ppotc::Args t = tc_deep_args(p, cfg, net, n, T);
+    t.obs_buf = obs, t.act_buf = act, t.adv = adv, t.logp_old = logp_old, t.ret = ret;
+    t.clip = clip_ratio, t.grad = grad, t.stats = stats;
+    t.ctl = reinterpret_cast<const int32_t*>(ctl), t.iter = iter;
+    if (n * (int64_t)T == 0) return ML4CA_OK;
+    __half* blob = nullptr;
+    rc = tc_blob(device, &blob);
+    if (rc != ML4CA_OK) return rc;
+    return ml4ca_ppo_grad_tc_launch(t, cfg.activation, net, blob, st);
+  }
+  if (a.params == nullptr) {     // fp32 mode or another shape: generic fp32 kernel
     ppogen::Args g = generic_args(p, cfg, net, n, T);
     g.obs_buf = obs, g.act_buf = act, g.adv = adv, g.logp_old = logp_old, g.ret = ret;
     g.clip = clip_ratio, g.grad = grad, g.stats = stats;
@@ -739,6 +770,14 @@ int ml4ca_trpo_policy_mu(ml4ca_policy* p, int64_t n, int32_t T, const float* obs
   int32_t device = 0;
   int rc = ppo_args(p, 0, n, T, "ml4ca_trpo_policy_mu", &a, &cfg, &device);
   if (rc != ML4CA_OK) return rc;
+  if (a.params == nullptr && g_trpo_tc && n * (int64_t)T > 0 && ml4ca_ppo_tc_supports(cfg.hidden, cfg.n_hidden, cfg.obs_dim, cfg.act_dim)) {
+    ppotc::Args t = tc_deep_args(p, cfg, 0, n, T);
+    t.obs_buf = obs, t.mu_out = mu;
+    __half* blob = nullptr;
+    rc = tc_blob(device, &blob);
+    if (rc != ML4CA_OK) return rc;
+    return ml4ca_ppo_grad_tc_launch(t, cfg.activation, 0, blob, static_cast<cudaStream_t>(stream));
+  }
   if (a.params == nullptr) {
     ppogen::Args g = generic_args(p, cfg, 0, n, T);
     g.obs_buf = obs, g.mu_out = mu;
@@ -765,6 +804,15 @@ int ml4ca_trpo_kl_grad(ml4ca_policy* p, int64_t n, int32_t T, const float* obs, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ML4CA_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)ml4ca_policy_num_params(&cfg), st));
   ML4CA_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 8, st));
+  if (a.params == nullptr && g_trpo_tc && n * (int64_t)T > 0 && ml4ca_ppo_tc_supports(cfg.hidden, cfg.n_hidden, cfg.obs_dim, cfg.act_dim)) {
+    ppotc::Args t = tc_deep_args(p, cfg, 0, n, T);
+    t.obs_buf = obs, t.act_buf = mu_old, t.kl_ls_old = log_std_old, t.loss_mode = 1;
+    t.grad = grad, t.stats = stats;
+    __half* blob = nullptr;
+    rc = tc_blob(device, &blob);
+    if (rc != ML4CA_OK) return rc;
+    return ml4ca_ppo_grad_tc_launch(t, cfg.activation, 0, blob, st);
+  }
   if (a.params == nullptr) {
     ppogen::Args g = generic_args(p, cfg, 0, n, T);
     g.obs_buf = obs, g.act_buf = mu_old, g.kl_ls_old = log_std_old, g.loss_mode = 1;

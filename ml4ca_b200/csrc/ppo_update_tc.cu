@@ -1,8 +1,11 @@
 // ppo_update_tc.cu -- K6 on the tensor cores: PPO policy / value gradients with tcgen05 MMAs and TMEM accumulators.
 //
 // Same contract as ppo_grad_kernel (ppo_update.cu; reference ppo.py:234-250, core.py:29-46): forward, loss and
-// backward of ONE 64 x 64 network over every sample of a [T, ., n] buffer, gradient SUMS into the flat vector.
-// All seven GEMMs of a 128-sample tile run as tcgen05.mma (fp16 operands in shared memory, fp32 accumulation in
+// backward of ONE network over every sample of a [T, ., n] buffer, gradient SUMS into the flat vector.  Shapes (template
+// parameters H, NL): 64 x 64 (the BASELINE config), and the reference's own 80 x 80 x 80 (train.py:30-32), 64 x 64 x 64, 80 x 80.
+// The text below spells out the 64 x 64 case; a deeper net repeats the hidden stage (one more forward GEMM, one more
+// weight-gradient accumulator, one more backward-data GEMM per layer), a wider one has KP = H + 16 = 96 operand columns.
+// All GEMMs of a 128-sample tile (seven for two hidden layers, ten for three) run as tcgen05.mma (fp16 operands in shared memory, fp32 accumulation in
 // tensor memory); the CUDA cores only do the activation / loss epilogues:
 //
 //   forward      D = A0 B1^T          [128 x 16] x [64 x 16]^T      A0 = obs, 1 (bias column), pad
@@ -23,8 +26,9 @@
 // rows of the same buffer; those accumulator rows are garbage and are never flushed (rows are independent).
 //
 // Bias gradients fall out of the constant-1 columns (row H of dWo / dW2, column obs of dW1T).  Weight-gradient
-// accumulators stay in TMEM for all tiles of the CTA (persistent grid) and are flushed once.  Three tile groups of
-// 128 threads (thread = sample = TMEM lane) run out of phase; an elected lane of the first two warps of a group issues its
+// accumulators stay in TMEM for all tiles of the CTA (persistent grid) and are flushed once.  Tile groups of 128 threads
+// (thread = sample = TMEM lane; three for 64 x 64, two for 64^3 and 80 x 80, one for 80^3: shared memory -- 100 KB of
+// operand buffers per group at 80^3 -- and the 512 TMEM columns decide) run out of phase; an elected lane of the first two warps of a group issues its
 // MMA chains (independent chains of a stage go to different issuers: one thread's MMAs run strictly one after the other).
 //
 // Numerics: fp16 operands (activations, weights, back-propagated signals x 64), fp32 accumulation: gradients agree
@@ -43,24 +47,36 @@ namespace ppotc {
 
 using namespace tc05;
 
-constexpr int H = 64, KP = 80, TS = 128, OP = 16;
-constexpr int G = 3;                       // tile groups per CTA
-constexpr int THREADS = G * 128;
+constexpr int TS = 128, OP = 16;
 constexpr float kScale = 64.0f;            // loss scaling of the back-propagated signals (fp16 range)
 
-// ---- shared memory --------------------------------------------------------------------------------------------------
-constexpr int A0_B = TS * 16 * 2, A1_B = TS * KP * 2, A2_B = TS * KP * 2, G3_B = TS * 16 * 2, G2_B = TS * H * 2;
-constexpr int GROUP_B = A0_B + A1_B + A2_B + G3_B + G2_B;      // 65536
-constexpr int B1_E = H * 16, B2_E = H * KP, BO_E = OP * KP, WOT_E = H * 16, W2N_E = H * H;
-constexpr int BLOB_E = B1_E + B2_E + BO_E + WOT_E + W2N_E;     // 12544 halves = 25088 B
-constexpr int OFF_BLOB = 0;
-constexpr int OFF_GROUPS = (BLOB_E * 2 + 127) & ~127;
-constexpr int OFF_TAIL = OFF_GROUPS + G * GROUP_B;             // 2 KB of zeros: spill target of the last transposed view
-constexpr int OFF_BARS = OFF_TAIL + 2048;
-constexpr int OFF_CONST = OFF_BARS + 64;                       // sd[8], inv[8], ls[8], kiv[8], kls[8]
-constexpr int OFF_TMEM = OFF_CONST + 160;
-constexpr int OFF_RED = OFF_TMEM + 16;                         // double [G * 4][8]
-constexpr int SMEM_BYTES = OFF_RED + G * 4 * 8 * 8;
+// Sizes, shared-memory plan and tensor-memory plan of one network shape (H hidden units, NL hidden layers).
+template <int H_, int NL_>
+struct Shape {
+  static constexpr int H = H_, NL = NL_, KP = H_ + 16;
+  // tile groups per CTA: 3 x 64 KB (64 x 64), 2 x 84 KB (64^3), 2 x 76 KB (80 x 80), 1 x 100 KB (80^3)
+  static constexpr int G = (H_ == 64 && NL_ == 2) ? 3 : ((H_ == 80 && NL_ == 3) ? 1 : 2);
+  static constexpr int THREADS = G * 128;
+  // ---- shared memory: per group A0 | A_1 .. A_NL (activations entering layers 2 .. NL and the output layer) | G_out | G_hidden
+  static constexpr int A0_B = TS * 16 * 2, AH_B = TS * KP * 2, GO_B = TS * 16 * 2, GH_B = TS * H * 2;
+  static constexpr int GROUP_B = A0_B + NL * AH_B + GO_B + GH_B;
+  // operand images: B1 | B_2 .. B_NL | Bo | WoT | Wn_2 .. Wn_NL
+  static constexpr int B1_E = H * 16, BH_E = H * KP, BO_E = OP * KP, WOT_E = H * 16, WN_E = H * H;
+  static constexpr int BLOB_E = B1_E + (NL - 1) * BH_E + BO_E + WOT_E + (NL - 1) * WN_E;
+  static constexpr int OFF_BLOB = 0;
+  static constexpr int OFF_GROUPS = (BLOB_E * 2 + 127) & ~127;
+  static constexpr int OFF_TAIL = OFF_GROUPS + G * GROUP_B;   // 2 KB of zeros: spill target of the last transposed view
+  static constexpr int OFF_BARS = OFF_TAIL + 2048;
+  static constexpr int OFF_CONST = OFF_BARS + 64;             // sd[8], inv[8], ls[8], kiv[8], kls[8]
+  static constexpr int OFF_TMEM = OFF_CONST + 160;
+  static constexpr int OFF_RED = OFF_TMEM + 16;               // double [G * 4][8]
+  static constexpr int SMEM_BYTES = OFF_RED + G * 4 * 8 * 8;
+  // ---- tensor memory, per group: D [H] | dW_2 .. dW_NL [H each] | dWo [16] | dW1T [16]
+  static constexpr int TMEM_G = NL * H + 32;
+  static_assert(G * TMEM_G <= 512, "tensor memory");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+  static_assert(BLOB_E <= kBlobHalves, "operand blob scratch");
+};
 
 __host__ __device__ __forceinline__ int canon(int row, int k, int K_total) {
   return (row >> 3) * (K_total * 8) + (k >> 3) * 64 + (row & 7) * 8 + (k & 7);
@@ -72,10 +88,14 @@ __host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn, int b_mn) {
 }
 
 
-// fp32 master parameters of one net -> the five fp16 operand images (canonical K-major).
+// fp32 master parameters of one net -> its fp16 operand images (canonical K-major).  off_w / off_b: [0] layer 1 (obs -> H),
+// [l - 1] hidden layer l, [NL] output layer.
+template <int H, int NL>
 __global__ void pack_kernel(Args A, __half* __restrict__ blob) {
+  using S = Shape<H, NL>;
+  constexpr int KP = S::KP;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= BLOB_E) return;
+  if (e >= S::BLOB_E) return;
   if (A.ctl != nullptr && A.ctl[0] != 0 && A.ctl[1] < A.iter) return;   // the policy loop has stopped (ml4ca_ppo_ctl)
   auto inv = [](int f, int K, int& row, int& k) {   // invert canon()
     const int rg = f / (K * 8), rem = f % (K * 8);
@@ -84,27 +104,29 @@ __global__ void pack_kernel(Args A, __half* __restrict__ blob) {
   const float* P = A.params;
   float v = 0.f;
   int row, k, f = e;
-  if (f < B1_E) {                                  // B1 [j][k]: W1[k][j], b1[j] at k = obs
+  if (f < S::B1_E) {                               // B1 [j][k]: W1[k][j], b1[j] at k = obs
     inv(f, 16, row, k);
-    if (k < A.obs) v = P[A.off_w1 + k * H + row];
-    else if (k == A.obs) v = P[A.off_b1 + row];
-  } else if ((f -= B1_E) < B2_E) {                 // B2 [j][k]: W2[k][j], b2[j] at k = H
-    inv(f, KP, row, k);
-    if (k < H) v = P[A.off_w2 + k * H + row];
-    else if (k == H) v = P[A.off_b2 + row];
-  } else if ((f -= B2_E) < BO_E) {                 // Bo [o][k]: Wo[k][o], bo[o] at k = H
+    if (k < A.obs) v = P[A.off_w[0] + k * H + row];
+    else if (k == A.obs) v = P[A.off_b[0] + row];
+  } else if ((f -= S::B1_E) < (NL - 1) * S::BH_E) { // B_l [j][k]: W_l[k][j], b_l[j] at k = H
+    const int l = 1 + f / S::BH_E;                  // index into off_w / off_b
+    inv(f % S::BH_E, KP, row, k);
+    if (k < H) v = P[A.off_w[l] + k * H + row];
+    else if (k == H) v = P[A.off_b[l] + row];
+  } else if ((f -= (NL - 1) * S::BH_E) < S::BO_E) { // Bo [o][k]: Wo[k][o], bo[o] at k = H
     inv(f, KP, row, k);
     if (row < A.nout) {
-      if (k < H) v = P[A.off_wo + k * A.nout + row];
-      else if (k == H) v = P[A.off_bo + row];
+      if (k < H) v = P[A.off_w[NL] + k * A.nout + row];
+      else if (k == H) v = P[A.off_b[NL] + row];
     }
-  } else if ((f -= BO_E) < WOT_E) {                // WoT [k][o]: Wo[k][o]
+  } else if ((f -= S::BO_E) < S::WOT_E) {           // WoT [k][o]: Wo[k][o]
     inv(f, 16, row, k);
-    if (k < A.nout) v = P[A.off_wo + row * A.nout + k];
-  } else {                                         // W2n [k_in][j]: W2[k_in][j]
-    f -= WOT_E;
-    inv(f, H, row, k);
-    v = P[A.off_w2 + row * H + k];
+    if (k < A.nout) v = P[A.off_w[NL] + row * A.nout + k];
+  } else {                                         // Wn_l [k_in][j]: W_l[k_in][j]
+    f -= S::WOT_E;
+    const int l = 1 + f / S::WN_E;
+    inv(f % S::WN_E, H, row, k);
+    v = P[A.off_w[l] + row * H + k];
   }
   blob[e] = __float2half_rn(v);
 }
@@ -129,9 +151,13 @@ __device__ __forceinline__ float2 act_grad2(uint32_t h2) {
 }
 
 // S97: the 9 -> 7 (pi) / 9 -> 1 (v) networks of RevoltFinal(extended_state, cont_ang) with the dims known at compile time.
-template <int ACTIVATION, int NET, bool S97>
-__global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
+template <int ACTIVATION, int NET, bool S97, int H, int NL>
+__global__ void __launch_bounds__((Shape<H, NL>::THREADS), 1) ppo_grad_tc_kernel(const Args A) {
   if (A.ctl != nullptr && A.ctl[0] != 0 && A.ctl[1] < A.iter) return;   // uniform: before any barrier / TMEM allocation
+  using S = Shape<H, NL>;
+  constexpr int KP = S::KP, G = S::G, THREADS = S::THREADS, GROUP_B = S::GROUP_B, A0_B = S::A0_B, AH_B = S::AH_B, GO_B = S::GO_B;
+  constexpr int OFF_BLOB = S::OFF_BLOB, OFF_GROUPS = S::OFF_GROUPS, OFF_BARS = S::OFF_BARS, OFF_CONST = S::OFF_CONST,
+                OFF_TMEM = S::OFF_TMEM, BLOB_E = S::BLOB_E;
   extern __shared__ __align__(128) uint8_t smem[];
   // warp index through a shuffle: warp-uniform for the compiler, so the group index and every MMA descriptor derived from it
   // live in uniform registers (tcgen05.mma then issues back to back, without a per-thread waterfall loop)
@@ -161,10 +187,9 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
   __syncthreads();
   {
     uint8_t* base = smem + OFF_GROUPS + g * GROUP_B;
-    __half* a1 = reinterpret_cast<__half*>(base + A0_B);
-    __half* a2 = reinterpret_cast<__half*>(base + A0_B + A1_B);
-    a1[canon(row, H, KP)] = __float2half_rn(1.0f);     // bias columns of the hidden operands
-    a2[canon(row, H, KP)] = __float2half_rn(1.0f);
+#pragma unroll
+    for (int l = 1; l <= NL; ++l)                      // bias columns of the hidden operands
+      reinterpret_cast<__half*>(base + A0_B + (l - 1) * AH_B)[canon(row, H, KP)] = __float2half_rn(1.0f);
   }
   if (threadIdx.x == 0) {
     for (int q = 0; q < G; ++q) mbar_init(&bars[q], 2);   // the two issuing warps of a group each commit their part of a stage
@@ -179,17 +204,24 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
 
   // ---- per-group addresses ----------------------------------------------------------------------------------------------
   const uint32_t sb = smem_u32(smem);
-  const uint32_t sA0 = sb + OFF_GROUPS + g * GROUP_B, sA1 = sA0 + A0_B, sA2 = sA1 + A1_B, sG3 = sA2 + A2_B, sG2 = sG3 + G3_B;
-  const uint32_t sG1 = sG2;                                    // G1 re-uses the G2 buffer (dead once the dW2 / G2 W2n^T chains are done)
-  const uint32_t sB1 = sb + OFF_BLOB, sB2 = sB1 + B1_E * 2, sBo = sB2 + B2_E * 2, sWoT = sBo + BO_E * 2, sW2n = sWoT + WOT_E * 2;
+  // operand buffers of the group: A0, A_l = activations leaving hidden layer l (l = 1 .. NL), G_out, one G_hidden buffer that
+  // every back-propagated signal re-uses (its readers have completed before the next one is written: each epilogue waits)
+  const uint32_t sA0 = sb + OFF_GROUPS + g * GROUP_B;
+  auto sA = [&](int l) { return sA0 + A0_B + (uint32_t)(l - 1) * AH_B; };
+  const uint32_t sGo = sA0 + A0_B + NL * AH_B, sGh = sGo + GO_B;
+  // operand images: B1, B_l (l = 2 .. NL), Bo, WoT, Wn_l (l = 2 .. NL)
+  const uint32_t sB1 = sb + OFF_BLOB;
+  auto sB = [&](int l) { return sB1 + S::B1_E * 2 + (uint32_t)(l - 2) * S::BH_E * 2; };
+  const uint32_t sBo = sB1 + S::B1_E * 2 + (NL - 1) * S::BH_E * 2, sWoT = sBo + S::BO_E * 2;
+  auto sWn = [&](int l) { return sWoT + S::WOT_E * 2 + (uint32_t)(l - 2) * S::WN_E * 2; };
   uint8_t* gbase = smem + OFF_GROUPS + g * GROUP_B;
   __half* pA0 = reinterpret_cast<__half*>(gbase);
-  uint8_t* pA1 = gbase + A0_B;
-  uint8_t* pA2 = pA1 + A1_B;
-  __half* pG3 = reinterpret_cast<__half*>(pA2 + A2_B);
-  uint8_t* pG2 = pA2 + A2_B + G3_B;
-  uint8_t* pG1 = pG2;
-  const uint32_t tD = tmem_base + g * 160, tW2 = tD + 64, tWo = tD + 128, tW1 = tD + 144;
+  auto pA = [&](int l) { return gbase + A0_B + (l - 1) * AH_B; };
+  __half* pGo = reinterpret_cast<__half*>(gbase + A0_B + NL * AH_B);
+  uint8_t* pGh = gbase + A0_B + NL * AH_B + GO_B;
+  // accumulators: D, dW_l (l = 2 .. NL), dWo, dW1T
+  const uint32_t tD = tmem_base + g * S::TMEM_G, tWo = tD + NL * H, tW1 = tWo + 16;
+  auto tW = [&](int l) { return tD + (uint32_t)(l - 1) * H; };
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
 
   // MMA chains (one elected thread per group).  K-major operand: lbo = 128 B, sbo = K_total * 16 B, +256 B per k-step.
@@ -310,29 +342,29 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
       fence_before_sync();
       sync_group();
     };
-    hidden(pA1);
-    if ((warp & 3) < 2) {                                          // warp-uniform: the two issuing warps of the group
-      if (elect_one()) {
-        fence_after_sync();
-        if ((warp & 3) == 0) {
-          chain_k(tD, sA1, KP, sB2, KP, H, KP / 16, false);        // F2
-        }
-        mma_commit(&bars[g]);
+#define ML4CA_ISSUE2(W0, W1)                                                                                      \
+  if ((warp & 3) < 2) { /* warp-uniform: the two issuing warps of the group */                                     \
+    if (elect_one()) {                                                                                            \
+      fence_after_sync();                                                                                         \
+      if ((warp & 3) == 0) {                                                                                      \
+        W0;                                                                                                       \
+      } else {                                                                                                    \
+        W1;                                                                                                       \
+      }                                                                                                           \
+      mma_commit(&bars[g]);                                                                                       \
+    }                                                                                                             \
+    __syncwarp();                                                                                                 \
+  }
+#pragma unroll
+    for (int l = 1; l <= NL; ++l) {
+      hidden(pA(l));
+      if (l < NL) {
+        ML4CA_ISSUE2(chain_k(tD, sA(l), KP, sB(l + 1), KP, H, KP / 16, false), (void)0);       // F_{l+1}
+      } else {
+        ML4CA_ISSUE2(chain_k(tD, sA(NL), KP, sBo, KP, OP, KP / 16, false), (void)0);           // output layer
       }
-      __syncwarp();
     }
-    hidden(pA2);
-    if ((warp & 3) < 2) {                                          // warp-uniform: the two issuing warps of the group
-      if (elect_one()) {
-        fence_after_sync();
-        if ((warp & 3) == 0) {
-          chain_k(tD, sA2, KP, sBo, KP, OP, KP / 16, false);       // F3
-        }
-        mma_commit(&bars[g]);
-      }
-      __syncwarp();
-    }
-    // ---- loss: per-sample dOUT (sum convention), scaled, -> G3 ---------------------------------------------------------------
+    // ---- loss: per-sample dOUT (sum convention), scaled, -> G_out ---------------------------------------------------------------
     wait_mma();
     float out[16];
     tmem_ld16(tD + lane_off, out);
@@ -396,22 +428,12 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
       uint32_t w[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) w[k] = pack_f16x2(dout[2 * k] * kScale, dout[2 * k + 1] * kScale);
-      *reinterpret_cast<uint4*>(pG3 + canon(row, 0, 16)) = make_uint4(w[0], w[1], w[2], w[3]);
-      *reinterpret_cast<uint4*>(pG3 + canon(row, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(pGo + canon(row, 0, 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(pGo + canon(row, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
     }
     sync_group();
-    if ((warp & 3) < 2) {                                          // warp-uniform: the two issuing warps of the group
-      if (elect_one()) {
-        fence_after_sync();
-        if ((warp & 3) == 0) {
-          chain_mn(tWo, sA2, KP, sG3, 16, OP, acc);                // dWo += A2^T G3
-        } else {
-          chain_k(tD, sG3, 16, sWoT, 16, H, 1, false);             // D = G3 WoT^T
-        }
-        mma_commit(&bars[g]);
-      }
-      __syncwarp();
-    }
+    ML4CA_ISSUE2(chain_mn(tWo, sA(NL), KP, sGo, 16, OP, acc),        // dWo += A_NL^T G_out
+                 chain_k(tD, sGo, 16, sWoT, 16, H, 1, false));       // D = G_out WoT^T
     // ---- backward epilogues: G = D .* f'(h) ------------------------------------------------------------------------------------
     auto backward = [&](const uint8_t* hsrc, uint8_t* dst) {
       wait_mma();
@@ -435,30 +457,15 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
       fence_before_sync();
       sync_group();
     };
-    backward(pA2, pG2);
-    if ((warp & 3) < 2) {                                          // warp-uniform: the two issuing warps of the group
-      if (elect_one()) {
-        fence_after_sync();
-        if ((warp & 3) == 0) {
-          chain_mn(tW2, sA1, KP, sG2, H, H, acc);                  // dW2 += A1^T G2
-        } else {
-          chain_k(tD, sG2, H, sW2n, H, H, H / 16, false);          // D = G2 W2n^T
-        }
-        mma_commit(&bars[g]);
-      }
-      __syncwarp();
+#pragma unroll
+    for (int l = NL; l >= 2; --l) {
+      backward(pA(l), pGh);                                          // G_l = D .* f'(A_l)
+      ML4CA_ISSUE2(chain_mn(tW(l), sA(l - 1), KP, sGh, H, H, acc),   // dW_l += A_{l-1}^T G_l
+                   chain_k(tD, sGh, H, sWn(l), H, H, H / 16, false)); // D = G_l Wn_l^T
     }
-    backward(pA1, pG1);                                            // G1 takes over the G2 buffer (its readers have completed)
-    if ((warp & 3) < 2) {                                          // warp-uniform: the two issuing warps of the group
-      if (elect_one()) {
-        fence_after_sync();
-        if ((warp & 3) == 0) {
-          chain_mn(tW1, sG1, H, sA0, 16, OP, acc);                 // dW1T += G1^T A0
-        }
-        mma_commit(&bars[g]);
-      }
-      __syncwarp();
-    }
+    backward(pA(1), pGh);                                            // G_1 (the buffer's readers have completed)
+    ML4CA_ISSUE2(chain_mn(tW1, sGh, H, sA0, 16, OP, acc), (void)0);  // dW1T += G_1^T A0
+#undef ML4CA_ISSUE2
     acc = true;
     pending = true;                                                // waited for before A0 / G2 are written again
   }
@@ -471,26 +478,29 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
     float v[16];
     // tcgen05.ld is warp-collective: every thread loads, the row test only guards the atomics
 #pragma unroll
-    for (int c0 = 0; c0 < H; c0 += 16) {               // dW2 rows k = 0..63, row 64 = bias b2
-      tmem_ld16(tW2 + lane_off + c0, v);
-      if (row <= H) {
+    for (int l = 2; l <= NL; ++l) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          atomicAdd(gr + (row < H ? A.off_w2 + row * H : A.off_b2) + c0 + j, v[j] * unscale);
+      for (int c0 = 0; c0 < H; c0 += 16) {             // dW_l rows k = 0 .. H - 1, row H = bias b_l
+        tmem_ld16(tW(l) + lane_off + c0, v);
+        if (row <= H) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            atomicAdd(gr + (row < H ? A.off_w[l - 1] + row * H : A.off_b[l - 1]) + c0 + j, v[j] * unscale);
+        }
       }
     }
     tmem_ld16(tWo + lane_off, v);
     if (row <= H) {
 #pragma unroll
       for (int o = 0; o < 8; ++o)
-        if (o < nout) atomicAdd(gr + (row < H ? A.off_wo + row * nout : A.off_bo) + o, v[o] * unscale);
+        if (o < nout) atomicAdd(gr + (row < H ? A.off_w[NL] + row * nout : A.off_b[NL]) + o, v[o] * unscale);
     }
     tmem_ld16(tW1 + lane_off, v);        // dW1T: lane = hidden unit j, column = input k (k = obs: bias b1)
     if (row < H) {
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        if (k < obs) atomicAdd(gr + A.off_w1 + k * H + row, v[k] * unscale);
-        else if (k == obs) atomicAdd(gr + A.off_b1 + row, v[k] * unscale);
+        if (k < obs) atomicAdd(gr + A.off_w[0] + k * H + row, v[k] * unscale);
+        else if (k == obs) atomicAdd(gr + A.off_b[0] + row, v[k] * unscale);
       }
     }
   }
@@ -520,25 +530,29 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc_kernel(const Args A) {
 using namespace ml4ca;
 
 // Host side: called by ml4ca_ppo_grad (ppo_update.cu) unless ML4CA_PPO_FP32 is set.  `blob` is scratch for the packed
-// fp16 operands (>= ppotc::BLOB_E halves), owned by the caller.
-static_assert(ppotc::BLOB_E == ppotc::kBlobHalves, "operand blob size");
-
-int ml4ca_ppo_grad_tc_launch(const ppotc::Args& args, int activation, int net, void* blob, cudaStream_t st) {
+// fp16 operands (>= ppotc::kBlobHalves halves), owned by the caller.
+template <int H, int NL>
+static int launch_shape(const ppotc::Args& args, int activation, int net, void* blob, cudaStream_t st) {
+  using S = ppotc::Shape<H, NL>;
   ppotc::Args a = args;
   __half* b = static_cast<__half*>(blob);
-  ppotc::pack_kernel<<<(ppotc::BLOB_E + 255) / 256, 256, 0, st>>>(a, b);
+  ppotc::pack_kernel<H, NL><<<(S::BLOB_E + 255) / 256, 256, 0, st>>>(a, b);
   int rc = check_launch("ppo pack_kernel");
   if (rc != ML4CA_OK) return rc;
   a.blob = b;
   const int64_t tiles = (a.n * (int64_t)a.T + ppotc::TS - 1) / ppotc::TS;
-  const int64_t want = (tiles + ppotc::G - 1) / ppotc::G;
+  const int64_t want = (tiles + S::G - 1) / S::G;
   const int grid = (int)(want < kNumSMs ? want : kNumSMs);
   const bool s97 = a.obs == 9 && a.act == 7;
+  // the 9 -> 7 dims are compiled in for every shape; other dims exist for the 64 x 64 config only (ml4ca_ppo_tc_supports)
 #define ML4CA_TC_LAUNCH(ACTV, NETV)                                                                                      \
   do {                                                                                                                   \
-    auto k = s97 ? ppotc::ppo_grad_tc_kernel<ACTV, NETV, true> : ppotc::ppo_grad_tc_kernel<ACTV, NETV, false>;           \
-    ML4CA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, ppotc::SMEM_BYTES));                 \
-    k<<<grid, ppotc::THREADS, ppotc::SMEM_BYTES, st>>>(a);                                                               \
+    auto k = ppotc::ppo_grad_tc_kernel<ACTV, NETV, true, H, NL>;                                                         \
+    if constexpr (H == 64 && NL == 2) {                                                                                  \
+      if (!s97) k = ppotc::ppo_grad_tc_kernel<ACTV, NETV, false, H, NL>;                                                 \
+    }                                                                                                                    \
+    ML4CA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));                     \
+    k<<<grid, S::THREADS, S::SMEM_BYTES, st>>>(a);                                                                       \
   } while (0)
   if (activation == 1) {
     if (net == 0) ML4CA_TC_LAUNCH(1, 0); else ML4CA_TC_LAUNCH(1, 1);
@@ -547,4 +561,17 @@ int ml4ca_ppo_grad_tc_launch(const ppotc::Args& args, int activation, int net, v
   }
 #undef ML4CA_TC_LAUNCH
   return check_launch("ppo_grad_tc_kernel");
+}
+
+bool ml4ca_ppo_tc_supports(int hidden, int n_hidden, int obs, int act) {
+  if (hidden == 64 && n_hidden == 2) return obs <= 15 && act <= 8;
+  return (hidden == 64 || hidden == 80) && (n_hidden == 2 || n_hidden == 3) && obs == 9 && act == 7;
+}
+
+int ml4ca_ppo_grad_tc_launch(const ppotc::Args& args, int activation, int net, void* blob, cudaStream_t st) {
+  ML4CA_REQUIRE(ml4ca_ppo_tc_supports(args.hidden, args.n_hidden, args.obs, args.act), "shape not built for the tensor-core gradient kernel");
+  if (args.hidden == 64) {
+    return args.n_hidden == 2 ? launch_shape<64, 2>(args, activation, net, blob, st) : launch_shape<64, 3>(args, activation, net, blob, st);
+  }
+  return args.n_hidden == 2 ? launch_shape<80, 2>(args, activation, net, blob, st) : launch_shape<80, 3>(args, activation, net, blob, st);
 }
