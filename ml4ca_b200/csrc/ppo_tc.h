@@ -12,7 +12,7 @@ struct Args {
   const float* params;     // flat fp32 master parameters
   const __half* blob;      // packed fp16 operands of this net (filled by the launcher)
   int obs, act, nout;      // nout = act (pi) or 1 (v)
-  int hidden, n_hidden;    // H and NL: 64 x 64, 64^3, 80 x 80, 80^3
+  int hidden, n_hidden;    // H and NL: 64 x 64, 64^3, 80^3
   int off_w[4], off_b[4];  // flat offsets: [0] layer 1 (obs -> H), [l - 1] hidden layer l, [NL] output layer
   int off_ls;
   int64_t n;

@@ -2,7 +2,7 @@
 //
 // Same contract as ppo_grad_kernel (ppo_update.cu; reference ppo.py:234-250, core.py:29-46): forward, loss and
 // backward of ONE network over every sample of a [T, ., n] buffer, gradient SUMS into the flat vector.  Shapes (template
-// parameters H, NL): 64 x 64 (the BASELINE config), and the reference's own 80 x 80 x 80 (train.py:30-32), 64 x 64 x 64, 80 x 80.
+// parameters H, NL): 64 x 64 (the BASELINE config), and the reference's own 80 x 80 x 80 (train.py:30-32) and 64 x 64 x 64.
 // The text below spells out the 64 x 64 case; a deeper net repeats the hidden stage (one more forward GEMM, one more
 // weight-gradient accumulator, one more backward-data GEMM per layer), a wider one has KP = H + 16 = 96 operand columns.
 // All GEMMs of a 128-sample tile (seven for two hidden layers, ten for three) run as tcgen05.mma (fp16 operands in shared memory, fp32 accumulation in
@@ -27,7 +27,7 @@
 //
 // Bias gradients fall out of the constant-1 columns (row H of dWo / dW2, column obs of dW1T).  Weight-gradient
 // accumulators stay in TMEM for all tiles of the CTA (persistent grid) and are flushed once.  Tile groups of 128 threads
-// (thread = sample = TMEM lane; three for 64 x 64, two for 64^3 and 80 x 80, one for 80^3: shared memory -- 100 KB of
+// (thread = sample = TMEM lane; three for 64 x 64, two for 64^3, one for 80^3: shared memory -- 100 KB of
 // operand buffers per group at 80^3 -- and the 512 TMEM columns decide) run out of phase; an elected lane of the first two warps of a group issues its
 // MMA chains (independent chains of a stage go to different issuers: one thread's MMAs run strictly one after the other).
 //
@@ -54,7 +54,7 @@ constexpr float kScale = 64.0f;            // loss scaling of the back-propagate
 template <int H_, int NL_>
 struct Shape {
   static constexpr int H = H_, NL = NL_, KP = H_ + 16;
-  // tile groups per CTA: 3 x 64 KB (64 x 64), 2 x 84 KB (64^3), 2 x 76 KB (80 x 80), 1 x 100 KB (80^3)
+  // tile groups per CTA: 3 x 64 KB (64 x 64), 2 x 84 KB (64^3), 1 x 100 KB (80^3)
   static constexpr int G = (H_ == 64 && NL_ == 2) ? 3 : ((H_ == 80 && NL_ == 3) ? 1 : 2);
   static constexpr int THREADS = G * 128;
   // ---- shared memory: per group A0 | A_1 .. A_NL (activations entering layers 2 .. NL and the output layer) | G_out | G_hidden
@@ -565,7 +565,7 @@ static int launch_shape(const ppotc::Args& args, int activation, int net, void* 
 
 bool ml4ca_ppo_tc_supports(int hidden, int n_hidden, int obs, int act) {
   if (hidden == 64 && n_hidden == 2) return obs <= 15 && act <= 8;
-  return (hidden == 64 || hidden == 80) && (n_hidden == 2 || n_hidden == 3) && obs == 9 && act == 7;
+  return (hidden == 64 || hidden == 80) && n_hidden == 3 && obs == 9 && act == 7;     // the shapes policy.cu runs forward
 }
 
 int ml4ca_ppo_grad_tc_launch(const ppotc::Args& args, int activation, int net, void* blob, cudaStream_t st) {
@@ -573,5 +573,5 @@ int ml4ca_ppo_grad_tc_launch(const ppotc::Args& args, int activation, int net, v
   if (args.hidden == 64) {
     return args.n_hidden == 2 ? launch_shape<64, 2>(args, activation, net, blob, st) : launch_shape<64, 3>(args, activation, net, blob, st);
   }
-  return args.n_hidden == 2 ? launch_shape<80, 2>(args, activation, net, blob, st) : launch_shape<80, 3>(args, activation, net, blob, st);
+  return launch_shape<80, 3>(args, activation, net, blob, st);
 }

@@ -75,7 +75,7 @@ def test_gradients_and_statistics(cuda_device, precision, activation, T, n):
     assert abs(s[1] / N - info["v_loss"]) < stol * info["v_loss"]
 
 
-@pytest.mark.parametrize("hidden", [(80, 80, 80), (64, 64, 64), (80, 80), (48,)])
+@pytest.mark.parametrize("hidden", [(80, 80, 80), (64, 64, 64), (48,)])
 @pytest.mark.parametrize("activation", ["leaky_relu", "tanh"])
 def test_gradients_of_the_reference_network_shapes(cuda_device, precision, hidden, activation):
     """The reference trains 80 x 80 x 80 by default (train.py:30-32; every shipped checkpoint is 80^3 or 64^3): those shapes
@@ -179,9 +179,10 @@ def test_graph_update_equals_eager_update(cuda_device, hidden, target_kl, want_s
     floor = float((pa - pc).norm()) / moved
     dist = float((pa - pb).norm()) / moved
     assert floor < 0.03 and dist < 0.03, (floor, dist)
-    # the noise level itself scatters between pairs of runs (80^3 in that record: 2.6e-3 .. 6.8e-3), so one measured floor is
-    # no sharp bound for another pair: three floors or the largest recorded level, whichever is larger
-    assert dist <= max(3.0 * floor, 8e-3), (floor, dist)
+    # the noise level itself scatters between pairs of runs (80^3 on the tensor-core kernel, second part of that record: eager vs
+    # eager 6.3e-3 .. 1.9e-2, graph vs graph 5.4e-3 .. 1.7e-2, eager vs graph 6.3e-3 .. 1.9e-2), so one measured floor is no sharp
+    # bound for another pair: three floors or the largest recorded level, whichever is larger
+    assert dist <= max(3.0 * floor, 2e-2), (floor, dist)
     for a, b in zip(ia, ib):
         for k in ("LossPi", "LossV", "KL", "Entropy", "ClipFrac", "DeltaLossPi", "DeltaLossV"):
             assert abs(a[k] - b[k]) <= 2e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])
