@@ -175,3 +175,43 @@ def test_tensor_core_kernel_option(cuda_device):
     assert np.dot(x, x64) / (np.linalg.norm(x) * np.linalg.norm(x64)) > 0.998
     assert abs(upd.last["alpha"] / ref["alpha"] - 1) < 0.02
     assert info["KL"] <= 0.01 and info["DeltaLossPi"] < 0
+
+
+def test_tensor_core_kernel_option_for_the_shipped_architecture(cuda_device):
+    """kernel='tensor_core' with the reference's default 80 x 80 x 80 network: the KL-gradient passes run on the tcgen05 kernel
+    templated on width and depth (csrc/ppo_update_tc.cu); the check is the generic fp32 kernel on the same buffer (the float64
+    TRPO restatement covers two hidden layers): means within the fp16 tolerance, Hessian-vector product within 2 %, and a
+    whole TRPO update inside the KL budget that improves the surrogate."""
+    import ml4ca_b200 as M
+    T, n = 4, 8192
+    rng = np.random.default_rng(3)
+    dims = dict(obs_dim=9, act_dim=7, hidden=80, n_hidden=3)
+    flat = MO.glorot_params(dims, seed=5)
+    flat = (flat + rng.normal(size=flat.size).astype(np.float32) * 0.05).astype(np.float32)
+    ac = M.ActorCritic(9, 7, (80, 80, 80), "leaky_relu", params=flat, device=cuda_device)
+    obs = torch.as_tensor((rng.normal(size=(T, 9, n)) * np.array([2, 2, .3, .5, .1, .2, .5, .5, .5])[None, :, None]).astype(np.float32),
+                          device=cuda_device)
+    buf = M.GAEBuffer(9, 7, T, n, device=cuda_device)
+    buf.obs_buf.copy_(obs)
+    a, _, lp = ac.step(obs.permute(1, 0, 2).reshape(9, -1).contiguous(), deterministic=False, step=0)
+    act = a.reshape(7, T, n).permute(1, 0, 2).contiguous()
+    buf.record_info(ac)                                          # means of the old policy from the fp32 generic kernel
+    mu_fp32 = buf.mu_buf.clone()
+    eps = (act - mu_fp32) / torch.exp(buf.log_std_buf.reshape(1, 7, 1))
+    adv = eps[:, 0, :] + 0.5 * torch.randn(T, n, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(1))
+    adv = (adv - adv.mean()) / adv.std()
+    data = [obs, act, adv.contiguous(), torch.zeros(T, n, device=cuda_device), lp.reshape(T, n).contiguous()]
+    full = data + [buf.log_std_buf, buf.mu_buf]
+    upd = M.TRPOUpdater(ac, kernel='tensor_core')
+    upd._record_mu_tc(full, T, n)
+    scale = 1 + float(mu_fp32.abs().max())
+    assert float((upd._mu_tc - mu_fp32).abs().max()) < 6e-3 * scale          # three fp16 layers (two: 4e-3)
+    g0, kl0 = upd._kl(full, T, n, tensor_core=True)
+    assert abs(kl0) < 1e-6
+    theta = upd._pi_params().double().cpu().numpy()
+    v, _ = upd._surrogate(full, T, n)                            # the direction the CG solve starts from (as in the 64 x 64 test)
+    h_tc = upd.hvp(full, T, n, theta, v, tensor_core=True)
+    h_32 = upd.hvp(full, T, n, theta, v, tensor_core=False)
+    assert np.linalg.norm(h_tc - h_32) < 2e-2 * np.linalg.norm(h_32)
+    info = upd.update_policy(full, T, n)
+    assert info["KL"] <= 0.01 and info["DeltaLossPi"] < 0
