@@ -716,9 +716,9 @@ def run_b200(args, rank, local_rank, world):
         except Exception as e:  # noqa: BLE001
             extra["ppo_train"] = {"error": repr(e)}
         # the same training loop with the reference's OWN default network (train.py:30-32: 80 x 80 x 80, every shipped checkpoint but
-        # one): tcgen05 forward, generic fp32 gradient kernel (csrc/ppo_update_generic.cu); 2 Ki envs/GPU keep the leg short
+        # one): tcgen05 forward and tcgen05 gradient kernel (csrc/ppo_update_tc.cu templated on width and depth), same batch as above
         try:
-            ne, Tp = 1 << 11, 400
+            ne, Tp = 1 << 14, 400
             env4 = RevoltFinal(StandInHull(), extended_state=True, cont_ang=True, num_envs=ne, device=dev, seed=6,
                                auto_reset=True, env_id_offset=rank * ne)
             ac4 = M.ActorCritic(9, 7, (80, 80, 80), "leaky_relu", device=dev, seed=6)
@@ -731,8 +731,8 @@ def run_b200(args, rank, local_rank, world):
             dt = max_over_ranks(sorted(b - a for a, b in zip(marks[1:-1], marks[2:]))[0])
             hist = hist[2:]
             passes = sum(h["StopIter"] + 1 + 80 + 2 for h in hist) / float(len(hist))
-            extra["ppo_train_80x3"] = {"workload": "PPO epoch with the reference's default 80 x 80 x 80 network, 2 Ki envs/GPU x 400 steps "
-                                                   "(generic fp32 gradient kernel)",
+            extra["ppo_train_80x3"] = {"workload": "PPO epoch with the reference's default 80 x 80 x 80 network, 16 Ki envs/GPU x 400 steps "
+                                                   "(tcgen05 forward and gradient kernels, one tile group per CTA at this width)",
                                        "value": ne * world * Tp / dt, "unit": "env-steps/s incl. update", "s_per_epoch": dt,
                                        "gradient_passes_per_epoch": passes, "sample_passes_per_s": passes * ne * world * Tp / dt}
             del env4, ac4
