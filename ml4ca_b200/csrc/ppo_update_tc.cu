@@ -56,7 +56,12 @@ struct Shape {
   static constexpr int H = H_, NL = NL_, KP = H_ + 16;
   // tile groups per CTA: 3 x 64 KB (64 x 64), 2 x 84 KB (64^3), 1 x 100 KB (80^3)
   static constexpr int G = (H_ == 64 && NL_ == 2) ? 3 : ((H_ == 80 && NL_ == 3) ? 1 : 2);
-  static constexpr int THREADS = G * 128;
+  // threads per sample row: with a single group nothing overlaps its epilogues, so two threads share a row (two warps may read
+  // the same TMEM lane quadrant: warp w reaches lanes 32 (w % 4) ..) and each converts half of the accumulator columns
+  static constexpr int SPLIT = (G == 1) ? 2 : 1;
+  static constexpr int C_SPLIT = (H_ == 80) ? 48 : H_ / 2;     // columns [0, C_SPLIT) to the first thread of a row (multiple of 16)
+  static constexpr int GT = 128 * SPLIT;                        // threads of a group
+  static constexpr int THREADS = G * GT;
   // ---- shared memory: per group A0 | A_1 .. A_NL (activations entering layers 2 .. NL and the output layer) | G_out | G_hidden
   static constexpr int A0_B = TS * 16 * 2, AH_B = TS * KP * 2, GO_B = TS * 16 * 2, GH_B = TS * H * 2;
   static constexpr int GROUP_B = A0_B + NL * AH_B + GO_B + GH_B;
@@ -162,7 +167,10 @@ __global__ void __launch_bounds__((Shape<H, NL>::THREADS), 1) ppo_grad_tc_kernel
   // warp index through a shuffle: warp-uniform for the compiler, so the group index and every MMA descriptor derived from it
   // live in uniform registers (tcgen05.mma then issues back to back, without a per-thread waterfall loop)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int g = warp >> 2, row = (warp & 3) * 32 + lane;
+  constexpr int SPLIT = S::SPLIT, GT = S::GT;
+  const int g = warp / (4 * SPLIT), wg = warp % (4 * SPLIT);   // group, warp within the group
+  const int half = wg >> 2, row = (wg & 3) * 32 + lane;        // which half of the columns (SPLIT = 2), sample row = TMEM lane
+  const int c_lo = (SPLIT == 2 && half == 1) ? S::C_SPLIT : 0, c_hi = (SPLIT == 2 && half == 0) ? S::C_SPLIT : H;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
   float* consts = reinterpret_cast<float*>(smem + OFF_CONST);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
@@ -222,7 +230,7 @@ __global__ void __launch_bounds__((Shape<H, NL>::THREADS), 1) ppo_grad_tc_kernel
   // accumulators: D, dW_l (l = 2 .. NL), dWo, dW1T
   const uint32_t tD = tmem_base + g * S::TMEM_G, tWo = tD + NL * H, tW1 = tWo + 16;
   auto tW = [&](int l) { return tD + (uint32_t)(l - 1) * H; };
-  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t lane_off = (uint32_t)((wg & 3) * 32) << 16;
 
   // MMA chains (one elected thread per group).  K-major operand: lbo = 128 B, sbo = K_total * 16 B, +256 B per k-step.
   // MN-major view of a buffer with K_total columns: lbo = K_total * 16 B, sbo = 128 B, + 2 lbo per k-step (16 samples).
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__((Shape<H, NL>::THREADS), 1) ppo_grad_tc_kernel
   uint32_t phase = 0;
   auto sync_group = [&]() {
     fence_async_smem();
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(GT) : "memory");
   };
   auto wait_mma = [&]() {
     mbar_wait(&bars[g], phase);
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__((Shape<H, NL>::THREADS), 1) ppo_grad_tc_kernel
   float pf_o[kPreObs], pf_a[8], pf_adv = 0.f, pf_lpo = 0.f, pf_ret = 0.f;
   auto fetch = [&](int64_t tl) {
     const int64_t smp = tl * TS + row;
-    const bool live = smp < total;
+    const bool live = smp < total && half == 0;      // the second thread of a row takes no part in the inputs or the loss
     int64_t t = 0, i = 0;
     if (live) split_sample(smp, n, t, i);
 #pragma unroll
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__((Shape<H, NL>::THREADS), 1) ppo_grad_tc_kernel
   bool first_tile = true;
   for (int64_t tile = (int64_t)blockIdx.x * G + g; tile < num_tiles; tile += (int64_t)gridDim.x * G) {
     const int64_t smp = tile * TS + row;
-    const bool live = smp < total;
+    const bool live = smp < total && half == 0;
     int64_t t = 0, i = 0;
     if (live) split_sample(smp, n, t, i);
     // ---- inputs: thread = sample.  Requested one tile ahead (below, after the first hand-over), so their HBM latency is
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__((Shape<H, NL>::THREADS), 1) ppo_grad_tc_kernel
       wait_mma();
       pending = false;
     }
-    {
+    if (half == 0) {
       uint32_t w[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) w[c] = pack_f16x2(o[2 * c], o[2 * c + 1]);
@@ -311,10 +319,10 @@ __global__ void __launch_bounds__((Shape<H, NL>::THREADS), 1) ppo_grad_tc_kernel
       *reinterpret_cast<uint4*>(pA0 + canon(row, 8, 16)) = make_uint4(w[4], w[5], w[6], w[7]);
     }
     sync_group();
-    if ((warp & 3) < 2) {                                          // warp-uniform: the two issuing warps of the group
+    if (wg < 2) {                                                  // warp-uniform: the two issuing warps of the group
       if (elect_one()) {
         fence_after_sync();
-        if ((warp & 3) == 0) {
+        if (wg == 0) {
           chain_k(tD, sA0, 16, sB1, 16, H, 1, false);              // F1
         }
         mma_commit(&bars[g]);
@@ -328,6 +336,7 @@ __global__ void __launch_bounds__((Shape<H, NL>::THREADS), 1) ppo_grad_tc_kernel
       uint32_t buf[16];
 #pragma unroll
       for (int c0 = 0; c0 < H; c0 += 16) {
+        if (c0 < c_lo || c0 >= c_hi) continue;         // this thread's share of the row (warp-uniform)
         tmem_ld16_async(tD + lane_off + c0, buf);
         wait_ld();
 #pragma unroll
@@ -343,10 +352,10 @@ __global__ void __launch_bounds__((Shape<H, NL>::THREADS), 1) ppo_grad_tc_kernel
       sync_group();
     };
 #define ML4CA_ISSUE2(W0, W1)                                                                                      \
-  if ((warp & 3) < 2) { /* warp-uniform: the two issuing warps of the group */                                     \
+  if (wg < 2) { /* warp-uniform: the two issuing warps of the group */                                             \
     if (elect_one()) {                                                                                            \
       fence_after_sync();                                                                                         \
-      if ((warp & 3) == 0) {                                                                                      \
+      if (wg == 0) {                                                                                              \
         W0;                                                                                                       \
       } else {                                                                                                    \
         W1;                                                                                                       \
@@ -424,7 +433,7 @@ __global__ void __launch_bounds__((Shape<H, NL>::THREADS), 1) ppo_grad_tc_kernel
       dout[0] = live ? 2.0f * e : 0.f;
       if (live) st[1] += (double)e * (double)e;
     }
-    {
+    if (half == 0) {
       uint32_t w[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) w[k] = pack_f16x2(dout[2 * k] * kScale, dout[2 * k + 1] * kScale);
@@ -440,6 +449,7 @@ __global__ void __launch_bounds__((Shape<H, NL>::THREADS), 1) ppo_grad_tc_kernel
       uint32_t buf[16];
 #pragma unroll
       for (int c0 = 0; c0 < H; c0 += 16) {
+        if (c0 < c_lo || c0 >= c_hi) continue;         // this thread's share of the row (warp-uniform)
         tmem_ld16_async(tD + lane_off + c0, buf);
         const uint4 h0 = *reinterpret_cast<const uint4*>(hsrc + (size_t)canon(row, c0, KP) * 2);
         const uint4 h1 = *reinterpret_cast<const uint4*>(hsrc + (size_t)canon(row, c0 + 8, KP) * 2);
@@ -481,6 +491,7 @@ __global__ void __launch_bounds__((Shape<H, NL>::THREADS), 1) ppo_grad_tc_kernel
     for (int l = 2; l <= NL; ++l) {
 #pragma unroll
       for (int c0 = 0; c0 < H; c0 += 16) {             // dW_l rows k = 0 .. H - 1, row H = bias b_l
+        if (c0 < c_lo || c0 >= c_hi) continue;
         tmem_ld16(tW(l) + lane_off + c0, v);
         if (row <= H) {
 #pragma unroll
@@ -490,13 +501,13 @@ __global__ void __launch_bounds__((Shape<H, NL>::THREADS), 1) ppo_grad_tc_kernel
       }
     }
     tmem_ld16(tWo + lane_off, v);
-    if (row <= H) {
+    if (row <= H && half == 0) {
 #pragma unroll
       for (int o = 0; o < 8; ++o)
         if (o < nout) atomicAdd(gr + (row < H ? A.off_w[NL] + row * nout : A.off_b[NL]) + o, v[o] * unscale);
     }
     tmem_ld16(tW1 + lane_off, v);        // dW1T: lane = hidden unit j, column = input k (k = obs: bias b1)
-    if (row < H) {
+    if (row < H && half == SPLIT - 1) {
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         if (k < obs) atomicAdd(gr + A.off_w[0] + k * H + row, v[k] * unscale);
