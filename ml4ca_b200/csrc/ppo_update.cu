@@ -608,8 +608,9 @@ static int ppo_args(ml4ca_policy* p, int32_t net, int64_t n, int32_t T, const ch
   if (rc != ML4CA_OK) return rc;
   *cfg_out = cfg, *device_out = device;
   if (!(cfg.hidden == 64 && cfg.n_hidden == 2 && cfg.obs_dim <= ppo::XR)) {
-    // not the 64 x 64 config the specialised kernels are built for: the caller takes the generic fp32 kernel
-    // (ppo_update_generic.cu: any width <= 96, 1..3 hidden layers -- the reference's 80^3 and 64^3 networks)
+    // not the 64 x 64 config ppo::Args describes: the caller takes the tensor-core kernel of that shape (ppo_update_tc.cu:
+    // the reference's 80^3 and 64^3 networks) or the generic fp32 kernel (ppo_update_generic.cu: any width <= 96, 1..3 hidden
+    // layers; fp32 mode and every other shape)
     if (cfg.hidden > 96 || cfg.n_hidden < 1 || cfg.n_hidden > 3 || cfg.obs_dim > 15) {
       set_error("%s: training kernels exist for hidden widths <= 96 and 1..3 hidden layers", who);
       return ML4CA_ERR_UNSUPPORTED;

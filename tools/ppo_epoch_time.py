@@ -18,7 +18,7 @@ for hidden in ((64, 64), (80, 80, 80)):
                 marks.append(time.perf_counter())
             epochs = 6 if ne > 100 or hidden == (64, 64) else 5
             if hidden == (80, 80, 80) and ne > 100:
-                epochs = 3          # generic fp32 kernel: ~6.5 M samples x 160 passes per epoch
+                epochs = 4
             _, hist = M.ppo(env, steps_per_epoch=400, epochs=epochs, seed=5, graph=True, update_graph=upd_graph, hidden_sizes=hidden,
                             logger=mark)
             dts = sorted(b - a for a, b in zip(marks[1:], marks[2:])) or [float("nan")]

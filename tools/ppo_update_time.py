@@ -1,6 +1,6 @@
 """Device time of one graph-replayed PPO update (80 + 80 iterations) under torchrun: the gradient exchange over NVLink peer memory
 (default) against NCCL (ML4CA_PEER_COMM=0), at the bench batch (16 Ki envs x 400 steps per rank) and the reference's (4 x 400).
-HIDDEN=80,80,80 times the reference's own network (generic fp32 gradient kernel) instead of the 64 x 64 of the bench config."""
+HIDDEN=80,80,80 times the reference's own network instead of the 64 x 64 of the bench config (ML4CA_PPO_FP32=1: the fp32 kernels)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist

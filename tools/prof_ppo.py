@@ -1,4 +1,4 @@
-"""Driver of the K6 ncu captures: three gradient passes of the pi-net over 1 Mi samples (HIDDEN=80,80,80 selects the generic fp32 kernel)."""
+"""Driver of the K6 ncu captures: three gradient passes of the pi-net over 1 Mi samples (HIDDEN=80,80,80: the reference's default network; ML4CA_PPO_FP32=1 selects the fp32 kernels)."""
 import os, sys
 sys.path.insert(0, '.')
 import torch
