@@ -55,10 +55,19 @@ template <int H_, int NL_>
 struct Shape {
   static constexpr int H = H_, NL = NL_, KP = H_ + 16;
   // tile groups per CTA: 3 x 64 KB (64 x 64), 2 x 84 KB (64^3), 1 x 100 KB (80^3)
-  static constexpr int G = (H_ == 64 && NL_ == 2) ? 3 : ((H_ == 80 && NL_ == 3) ? 1 : 2);
+#ifndef ML4CA_TC_G64X2
+#define ML4CA_TC_G64X2 3     // tuning knobs (tools/kernel_variants.sh): groups / threads per row of the 64 x 64 and 64^3 shapes
+#endif
+#ifndef ML4CA_TC_SPLIT64X2
+#define ML4CA_TC_SPLIT64X2 1
+#endif
+#ifndef ML4CA_TC_SPLIT64X3
+#define ML4CA_TC_SPLIT64X3 1
+#endif
+  static constexpr int G = (H_ == 64 && NL_ == 2) ? ML4CA_TC_G64X2 : ((H_ == 80 && NL_ == 3) ? 1 : 2);
   // threads per sample row: with a single group nothing overlaps its epilogues, so two threads share a row (two warps may read
   // the same TMEM lane quadrant: warp w reaches lanes 32 (w % 4) ..) and each converts half of the accumulator columns
-  static constexpr int SPLIT = (G == 1) ? 2 : 1;
+  static constexpr int SPLIT = (G == 1) ? 2 : ((H_ == 64 && NL_ == 2) ? ML4CA_TC_SPLIT64X2 : ML4CA_TC_SPLIT64X3);
   static constexpr int C_SPLIT = (H_ == 80) ? 48 : H_ / 2;     // columns [0, C_SPLIT) to the first thread of a row (multiple of 16)
   static constexpr int GT = 128 * SPLIT;                        // threads of a group
   static constexpr int THREADS = G * GT;
