@@ -89,7 +89,9 @@ def test_gradients_of_the_reference_network_shapes(cuda_device, precision, hidde
     flat = MO.glorot_params(dims, seed=11)
     flat = (flat + np.random.default_rng(2).normal(size=flat.size).astype(np.float32) * 0.05).astype(np.float32)
     ac = M.ActorCritic(9, 7, hidden, activation, params=flat, device=cuda_device)
-    for T, n in ((4, 400), (3, 1037)):
+    # (80^3 has two tensor-core variants, picked by the batch size: one tile group with two threads per row up to two waves of
+    # tiles, two groups on shared weight-gradient accumulators beyond -- the 80 000-sample case)
+    for T, n in ((4, 400), (3, 1037)) + (((2, 40000),) if hidden == (80, 80, 80) else ()):
         # tensor cores: the fp16 rounding of the operands enters once per layer, so the 3e-3 of the two-layer config scales with the depth
         gtol, stol = (2e-4, 1e-5) if precision == "fp32" else (3e-3 * len(hidden) / 2.0 + 0.5 / np.sqrt(T * n), 3e-2)
         if precision == "tensor_core" and activation == "tanh":

@@ -181,9 +181,9 @@ def test_tensor_core_kernel_option_for_the_shipped_architecture(cuda_device):
     """kernel='tensor_core' with the reference's default 80 x 80 x 80 network: the KL-gradient passes run on the tcgen05 kernel
     templated on width and depth (csrc/ppo_update_tc.cu); the check is the generic fp32 kernel on the same buffer (the float64
     TRPO restatement covers two hidden layers): means within the fp16 tolerance, Hessian-vector product within 2 %, and a
-    whole TRPO update inside the KL budget that improves the surrogate."""
+    whole TRPO update inside the KL budget that improves the surrogate.  65 536 samples: the two-group variant of the kernel."""
     import ml4ca_b200 as M
-    T, n = 4, 8192
+    T, n = 4, 16384
     rng = np.random.default_rng(3)
     dims = dict(obs_dim=9, act_dim=7, hidden=80, n_hidden=3)
     flat = MO.glorot_params(dims, seed=5)
