@@ -71,8 +71,11 @@ struct Shape {
   //  * both groups accumulate into ONE set of weight-gradient accumulators (TMEM: 2 x 80 + 192 columns).  MMAs into the same
   //    accumulator must not be in flight from two issuing threads at once: a weight-gradient chain is issued under a CTA-wide
   //    lock (shared-memory word) that its group releases when the chain has completed (the wait every stage ends with).
-  static constexpr bool SHARED = (H_ == 80 && NL_ == 3 && SH_);
-  static constexpr int G = (H_ == 64 && NL_ == 2) ? ML4CA_TC_G64X2 : ((H_ == 80 && NL_ == 3) ? (SHARED ? 2 : 1) : 2);
+  static constexpr bool SHARED = SH_ && ((H_ == 80 && NL_ == 3) || (H_ == 64 && NL_ == 2));
+#ifndef ML4CA_TC_G64X2_SHARED
+#define ML4CA_TC_G64X2_SHARED 4
+#endif
+  static constexpr int G = (H_ == 64 && NL_ == 2) ? (SHARED ? ML4CA_TC_G64X2_SHARED : ML4CA_TC_G64X2) : ((H_ == 80 && NL_ == 3) ? (SHARED ? 2 : 1) : 2);
   // threads per sample row: with a single group nothing overlaps its epilogues, so two threads share a row (two warps may read
   // the same TMEM lane quadrant: warp w reaches lanes 32 (w % 4) ..) and each converts half of the accumulator columns
   static constexpr int SPLIT = (G == 1) ? 2 : ((H_ == 64 && NL_ == 2) ? ML4CA_TC_SPLIT64X2 : ML4CA_TC_SPLIT64X3);
@@ -650,8 +653,14 @@ bool ml4ca_ppo_tc_supports(int hidden, int n_hidden, int obs, int act) {
 
 int ml4ca_ppo_grad_tc_launch(const ppotc::Args& args, int activation, int net, void* blob, cudaStream_t st) {
   ML4CA_REQUIRE(ml4ca_ppo_tc_supports(args.hidden, args.n_hidden, args.obs, args.act), "shape not built for the tensor-core gradient kernel");
+#ifndef ML4CA_TC_SHARED64X2
+#define ML4CA_TC_SHARED64X2 0
+#endif
+  const int64_t tiles64 = (args.n * (int64_t)args.T + ppotc::TS - 1) / ppotc::TS;
   if (args.hidden == 64) {
-    return args.n_hidden == 2 ? launch_shape<64, 2>(args, activation, net, blob, st) : launch_shape<64, 3>(args, activation, net, blob, st);
+    if (args.n_hidden == 3) return launch_shape<64, 3>(args, activation, net, blob, st);
+    if (ML4CA_TC_SHARED64X2 && tiles64 > 2 * kNumSMs) return launch_shape<64, 2, true>(args, activation, net, blob, st);
+    return launch_shape<64, 2>(args, activation, net, blob, st);
   }
   // 80^3: the two-group kernel on shared accumulators streams large batches 1.4 x faster (5.1 against 3.65 G sample-passes/s), the
   // single-group kernel with two threads per row has the shorter launch (31 against 53 us for one wave of tiles: the reference's
