@@ -302,9 +302,7 @@ __global__ void __launch_bounds__((Shape<H, NL, SH>::THREADS), 1) ppo_grad_tc_ke
       }
       __threadfence_block();
       fence_after_sync();
-      const bool was = lock[1 + a] != 0;
-      lock[1 + a] = 1;
-      return was;
+      return atomicExch(&lock[1 + a], 1) != 0;
     }
   };
 
