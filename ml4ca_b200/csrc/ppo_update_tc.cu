@@ -5,8 +5,8 @@
 // parameters H, NL): 64 x 64 (the BASELINE config), and the reference's own 80 x 80 x 80 (train.py:30-32) and 64 x 64 x 64.
 // The text below spells out the 64 x 64 case; a deeper net repeats the hidden stage (one more forward GEMM, one more
 // weight-gradient accumulator, one more backward-data GEMM per layer), a wider one has KP = H + 16 = 96 operand columns.
-// All GEMMs of a 128-sample tile (seven for two hidden layers, ten for three) run as tcgen05.mma (fp16 operands in shared memory, fp32 accumulation in
-// tensor memory); the CUDA cores only do the activation / loss epilogues:
+// All GEMMs of a 128-sample tile (seven for two hidden layers, ten for three) run as tcgen05.mma (fp16 operands in shared
+// memory, fp32 accumulation in tensor memory); the CUDA cores only do the activation / loss epilogues:
 //
 //   forward      D = A0 B1^T          [128 x 16] x [64 x 16]^T      A0 = obs, 1 (bias column), pad
 //                D = A1 B2^T          [128 x 80] x [64 x 80]^T      A1 = f(D), 1, pad
@@ -27,13 +27,16 @@
 //
 // Bias gradients fall out of the constant-1 columns (row H of dWo / dW2, column obs of dW1T).  Weight-gradient
 // accumulators stay in TMEM for all tiles of the CTA (persistent grid) and are flushed once.  Tile groups of 128 threads
-// (thread = sample = TMEM lane; three for 64 x 64, two for 64^3, one for 80^3: shared memory -- 100 KB of
-// operand buffers per group at 80^3 -- and the 512 TMEM columns decide) run out of phase; an elected lane of the first two warps of a group issues its
-// MMA chains (independent chains of a stage go to different issuers: one thread's MMAs run strictly one after the other).
+// (thread = sample = TMEM lane) run out of phase; an elected lane of the first two warps of a group issues its MMA chains
+// (independent chains of a stage go to different issuers: one thread's MMAs run strictly one after the other).  Groups per
+// CTA: three for 64 x 64, two for 64^3; 80^3 has two variants picked by the batch size (struct Shape below): two groups that
+// share one set of weight-gradient accumulators (large batches: 5.1 G sample-passes/s), or one group with two threads per
+// sample row (up to two waves of tiles: the shorter launch).  Measurements and dead ends: profiles/ppo_grad_r2.md.
 //
 // Numerics: fp16 operands (activations, weights, back-propagated signals x 64), fp32 accumulation: gradients agree
-// with the float64 oracle to ~1e-3 of the largest component (tests/test_ppo_update_gpu.py); the fp32 CUDA-core
-// kernel of ppo_update.cu remains available (ML4CA_PPO_FP32=1) where 1e-5 is wanted.
+// with the float64 oracle to ~1e-3 of the largest component for two hidden layers, 4.5e-3 stated for three (the rounding
+// enters once per layer; tests/test_ppo_update_gpu.py); the fp32 CUDA-core kernels (ppo_update.cu for 64 x 64,
+// ppo_update_generic.cu for every other shape) remain available (ML4CA_PPO_FP32=1) where 1e-4 .. 1e-5 is wanted.
 #include <stdlib.h>
 
 #include <cuda_fp16.h>
@@ -51,11 +54,12 @@ constexpr int TS = 128, OP = 16;
 constexpr float kScale = 64.0f;            // loss scaling of the back-propagated signals (fp16 range)
 
 // Sizes, shared-memory plan and tensor-memory plan of one network shape (H hidden units, NL hidden layers).
-// SH: the 80^3 variant with two tile groups on shared accumulators (large batches); false: its single-group variant (one wave of tiles)
+// SH: the variant with tile groups on SHARED weight-gradient accumulators (80^3, large batches; also built for 64 x 64 as a
+// measured-and-rejected experiment); false: every group owns its accumulators
 template <int H_, int NL_, bool SH_ = false>
 struct Shape {
   static constexpr int H = H_, NL = NL_, KP = H_ + 16;
-  // tile groups per CTA: 3 x 64 KB (64 x 64), 2 x 84 KB (64^3), 1 x 100 KB (80^3)
+  // tile groups per CTA: 3 x 64 KB (64 x 64), 2 x 84 KB (64^3), 1 x 100 KB or -- SHARED -- 2 x 80 KB (80^3)
 #ifndef ML4CA_TC_G64X2
 #define ML4CA_TC_G64X2 3     // tuning knobs (tools/kernel_variants.sh): groups / threads per row of the 64 x 64 and 64^3 shapes
 #endif
