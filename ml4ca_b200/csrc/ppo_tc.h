@@ -34,7 +34,7 @@ constexpr int kBlobHalves = 80 * 16 + 2 * 80 * 96 + 16 * 96 + 80 * 16 + 2 * 80 *
 }  // namespace ppotc
 }  // namespace ml4ca
 
-// Shapes the tensor-core kernel is built for (obs / act dims other than 9 / 7 only with 64 x 64).
+// Shapes the tensor-core kernel is built for (64 x 64, 64^3, 80^3; obs_dim <= 15, act_dim <= 8).
 bool ml4ca_ppo_tc_supports(int hidden, int n_hidden, int obs, int act);
 // Packs the operands into `blob` (>= kBlobHalves halves of device scratch) and launches the kernel.
 int ml4ca_ppo_grad_tc_launch(const ml4ca::ppotc::Args& args, int activation, int net, void* blob, cudaStream_t st);

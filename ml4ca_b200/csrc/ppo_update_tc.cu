@@ -629,13 +629,12 @@ static int launch_shape(const ppotc::Args& args, int activation, int net, void* 
   const int64_t tiles = (a.n * (int64_t)a.T + ppotc::TS - 1) / ppotc::TS;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   const bool s97 = a.obs == 9 && a.act == 7;
-  // the 9 -> 7 dims are compiled in for every shape; other dims exist for the 64 x 64 config only (ml4ca_ppo_tc_supports)
+  // the 9 -> 7 dims of RevoltFinal(extended_state, cont_ang) are compiled in; the other env classes (RevoltLimited: 5 actions,
+  // RevoltSimple: 3, no extended state: 6 observations ...) take the instantiation with run-time dims
 #define ML4CA_TC_LAUNCH(ACTV, NETV)                                                                                      \
   do {                                                                                                                   \
-    auto k = ppotc::ppo_grad_tc_kernel<ACTV, NETV, true, H, NL, SH>;                                                         \
-    if constexpr (H == 64 && NL == 2) {                                                                                  \
-      if (!s97) k = ppotc::ppo_grad_tc_kernel<ACTV, NETV, false, H, NL, SH>;                                                 \
-    }                                                                                                                    \
+    auto k = ppotc::ppo_grad_tc_kernel<ACTV, NETV, true, H, NL, SH>;                                                     \
+    if (!s97) k = ppotc::ppo_grad_tc_kernel<ACTV, NETV, false, H, NL, SH>;                                               \
     ML4CA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));                     \
     k<<<grid, S::THREADS, S::SMEM_BYTES, st>>>(a);                                                                       \
   } while (0)
@@ -649,8 +648,8 @@ static int launch_shape(const ppotc::Args& args, int activation, int net, void* 
 }
 
 bool ml4ca_ppo_tc_supports(int hidden, int n_hidden, int obs, int act) {
-  if (hidden == 64 && n_hidden == 2) return obs <= 15 && act <= 8;
-  return (hidden == 64 || hidden == 80) && n_hidden == 3 && obs == 9 && act == 7;     // the shapes policy.cu runs forward
+  const bool shape = (hidden == 64 && (n_hidden == 2 || n_hidden == 3)) || (hidden == 80 && n_hidden == 3);   // what policy.cu runs forward
+  return shape && obs >= 1 && obs <= 15 && act >= 1 && act <= 8;
 }
 
 int ml4ca_ppo_grad_tc_launch(const ppotc::Args& args, int activation, int net, void* blob, cudaStream_t st) {
